@@ -1,0 +1,197 @@
+// Feature / label extraction kernels.
+//
+// fgnn_k_row_copy      : dst[dst_index?[i]] = src[src_index?[i] & mask]
+//                        (GPUExtract cuda_extraction.cu:31-49, combine_miss_data /
+//                        combine_cache_data dist_cache_manager_device.cu:37-82,
+//                        extract_miss_data dist_cache_manager_host.cc:38-56 when
+//                        `src` is pinned host memory read through UVA)
+// fgnn_k_gather_cached : the reference's five-step trainer-side extraction
+//                        (dist_loops.cc:713-846) as one kernel; cache shards may
+//                        live on NVLink peers.
+//
+// The reference maps one thread to one 4-byte column element.  Here rows are
+// cut into 16-byte chunks (or the widest power of two that divides the row and
+// the base alignment) and chunks are spread flat over a persistent grid, four
+// independent 16-byte loads in flight per thread, streaming cache hints on both
+// sides (rows are touched once per batch).
+#include "common.cuh"
+
+namespace fgnn {
+namespace {
+
+template <typename V> struct VecIO;
+template <> struct VecIO<uint4> {
+  static __device__ __forceinline__ uint4 ld(const void *p) { return ld_nc_na_v4(p); }
+  static __device__ __forceinline__ void st(void *p, const uint4 &v) { st_na_v4(p, v); }
+};
+template <> struct VecIO<uint2> {
+  static __device__ __forceinline__ uint2 ld(const void *p) { return __ldg((const uint2 *)p); }
+  static __device__ __forceinline__ void st(void *p, const uint2 &v) { *(uint2 *)p = v; }
+};
+template <> struct VecIO<uint32_t> {
+  static __device__ __forceinline__ uint32_t ld(const void *p) { return __ldg((const uint32_t *)p); }
+  static __device__ __forceinline__ void st(void *p, const uint32_t &v) { *(uint32_t *)p = v; }
+};
+template <> struct VecIO<uint8_t> {
+  static __device__ __forceinline__ uint8_t ld(const void *p) { return __ldg((const uint8_t *)p); }
+  static __device__ __forceinline__ void st(void *p, const uint8_t &v) { *(uint8_t *)p = v; }
+};
+
+constexpr int kUnroll = 4;
+
+template <typename V>
+__global__ void __launch_bounds__(kBlock)
+row_copy_kernel(char *__restrict__ dst, const uint32_t *__restrict__ dst_index,
+                const char *__restrict__ src, const uint32_t *__restrict__ src_index,
+                uint64_t src_mask, uint32_t n_max, const uint32_t *__restrict__ d_n,
+                size_t row_bytes, uint32_t cpr /* chunks per row */) {
+  const uint32_t n = load_count(n_max, d_n);
+  const uint64_t total = (uint64_t)n * cpr;
+  const uint64_t stride = (uint64_t)gridDim.x * kBlock;
+  for (uint64_t c0 = (uint64_t)blockIdx.x * kBlock + threadIdx.x; c0 < total;
+       c0 += stride * kUnroll) {
+    V v[kUnroll];
+    char *dp[kUnroll];
+#pragma unroll
+    for (int u = 0; u < kUnroll; ++u) {
+      const uint64_t c = c0 + u * stride;
+      dp[u] = nullptr;
+      if (c < total) {
+        const uint32_t row = (uint32_t)(c / cpr);
+        const uint32_t col = (uint32_t)(c - (uint64_t)row * cpr);
+        const uint64_t s = src_index ? ((uint64_t)__ldg(src_index + row) & src_mask) : row;
+        const uint64_t d = dst_index ? (uint64_t)__ldg(dst_index + row) : row;
+        v[u] = VecIO<V>::ld(src + s * row_bytes + (size_t)col * sizeof(V));
+        dp[u] = dst + d * row_bytes + (size_t)col * sizeof(V);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < kUnroll; ++u)
+      if (dp[u]) VecIO<V>::st(dp[u], v[u]);
+  }
+}
+
+template <typename V>
+__global__ void __launch_bounds__(kBlock)
+gather_cached_kernel(char *__restrict__ out, const uint32_t *__restrict__ nodes, uint32_t n_max,
+                     const uint32_t *__restrict__ d_n, const uint32_t *__restrict__ table,
+                     const void *const *__restrict__ shards, uint32_t num_shards,
+                     const char *__restrict__ miss_src, uint64_t miss_mask, size_t row_bytes,
+                     uint32_t cpr, unsigned long long *d_stats) {
+  const uint32_t n = load_count(n_max, d_n);
+  const uint64_t total = (uint64_t)n * cpr;
+  const uint64_t stride = (uint64_t)gridDim.x * kBlock;
+  const char *shard0 = (const char *)__ldg((const unsigned long long *)shards);
+  uint32_t hits = 0, misses = 0;
+  for (uint64_t c0 = (uint64_t)blockIdx.x * kBlock + threadIdx.x; c0 < total;
+       c0 += stride * kUnroll) {
+    V v[kUnroll];
+    char *dp[kUnroll];
+#pragma unroll
+    for (int u = 0; u < kUnroll; ++u) {
+      const uint64_t c = c0 + u * stride;
+      dp[u] = nullptr;
+      if (c < total) {
+        const uint32_t row = (uint32_t)(c / cpr);
+        const uint32_t col = (uint32_t)(c - (uint64_t)row * cpr);
+        const uint32_t node = __ldg(nodes + row);
+        const uint32_t slot = __ldg(table + node);
+        const char *sp;
+        if (slot != kEmpty) {
+          if (num_shards == 1) {
+            sp = shard0 + (size_t)slot * row_bytes;
+          } else {  // striped: owner = slot mod T, local row = slot div T
+            const uint32_t owner = slot % num_shards;
+            const uint32_t lrow = slot / num_shards;
+            sp = (const char *)__ldg((const unsigned long long *)shards + owner) +
+                 (size_t)lrow * row_bytes;
+          }
+          hits += (col == 0);
+        } else {
+          sp = miss_src + ((uint64_t)node & miss_mask) * row_bytes;
+          misses += (col == 0);
+        }
+        v[u] = VecIO<V>::ld(sp + (size_t)col * sizeof(V));
+        dp[u] = out + (size_t)row * row_bytes + (size_t)col * sizeof(V);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < kUnroll; ++u)
+      if (dp[u]) VecIO<V>::st(dp[u], v[u]);
+  }
+  if (d_stats) {
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) {
+      hits += __shfl_down_sync(0xFFFFFFFFu, hits, d);
+      misses += __shfl_down_sync(0xFFFFFFFFu, misses, d);
+    }
+    if ((threadIdx.x & 31) == 0) {
+      if (hits) atomicAdd(d_stats + 0, (unsigned long long)hits);
+      if (misses) atomicAdd(d_stats + 1, (unsigned long long)misses);
+    }
+  }
+}
+
+inline int vec_width(size_t row_bytes, const void *a, const void *b, const void *c = nullptr) {
+  const uintptr_t bits = (uintptr_t)row_bytes | (uintptr_t)a | (uintptr_t)b | (uintptr_t)c;
+  if ((bits & 15) == 0) return 16;
+  if ((bits & 7) == 0) return 8;
+  if ((bits & 3) == 0) return 4;
+  return 1;
+}
+
+inline int copy_grid(uint64_t chunks) {
+  // 8 resident CTAs/SM x 4 chunks in flight per thread
+  return persistent_grid(chunks, kBlock * kUnroll, 8, false);
+}
+
+}  // namespace
+}  // namespace fgnn
+
+using namespace fgnn;
+
+extern "C" int fgnn_k_row_copy(void *dst, const uint32_t *dst_index, const void *src,
+                               const uint32_t *src_index, uint64_t src_mask, uint32_t n_max,
+                               const uint32_t *d_n, size_t row_bytes, fgnn_stream_t stream) {
+  if (n_max == 0 || row_bytes == 0) return 0;
+  if (!dst || !src) return FGNN_ERR_BAD_ARG;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int w = vec_width(row_bytes, dst, src);
+  const uint32_t cpr = (uint32_t)(row_bytes / w);
+  const int grid = copy_grid((uint64_t)n_max * cpr);
+#define FGNN_RC(V)                                                                              \
+  row_copy_kernel<V><<<grid, kBlock, 0, st>>>((char *)dst, dst_index, (const char *)src,        \
+                                              src_index, src_mask, n_max, d_n, row_bytes, cpr)
+  if (w == 16) FGNN_RC(uint4);
+  else if (w == 8) FGNN_RC(uint2);
+  else if (w == 4) FGNN_RC(uint32_t);
+  else FGNN_RC(uint8_t);
+#undef FGNN_RC
+  note_launch();
+  return check_last();
+}
+
+extern "C" int fgnn_k_gather_cached(void *out, const uint32_t *nodes, uint32_t n_max,
+                                    const uint32_t *d_n, const uint32_t *table,
+                                    const void *const *shards, uint32_t num_shards,
+                                    const void *miss_src, uint64_t miss_mask, size_t row_bytes,
+                                    unsigned long long *d_stats, fgnn_stream_t stream) {
+  if (n_max == 0 || row_bytes == 0) return 0;
+  if (!out || !nodes || !table || !shards || num_shards == 0 || !miss_src) return FGNN_ERR_BAD_ARG;
+  cudaStream_t st = (cudaStream_t)stream;
+  // shard bases are cudaMalloc'ed (256-B aligned); only out/miss_src/row_bytes decide
+  const int w = vec_width(row_bytes, out, miss_src);
+  const uint32_t cpr = (uint32_t)(row_bytes / w);
+  const int grid = copy_grid((uint64_t)n_max * cpr);
+#define FGNN_GC(V)                                                                               \
+  gather_cached_kernel<V><<<grid, kBlock, 0, st>>>((char *)out, nodes, n_max, d_n, table, shards, \
+                                                   num_shards, (const char *)miss_src, miss_mask, \
+                                                   row_bytes, cpr, d_stats)
+  if (w == 16) FGNN_GC(uint4);
+  else if (w == 8) FGNN_GC(uint2);
+  else if (w == 4) FGNN_GC(uint32_t);
+  else FGNN_GC(uint8_t);
+#undef FGNN_GC
+  note_launch();
+  return check_last();
+}

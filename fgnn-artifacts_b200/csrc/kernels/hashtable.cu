@@ -1,0 +1,238 @@
+// OrderedHashTable: running set of unique global ids with stable local
+// numbering (reference: cuda_hashtable.cu / cuda_hashtable.h, cuda_mapping.cu).
+//
+// B200-first layout: one 8-byte bucket {key, local} (the reference uses a
+// 16-byte {key, local, index, version} bucket), open addressing with linear
+// probing over a power-of-two table sized to stay mostly L2-resident.  The
+// "which duplicate owns the id" race of the reference (atomicCAS winner writes
+// its input index, cuda_hashtable.cu:49-61) is replaced by a deterministic
+// rule: while an id is new in this fill its `local` word holds
+// 0x80000000|min(input index) maintained with atomicMin; assigned local ids
+// (< 2^31) compare smaller, so the same atomicMin leaves ids from earlier fills
+// untouched.  Fill remembers each item's bucket position so that remapping the
+// edge list afterwards is a direct 4-byte read instead of a second probe.
+#include "common.cuh"
+
+namespace fgnn {
+namespace {
+
+struct __align__(8) Bucket {
+  uint32_t key;
+  uint32_t local;
+};
+
+constexpr uint32_t kPending = 0x80000000u;
+
+__device__ __forceinline__ uint32_t hash_id(uint32_t id, uint32_t mask) {
+  return ((id * 0x9E3779B1u) >> 7) & mask;
+}
+
+// returns bucket position holding `id` (inserting it if absent)
+__device__ __forceinline__ uint32_t insert_key(Bucket *table, uint32_t mask, uint32_t id) {
+  uint32_t pos = hash_id(id, mask);
+  while (true) {
+    const uint32_t cur = table[pos].key;
+    if (cur == id) return pos;
+    if (cur == kEmpty) {
+      const uint32_t old = atomicCAS(&table[pos].key, kEmpty, id);
+      if (old == kEmpty || old == id) return pos;
+    }
+    pos = (pos + 1) & mask;
+  }
+}
+
+__global__ void __launch_bounds__(kBlock)
+ht_fill_unique_kernel(Bucket *table, uint32_t mask, const uint32_t *__restrict__ input,
+                      uint32_t n_max, const uint32_t *__restrict__ d_n, uint32_t *n2o,
+                      uint32_t *d_num_items, int is_last_writer) {
+  const uint32_t n = load_count(n_max, d_n);
+  const uint32_t base = *d_num_items;
+  for (uint32_t i = blockIdx.x * kBlock + threadIdx.x; i < n; i += gridDim.x * kBlock) {
+    const uint32_t id = __ldg(input + i);
+    const uint32_t pos = insert_key(table, mask, id);
+    // ids are unique by contract: local = offset + index (cuda_hashtable.cu:164-170)
+    table[pos].local = base + i;
+    n2o[base + i] = id;
+  }
+  (void)is_last_writer;
+}
+
+__global__ void ht_bump_kernel(uint32_t *d_num_items, uint32_t n_max, const uint32_t *d_n) {
+  *d_num_items += load_count(n_max, d_n);
+}
+
+__global__ void __launch_bounds__(kBlock)
+ht_insert_kernel(Bucket *table, uint32_t mask, const uint32_t *__restrict__ input,
+                 uint32_t n_max, const uint32_t *__restrict__ d_n, uint32_t *__restrict__ pos_out) {
+  const uint32_t n = load_count(n_max, d_n);
+  for (uint32_t i = blockIdx.x * kBlock + threadIdx.x; i < n; i += gridDim.x * kBlock) {
+    const uint32_t id = __ldg(input + i);
+    const uint32_t pos = insert_key(table, mask, id);
+    atomicMin(&table[pos].local, kPending | i);
+    pos_out[i] = pos;
+  }
+}
+
+struct CompactSmem {
+  uint32_t warp[kBlock / 32 + 1];
+  ChainSmem chain;
+};
+
+__global__ void __launch_bounds__(kBlock)
+ht_compact_kernel(Bucket *table, const uint32_t *__restrict__ input, uint32_t n_max,
+                  const uint32_t *__restrict__ d_n, const uint32_t *__restrict__ pos,
+                  uint32_t *__restrict__ n2o, uint32_t *d_num_items, ChainWs *ws) {
+  __shared__ CompactSmem sm;
+  const uint32_t n = load_count(n_max, d_n);
+  const uint32_t p = chain_ticket(ws, &sm.chain);
+  uint32_t begin, end;
+  chunk_range(n, p, gridDim.x, kBlock, &begin, &end);
+  const uint32_t items0 = *d_num_items;  // stable: only the last ticket updates it, at the end
+
+  unsigned long long partial = 0;
+  for (uint32_t i = begin + threadIdx.x; i < end; i += kBlock)
+    partial += (table[pos[i]].local == (kPending | i)) ? 1u : 0u;
+  unsigned long long chunk_total;
+  unsigned long long base = chain_scan(ws, &sm.chain, p, partial, &chunk_total);
+
+  for (uint32_t t0 = begin; t0 < end; t0 += kBlock) {
+    const uint32_t i = t0 + threadIdx.x;
+    uint32_t flag = 0, bp = 0;
+    if (i < end) {
+      bp = pos[i];
+      flag = (table[bp].local == (kPending | i)) ? 1u : 0u;
+    }
+    uint32_t tile_total;
+    const uint32_t excl = block_excl_scan(flag, sm.warp, &tile_total);
+    if (flag) {
+      const uint32_t local = items0 + (uint32_t)base + excl;
+      table[bp].local = local;
+      n2o[local] = __ldg(input + i);
+    }
+    base += tile_total;
+  }
+  // every ticket read items0 before any can get here?  No: tickets run
+  // concurrently, so the counter is only advanced by the CTA that finishes
+  // LAST (after all others have read it).
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    // total number of new ids = base at the end of the last chunk; publish it
+    // through the chain workspace's pad word so the last finisher can add it.
+    if (p == gridDim.x - 1) ws->pad[0] = (uint32_t)base;
+  }
+  // chain_finish with the counter update folded in
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    const unsigned int prev = atomicAdd(&ws->done, 1u);
+    sm.chain.last = (prev == gridDim.x - 1) ? 1u : 0u;
+  }
+  __syncthreads();
+  if (sm.chain.last) {
+    for (uint32_t t = threadIdx.x; t < gridDim.x; t += kBlock) ws->agg[t] = 0ull;
+    if (threadIdx.x == 0) {
+      __threadfence();
+      *d_num_items = items0 + *((volatile unsigned int *)&ws->pad[0]);
+      ws->pad[0] = 0u;
+      ws->ticket = 0u;
+      ws->done = 0u;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(kBlock)
+ht_map_kernel(const Bucket *__restrict__ table, uint32_t mask, const uint32_t *__restrict__ global,
+              const uint32_t *__restrict__ pos, uint32_t n_max, const uint32_t *__restrict__ d_n,
+              uint32_t *__restrict__ out_local) {
+  const uint32_t n = load_count(n_max, d_n);
+  for (uint32_t i = blockIdx.x * kBlock + threadIdx.x; i < n; i += gridDim.x * kBlock) {
+    uint32_t local;
+    if (pos) {
+      local = table[pos[i]].local;
+    } else {
+      const uint32_t id = __ldg(global + i);
+      uint32_t b = hash_id(id, mask);
+      local = kEmpty;
+      while (true) {  // SearchForPositionO2N, cuda_hashtable.h:69-83
+        const Bucket bk = table[b];
+        if (bk.key == id) { local = bk.local; break; }
+        if (bk.key == kEmpty) break;  // absent -> EMPTY (the reference asserts)
+        b = (b + 1) & mask;
+      }
+    }
+    out_local[i] = local;
+  }
+}
+
+}  // namespace
+}  // namespace fgnn
+
+using namespace fgnn;
+
+extern "C" size_t fgnn_k_ht_capacity(size_t max_items) {
+  // power of two >= 1.5 * max_items, at least 1024 buckets
+  size_t want = max_items + (max_items >> 1) + 1;
+  size_t cap = 1024;
+  while (cap < want) cap <<= 1;
+  return cap;
+}
+
+extern "C" size_t fgnn_k_ht_bytes(size_t capacity) { return capacity * sizeof(Bucket); }
+
+extern "C" int fgnn_k_ht_reset(void *table, size_t capacity, uint32_t *d_num_items,
+                               fgnn_stream_t stream) {
+  if (!table || !d_num_items || (capacity & (capacity - 1))) return FGNN_ERR_BAD_ARG;
+  cudaError_t e = cudaMemsetAsync(table, 0xFF, capacity * sizeof(Bucket), (cudaStream_t)stream);
+  if (e != cudaSuccess) return (int)e;
+  e = cudaMemsetAsync(d_num_items, 0, sizeof(uint32_t), (cudaStream_t)stream);
+  return (int)e;
+}
+
+extern "C" int fgnn_k_ht_fill_unique(void *table, size_t capacity, const uint32_t *input,
+                                     uint32_t n_max, const uint32_t *d_n, uint32_t *n2o,
+                                     uint32_t *d_num_items, fgnn_stream_t stream) {
+  if (!table || !n2o || !d_num_items || (capacity & (capacity - 1))) return FGNN_ERR_BAD_ARG;
+  if (capacity > 0x80000000ull) return FGNN_ERR_UNSUPPORTED;
+  if (n_max == 0) return 0;
+  if (!input) return FGNN_ERR_BAD_ARG;
+  const int grid = persistent_grid(n_max, kBlock, 8, false);
+  ht_fill_unique_kernel<<<grid, kBlock, 0, (cudaStream_t)stream>>>(
+      (Bucket *)table, (uint32_t)(capacity - 1), input, n_max, d_n, n2o, d_num_items, 0);
+  ht_bump_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(d_num_items, n_max, d_n);
+  note_launch(2);
+  return check_last();
+}
+
+extern "C" int fgnn_k_ht_fill_duplicates(void *table, size_t capacity, const uint32_t *input,
+                                         uint32_t n_max, const uint32_t *d_n, uint32_t *pos,
+                                         uint32_t *n2o, uint32_t *d_num_items, void *chain_ws,
+                                         fgnn_stream_t stream) {
+  if (!table || !n2o || !d_num_items || !chain_ws || (capacity & (capacity - 1)))
+    return FGNN_ERR_BAD_ARG;
+  if (capacity > 0x80000000ull || n_max >= kPending) return FGNN_ERR_UNSUPPORTED;
+  if (n_max == 0) return 0;
+  if (!input || !pos) return FGNN_ERR_BAD_ARG;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int grid1 = persistent_grid(n_max, kBlock, 8, false);
+  ht_insert_kernel<<<grid1, kBlock, 0, st>>>((Bucket *)table, (uint32_t)(capacity - 1), input, n_max,
+                                            d_n, pos);
+  const int grid2 = persistent_grid(n_max, kBlock, 8, true);
+  ht_compact_kernel<<<grid2, kBlock, 0, st>>>((Bucket *)table, input, n_max, d_n, pos, n2o,
+                                             d_num_items, (ChainWs *)chain_ws);
+  note_launch(2);
+  return check_last();
+}
+
+extern "C" int fgnn_k_ht_map(const void *table, size_t capacity, const uint32_t *global,
+                             const uint32_t *pos, uint32_t n_max, const uint32_t *d_n,
+                             uint32_t *out_local, fgnn_stream_t stream) {
+  if (!table || !out_local || (capacity & (capacity - 1))) return FGNN_ERR_BAD_ARG;
+  if (n_max == 0) return 0;
+  if (!global && !pos) return FGNN_ERR_BAD_ARG;
+  const int grid = persistent_grid(n_max, kBlock, 8, false);
+  ht_map_kernel<<<grid, kBlock, 0, (cudaStream_t)stream>>>((const Bucket *)table,
+                                                          (uint32_t)(capacity - 1), global, pos,
+                                                          n_max, d_n, out_local);
+  note_launch();
+  return check_last();
+}

@@ -1,0 +1,252 @@
+// Uniform k-hop neighbour sampling without replacement, fused with COO
+// compaction.  Replaces sample_khop0/sample_khop2 + count_edge + DeviceScan +
+// compact_edge (reference: cuda_sampling_khop0.cu:42-253, cuda_sampling_khop2.cu:
+// 42-252) with ONE persistent launch:
+//
+//   phase 1  thread-per-seed: read (indptr[v], indptr[v+1]) -> cnt = min(deg,f)
+//            chunk aggregate -> chunk-chained scan (common.cuh) -> global base
+//   phase 2  per 256-seed tile: block scan of cnt; warp-per-seed selection of
+//            the f positions (Philox, all in registers/shared memory — no
+//            memory traffic); then an *edge-parallel* gather: every thread owns
+//            output slots, finds its (seed, j) by binary search in shared
+//            memory, issues the 4-byte neighbour gather and writes the compact
+//            COO coalesced.  All lanes are busy and each thread keeps several
+//            independent gathers in flight, which is what the HBM-latency-bound
+//            4-byte gathers need.
+//
+// variant 2 (Fisher-Yates, the default sampler of the training scripts) keeps
+// the reference's draw sequence r_j % (len-j) but applies the swaps to a
+// virtual copy held across the warp (lane t owns the write made at step t), so
+// the CSR in HBM is read-only.  variant 0 (reservoir / Algorithm R) evaluates
+// the len-f replacement draws in parallel and resolves "last writer wins" with
+// a shared-memory atomicMax.
+#include "common.cuh"
+
+namespace fgnn {
+namespace {
+
+constexpr int kTile = kBlock;  // seeds per tile
+
+struct TileSmem {
+  uint32_t rid[kTile];
+  uint32_t off[kTile];
+  uint32_t deg[kTile];
+  uint32_t out[kTile + 1];  // exclusive edge offsets inside the tile
+  uint32_t warp[kBlock / 32 + 1];
+  ChainSmem chain;
+};
+
+// Fisher-Yates over a virtual array, one warp per seed, NS slots per lane.
+template <int NS>
+__device__ __forceinline__ void select_fisher_yates(const RngKey &key, uint32_t item,
+                                                    uint32_t deg, uint32_t fanout,
+                                                    uint32_t *choice) {
+  const int lane = threadIdx.x & 31;
+  uint32_t kmine[NS], mkey[NS], mval[NS];
+#pragma unroll
+  for (int s = 0; s < NS; ++s) {
+    const uint32_t j = lane + 32 * s;
+    mkey[s] = kEmpty;
+    mval[s] = 0;
+    kmine[s] = 0;
+    if (j < fanout) kmine[s] = rand_u32(key, item, j) % (deg - j);
+  }
+  for (uint32_t j = 0; j < fanout; ++j) {
+    const int owner = j & 31, slot = j >> 5;
+    uint32_t k = 0;
+#pragma unroll
+    for (int s = 0; s < NS; ++s)
+      if (s == slot) k = __shfl_sync(0xFFFFFFFFu, kmine[s], owner);
+    const uint32_t last = deg - j - 1;
+    uint32_t vk = k, vlast = last;
+    bool fk = false, fl = false;
+    // latest earlier write wins: scan slots from high to low, lanes from high
+#pragma unroll
+    for (int s = NS - 1; s >= 0; --s) {
+      const uint32_t mk = __ballot_sync(0xFFFFFFFFu, mkey[s] == k);
+      const uint32_t ml = __ballot_sync(0xFFFFFFFFu, mkey[s] == last);
+      const uint32_t cand_k = __shfl_sync(0xFFFFFFFFu, mval[s], mk ? 31 - __clz(mk) : 0);
+      const uint32_t cand_l = __shfl_sync(0xFFFFFFFFu, mval[s], ml ? 31 - __clz(ml) : 0);
+      if (!fk && mk) { vk = cand_k; fk = true; }
+      if (!fl && ml) { vlast = cand_l; fl = true; }
+    }
+#pragma unroll
+    for (int s = 0; s < NS; ++s) {
+      if (s == slot && lane == owner) {
+        mkey[s] = k;
+        mval[s] = vlast;
+        choice[j] = vk;
+      }
+    }
+  }
+}
+
+// Algorithm R for j = fanout..deg-1, `nthreads` cooperating threads.
+__device__ __forceinline__ void select_reservoir(const RngKey &key, uint32_t item,
+                                                 uint32_t deg, uint32_t fanout,
+                                                 uint32_t *choice, uint32_t tid,
+                                                 uint32_t nthreads) {
+  const uint32_t ndraw = deg - fanout;
+  // each thread evaluates whole Philox blocks (4 draws)
+  for (uint32_t b = tid; b * 4u < ndraw; b += nthreads) {
+    const uint4 r = philox_block(key, item, b);
+#pragma unroll
+    for (uint32_t w = 0; w < 4; ++w) {
+      const uint32_t d = b * 4u + w;
+      if (d < ndraw) {
+        const uint32_t j = fanout + d;
+        const uint32_t k = pick_word(r, w) % (j + 1u);
+        if (k < fanout) atomicMax(&choice[k], j);
+      }
+    }
+  }
+}
+
+constexpr uint32_t kCtaSeedDegree = 4096;  // reservoir: above this a whole CTA helps
+
+template <int VARIANT, int NS>
+__global__ void __launch_bounds__(kBlock)
+sample_khop_kernel(const uint32_t *__restrict__ indptr, const uint32_t *__restrict__ indices,
+                   const uint32_t *__restrict__ input, uint32_t n_max,
+                   const uint32_t *__restrict__ d_n, uint32_t fanout, RngKey key,
+                   uint32_t *__restrict__ out_src, uint32_t *__restrict__ out_dst,
+                   uint32_t *__restrict__ out_src_local, uint32_t *__restrict__ d_num_out,
+                   ChainWs *ws) {
+  extern __shared__ uint32_t s_choice[];  // [kTile][fanout]
+  __shared__ TileSmem sm;
+
+  const uint32_t n = load_count(n_max, d_n);
+  const uint32_t p = chain_ticket(ws, &sm.chain);
+  uint32_t begin, end;
+  chunk_range(n, p, gridDim.x, kTile, &begin, &end);
+
+  // ---- phase 1: chunk aggregate ------------------------------------------
+  unsigned long long partial = 0;
+  for (uint32_t i = begin + threadIdx.x; i < end; i += kBlock) {
+    const uint32_t v = __ldg(input + i);
+    const uint32_t deg = __ldg(indptr + v + 1) - __ldg(indptr + v);
+    partial += deg < fanout ? deg : fanout;
+  }
+  unsigned long long chunk_total;
+  unsigned long long base = chain_scan(ws, &sm.chain, p, partial, &chunk_total);
+  if (p == gridDim.x - 1 && threadIdx.x == 0) *d_num_out = (uint32_t)(base + chunk_total);
+
+  // ---- phase 2: tiles -------------------------------------------------------
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (uint32_t t0 = begin; t0 < end; t0 += kTile) {
+    const uint32_t i = t0 + threadIdx.x;
+    uint32_t cnt = 0;
+    if (i < end) {
+      const uint32_t v = __ldg(input + i);
+      const uint32_t o = __ldg(indptr + v);
+      const uint32_t deg = __ldg(indptr + v + 1) - o;
+      sm.rid[threadIdx.x] = v;
+      sm.off[threadIdx.x] = o;
+      sm.deg[threadIdx.x] = deg;
+      cnt = deg < fanout ? deg : fanout;
+    } else {
+      sm.deg[threadIdx.x] = 0;
+    }
+    uint32_t tile_total;
+    const uint32_t excl = block_excl_scan(cnt, sm.warp, &tile_total);
+    sm.out[threadIdx.x] = excl;
+    if (threadIdx.x == kBlock - 1) sm.out[kTile] = tile_total;
+    // identity choice (covers deg <= fanout and the reservoir's initial fill)
+    for (uint32_t e = threadIdx.x; e < kTile * fanout; e += kBlock) s_choice[e] = e % fanout;
+    __syncthreads();
+
+    // selection, warp per seed
+    for (int s = warp; s < kTile; s += kBlock / 32) {
+      const uint32_t deg = sm.deg[s];
+      if (deg <= fanout) continue;
+      uint32_t *choice = s_choice + s * fanout;
+      if (VARIANT == 2) {
+        select_fisher_yates<NS>(key, t0 + s, deg, fanout, choice);
+      } else {
+        if (deg - fanout <= kCtaSeedDegree)
+          select_reservoir(key, t0 + s, deg, fanout, choice, lane, 32);
+      }
+    }
+    if (VARIANT == 0) {
+      // hub rows: the whole CTA evaluates the replacement draws
+      for (int s = 0; s < kTile; ++s) {
+        const uint32_t deg = sm.deg[s];
+        if (deg > fanout && deg - fanout > kCtaSeedDegree)
+          select_reservoir(key, t0 + s, deg, fanout, s_choice + s * fanout, threadIdx.x, kBlock);
+      }
+    }
+    __syncthreads();
+
+    // edge-parallel gather + coalesced compact write
+    for (uint32_t e = threadIdx.x; e < tile_total; e += kBlock) {
+      // largest s with out[s] <= e
+      uint32_t lo = 0, hi = kTile;
+#pragma unroll
+      for (int it = 0; it < 8; ++it) {
+        const uint32_t mid = (lo + hi) >> 1;
+        if (sm.out[mid] <= e) lo = mid; else hi = mid;
+      }
+      const uint32_t s = lo;
+      const uint32_t j = e - sm.out[s];
+      const uint32_t k = s_choice[s * fanout + j];
+      const uint32_t nbr = __ldg(indices + (size_t)sm.off[s] + k);
+      const size_t o = (size_t)base + e;
+      out_dst[o] = nbr;
+      if (out_src) out_src[o] = sm.rid[s];
+      if (out_src_local) out_src_local[o] = t0 + s;
+    }
+    base += tile_total;
+    __syncthreads();
+  }
+  chain_finish(ws, &sm.chain);
+}
+
+template <int VARIANT, int NS>
+int launch(const uint32_t *indptr, const uint32_t *indices, const uint32_t *input,
+           uint32_t n_max, const uint32_t *d_n, uint32_t fanout, RngKey key,
+           uint32_t *out_src, uint32_t *out_dst, uint32_t *out_src_local,
+           uint32_t *d_num_out, void *chain_ws, cudaStream_t stream) {
+  const size_t smem = (size_t)kTile * fanout * sizeof(uint32_t);
+  auto kern = sample_khop_kernel<VARIANT, NS>;
+  if (smem > 48 * 1024) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+  }
+  int occ = 1;
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kBlock, smem);
+  if (occ < 1) occ = 1;
+  const int grid = persistent_grid(n_max, kTile, occ, true);
+  kern<<<grid, kBlock, smem, stream>>>(indptr, indices, input, n_max, d_n, fanout, key, out_src,
+                                       out_dst, out_src_local, d_num_out, (ChainWs *)chain_ws);
+  note_launch();
+  return check_last();
+}
+
+}  // namespace
+}  // namespace fgnn
+
+extern "C" int fgnn_k_sample_khop(int variant, const uint32_t *indptr, const uint32_t *indices,
+                                  const uint32_t *input, uint32_t n_max, const uint32_t *d_n,
+                                  uint32_t fanout, fgnn_rng rng, uint32_t *out_src,
+                                  uint32_t *out_dst, uint32_t *out_src_local,
+                                  uint32_t *d_num_out, void *chain_ws, fgnn_stream_t stream) {
+  using namespace fgnn;
+  if (!indptr || !indices || !out_dst || !d_num_out || !chain_ws) return FGNN_ERR_BAD_ARG;
+  if (n_max > 0 && !input) return FGNN_ERR_BAD_ARG;
+  if (fanout == 0 || fanout > 128) return FGNN_ERR_UNSUPPORTED;
+  if ((uint64_t)n_max * fanout > 0xFFFFFFFFull) return FGNN_ERR_UNSUPPORTED;
+  const RngKey key = make_rng_key(rng);
+  cudaStream_t st = (cudaStream_t)stream;
+#define FGNN_GO(V, NS)                                                                      \
+  return launch<V, NS>(indptr, indices, input, n_max, d_n, fanout, key, out_src, out_dst,   \
+                       out_src_local, d_num_out, chain_ws, st)
+  if (variant == 2) {
+    if (fanout <= 32) FGNN_GO(2, 1);
+    if (fanout <= 64) FGNN_GO(2, 2);
+    FGNN_GO(2, 4);
+  } else if (variant == 0) {
+    FGNN_GO(0, 1);
+  }
+#undef FGNN_GO
+  return FGNN_ERR_BAD_ARG;
+}

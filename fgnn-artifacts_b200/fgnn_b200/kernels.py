@@ -1,0 +1,228 @@
+"""ctypes binding of the kernel C-ABI (include/fgnn_kernels.h) for torch CUDA tensors.
+
+PyTorch is plumbing here: it owns the device buffers and the stream; every
+operation below is one call into libfgnn_kernels.so.  There is no fallback:
+a missing library or a non-zero status raises.
+"""
+import ctypes as C
+import os
+
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(os.path.dirname(HERE), "lib", "libfgnn_kernels.so")
+EMPTY = 0xFFFFFFFF
+CHAIN_WS_BYTES = 16 + 8 * 4096
+
+SAMPLE_KHOP0, SAMPLE_KHOP1, SAMPLE_WEIGHTED, SAMPLE_RANDOM_WALK = 0, 1, 2, 3
+SAMPLE_WEIGHTED_PREFIX, SAMPLE_KHOP2, SAMPLE_WEIGHTED_HASH_DEDUP = 4, 5, 6
+
+
+class FgnnRng(C.Structure):
+    _fields_ = [("seed", C.c_uint64), ("batch_key", C.c_uint64), ("tag", C.c_uint32)]
+
+
+class KernelError(RuntimeError):
+    pass
+
+
+_vp = C.c_void_p
+_u32 = C.c_uint32
+_u64 = C.c_uint64
+_sz = C.c_size_t
+
+_SIGS = {
+    "fgnn_k_sample_khop": [C.c_int, _vp, _vp, _vp, _u32, _vp, _u32, FgnnRng, _vp, _vp, _vp, _vp, _vp, _vp],
+    "fgnn_k_sample_replace": [C.c_int, _vp, _vp, _vp, _vp, _vp, _vp, _u32, _vp, _u32, FgnnRng, _vp, _vp, _vp,
+                              _vp, _vp, _sz, _vp, _vp],
+    "fgnn_k_sample_weighted_hash_dedup": [_vp, _vp, _vp, _vp, _vp, _u32, _vp, _u32, FgnnRng, _vp, _vp, _vp, _vp,
+                                          _vp, _vp],
+    "fgnn_k_sample_random_walk": [_vp, _vp, _vp, _u32, _vp, _u32, C.c_double, _u32, _u32, FgnnRng, _vp, _vp,
+                                  _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp, _vp],
+    "fgnn_k_ht_reset": [_vp, _sz, _vp, _vp],
+    "fgnn_k_ht_fill_unique": [_vp, _sz, _vp, _u32, _vp, _vp, _vp, _vp],
+    "fgnn_k_ht_fill_duplicates": [_vp, _sz, _vp, _u32, _vp, _vp, _vp, _vp, _vp, _vp],
+    "fgnn_k_ht_map": [_vp, _sz, _vp, _vp, _u32, _vp, _vp, _vp],
+    "fgnn_k_cache_table_build": [_vp, _sz, _vp, _sz, _vp],
+    "fgnn_k_cache_split": [_vp, _vp, _u32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp],
+    "fgnn_k_row_copy": [_vp, _vp, _vp, _vp, _u64, _u32, _vp, _sz, _vp],
+    "fgnn_k_gather_cached": [_vp, _vp, _u32, _vp, _vp, _vp, _u32, _vp, _u64, _sz, _vp, _vp],
+    "fgnn_k_freq_count": [_vp, _vp, _u32, _vp, _vp],
+    "fgnn_k_presc_rank": [_vp, _sz, _vp, _vp, _sz, _vp],
+}
+_SIZE_FNS = {
+    "fgnn_k_ht_capacity": [_sz],
+    "fgnn_k_ht_bytes": [_sz],
+    "fgnn_k_sample_replace_workspace_bytes": [_u32, _u32],
+    "fgnn_k_sample_random_walk_workspace_bytes": [_u32, _u32],
+    "fgnn_k_presc_rank_workspace_bytes": [_sz],
+}
+
+_lib = None
+
+
+def exported_symbols():
+    return list(_SIGS) + list(_SIZE_FNS) + ["fgnn_k_version", "fgnn_k_error_string", "fgnn_k_launch_count"]
+
+
+def load(path=None):
+    """Load libfgnn_kernels.so (raises if it has not been built)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    path = path or os.environ.get("FGNN_KERNELS_LIB", LIB_PATH)
+    if not os.path.exists(path):
+        raise KernelError("%s not found: run `python fgnn-artifacts_b200/build.py` (no CPU fallback exists)" % path)
+    lib = C.CDLL(path, mode=C.RTLD_GLOBAL)
+    for name, args in _SIGS.items():
+        fn = getattr(lib, name)
+        fn.argtypes = args
+        fn.restype = C.c_int
+    for name, args in _SIZE_FNS.items():
+        fn = getattr(lib, name)
+        fn.argtypes = args
+        fn.restype = _sz
+    lib.fgnn_k_version.restype = C.c_char_p
+    lib.fgnn_k_error_string.restype = C.c_char_p
+    lib.fgnn_k_error_string.argtypes = [C.c_int]
+    lib.fgnn_k_launch_count.restype = _u64
+    _lib = lib
+    return lib
+
+
+def _check(code, what):
+    if code != 0:
+        raise KernelError("%s failed: %s (%d)" % (what, load().fgnn_k_error_string(code).decode(), code))
+
+
+def _ptr(t):
+    if t is None:
+        return None
+    if isinstance(t, int):
+        return t
+    return t.data_ptr()
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def launch_count():
+    return int(load().fgnn_k_launch_count())
+
+
+def new_chain_ws(device="cuda"):
+    return torch.zeros(CHAIN_WS_BYTES // 4, dtype=torch.int32, device=device)
+
+
+def rng(seed, batch_key, tag):
+    return FgnnRng(seed & 0xFFFFFFFFFFFFFFFF, batch_key & 0xFFFFFFFFFFFFFFFF, tag & 0xFFFFFFFF)
+
+
+# ---------------------------------------------------------------------------
+# thin wrappers (tensors are int32-typed views of uint32 data)
+# ---------------------------------------------------------------------------
+def sample_khop(variant, indptr, indices, inp, n_max, d_n, fanout, r, out_src, out_dst, out_src_local,
+                d_num_out, chain_ws):
+    _check(load().fgnn_k_sample_khop(variant, _ptr(indptr), _ptr(indices), _ptr(inp), n_max, _ptr(d_n), fanout,
+                                     r, _ptr(out_src), _ptr(out_dst), _ptr(out_src_local), _ptr(d_num_out),
+                                     _ptr(chain_ws), _stream()), "sample_khop")
+
+
+def sample_replace_workspace_bytes(n_max, fanout):
+    return int(load().fgnn_k_sample_replace_workspace_bytes(n_max, fanout))
+
+
+def sample_replace(kind, indptr, indices, prob, alias, prefix, inp, n_max, d_n, fanout, r, out_src, out_dst,
+                   out_src_local, d_num_out, workspace, chain_ws):
+    _check(load().fgnn_k_sample_replace(kind, _ptr(indptr), _ptr(indices), _ptr(prob), _ptr(alias), _ptr(prefix),
+                                        _ptr(inp), n_max, _ptr(d_n), fanout, r, _ptr(out_src), _ptr(out_dst),
+                                        _ptr(out_src_local), _ptr(d_num_out), _ptr(workspace),
+                                        workspace.numel() * workspace.element_size(), _ptr(chain_ws), _stream()),
+           "sample_replace")
+
+
+def sample_weighted_hash_dedup(indptr, indices, prob, alias, inp, n_max, d_n, fanout, r, out_src, out_dst,
+                               out_src_local, d_num_out, chain_ws):
+    _check(load().fgnn_k_sample_weighted_hash_dedup(_ptr(indptr), _ptr(indices), _ptr(prob), _ptr(alias),
+                                                    _ptr(inp), n_max, _ptr(d_n), fanout, r, _ptr(out_src),
+                                                    _ptr(out_dst), _ptr(out_src_local), _ptr(d_num_out),
+                                                    _ptr(chain_ws), _stream()), "sample_weighted_hash_dedup")
+
+
+def sample_random_walk_workspace_bytes(n_max, K):
+    return int(load().fgnn_k_sample_random_walk_workspace_bytes(n_max, K))
+
+
+def sample_random_walk(indptr, indices, inp, n_max, d_n, walk_len, restart_prob, num_walk, K, r, out_src,
+                       out_dst, out_src_local, out_data, d_num_out, tmp_src, tmp_dst, workspace, chain_ws):
+    _check(load().fgnn_k_sample_random_walk(_ptr(indptr), _ptr(indices), _ptr(inp), n_max, _ptr(d_n), walk_len,
+                                            float(restart_prob), num_walk, K, r, _ptr(out_src), _ptr(out_dst),
+                                            _ptr(out_src_local), _ptr(out_data), _ptr(d_num_out), _ptr(tmp_src),
+                                            _ptr(tmp_dst), _ptr(workspace),
+                                            workspace.numel() * workspace.element_size(), _ptr(chain_ws),
+                                            _stream()), "sample_random_walk")
+
+
+def ht_capacity(max_items):
+    return int(load().fgnn_k_ht_capacity(max_items))
+
+
+def ht_bytes(capacity):
+    return int(load().fgnn_k_ht_bytes(capacity))
+
+
+def ht_reset(table, capacity, d_num_items):
+    _check(load().fgnn_k_ht_reset(_ptr(table), capacity, _ptr(d_num_items), _stream()), "ht_reset")
+
+
+def ht_fill_unique(table, capacity, inp, n_max, d_n, n2o, d_num_items):
+    _check(load().fgnn_k_ht_fill_unique(_ptr(table), capacity, _ptr(inp), n_max, _ptr(d_n), _ptr(n2o),
+                                        _ptr(d_num_items), _stream()), "ht_fill_unique")
+
+
+def ht_fill_duplicates(table, capacity, inp, n_max, d_n, pos, n2o, d_num_items, chain_ws):
+    _check(load().fgnn_k_ht_fill_duplicates(_ptr(table), capacity, _ptr(inp), n_max, _ptr(d_n), _ptr(pos),
+                                            _ptr(n2o), _ptr(d_num_items), _ptr(chain_ws), _stream()),
+           "ht_fill_duplicates")
+
+
+def ht_map(table, capacity, glob, pos, n_max, d_n, out_local):
+    _check(load().fgnn_k_ht_map(_ptr(table), capacity, _ptr(glob), _ptr(pos), n_max, _ptr(d_n), _ptr(out_local),
+                                _stream()), "ht_map")
+
+
+def cache_table_build(table, num_nodes, rank, num_cached):
+    _check(load().fgnn_k_cache_table_build(_ptr(table), num_nodes, _ptr(rank), num_cached, _stream()),
+           "cache_table_build")
+
+
+def cache_split(table, nodes, n_max, d_n, miss_src, miss_dst, cache_src, cache_dst, d_counts, chain_ws):
+    _check(load().fgnn_k_cache_split(_ptr(table), _ptr(nodes), n_max, _ptr(d_n), _ptr(miss_src), _ptr(miss_dst),
+                                     _ptr(cache_src), _ptr(cache_dst), _ptr(d_counts), _ptr(chain_ws), _stream()),
+           "cache_split")
+
+
+def row_copy(dst, dst_index, src, src_index, n_max, d_n, row_bytes, src_mask=0xFFFFFFFFFFFFFFFF):
+    _check(load().fgnn_k_row_copy(_ptr(dst), _ptr(dst_index), _ptr(src), _ptr(src_index), src_mask, n_max,
+                                  _ptr(d_n), row_bytes, _stream()), "row_copy")
+
+
+def gather_cached(out, nodes, n_max, d_n, table, shards, num_shards, miss_src, row_bytes, d_stats=None,
+                  miss_mask=0xFFFFFFFFFFFFFFFF):
+    _check(load().fgnn_k_gather_cached(_ptr(out), _ptr(nodes), n_max, _ptr(d_n), _ptr(table), _ptr(shards),
+                                       num_shards, _ptr(miss_src), miss_mask, row_bytes, _ptr(d_stats), _stream()),
+           "gather_cached")
+
+
+def freq_count(freq, nodes, n_max, d_n):
+    _check(load().fgnn_k_freq_count(_ptr(freq), _ptr(nodes), n_max, _ptr(d_n), _stream()), "freq_count")
+
+
+def presc_rank_workspace_bytes(num_nodes):
+    return int(load().fgnn_k_presc_rank_workspace_bytes(num_nodes))
+
+
+def presc_rank(freq, num_nodes, rank, workspace):
+    _check(load().fgnn_k_presc_rank(_ptr(freq), num_nodes, _ptr(rank), _ptr(workspace),
+                                    workspace.numel() * workspace.element_size(), _stream()), "presc_rank")

@@ -1,0 +1,207 @@
+/* fgnn_kernels.h — thin C-ABI over the hand-written sm_100a kernels of the
+ * factored sampling-and-extraction hot path.
+ *
+ * This is the boundary the C++ host runtime (csrc/runtime) and the tests call
+ * through: plain pointers and sizes, no C++/torch types, no allocation inside,
+ * every call asynchronous on `stream`.  Each entry point cites the reference
+ * function it replaces (paths relative to /root/reference/samgraph/common/).
+ *
+ * Conventions
+ *   - ids are uint32_t (IdType, common.h:35); FGNN_EMPTY == Constant::kEmptyKey.
+ *   - "device counts": an element count is passed as (n_max, d_n).  If d_n is
+ *     NULL the count is n_max; otherwise the kernel reads *d_n (<= n_max) on the
+ *     device, so a whole mini-batch can be enqueued (or graph-captured) without
+ *     a host round trip per layer (the reference syncs ~12x per layer,
+ *     cuda_loops.cc:163-166, cuda_hashtable.cu:783-785).
+ *   - `chain_ws` is FGNN_CHAIN_WS_BYTES of device memory, zeroed once at
+ *     allocation.  Kernels that compact leave it zeroed, so one buffer per
+ *     stream can be reused by every call on that stream.
+ *   - return value: 0 on success, otherwise a cudaError_t (>0) or a negative
+ *     FGNN_ERR_* code.  Nothing falls back to the CPU.
+ */
+#ifndef FGNN_KERNELS_H
+#define FGNN_KERNELS_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FGNN_EMPTY 0xFFFFFFFFu
+#define FGNN_CHAIN_WS_BYTES (16u + 8u * 4096u)
+
+#define FGNN_ERR_BAD_ARG (-1)
+#define FGNN_ERR_UNSUPPORTED (-2)
+
+typedef struct CUstream_st *fgnn_stream_t; /* == cudaStream_t */
+
+/* RNG stream identity: Philox4x32-10, key=(seed.lo, seed.hi^batch_key.hi),
+ * ctr=(draw>>2, item, tag, batch_key.lo).  Replaces GPURandomStates
+ * (cuda_random_states.cu:36-108: per-thread XORWOW states, wall-clock seed). */
+typedef struct fgnn_rng {
+  uint64_t seed;
+  uint64_t batch_key; /* Engine::GetBatchKey: epoch*steps+step, engine.h:49-53 */
+  uint32_t tag;       /* layer index */
+} fgnn_rng;
+
+const char *fgnn_k_version(void);
+const char *fgnn_k_error_string(int code);
+/* number of kernel launches issued through this library since load */
+uint64_t fgnn_k_launch_count(void);
+
+/* ---- uniform k-hop sampling --------------------------------------------- */
+/* variant 0: GPUSampleKHop0 (cuda_sampling_khop0.cu:178-253, reservoir)
+ * variant 2: GPUSampleKHop2 (cuda_sampling_khop2.cu:177-252, Fisher-Yates,
+ *            stateless: the CSR is never mutated)
+ * Output is the compact COO in seed-major order (== sample + count_edge +
+ * compact_edge of the reference, fused):  out_src[e] global seed id (may be
+ * NULL), out_dst[e] global neighbour id, out_src_local[e] = index of the seed
+ * in `input` (may be NULL; equals the seed's local id, cuda_loops.cc:203-221).
+ * *d_num_out <- number of edges.  Outputs must hold n_max*fanout entries. */
+int fgnn_k_sample_khop(int variant, const uint32_t *indptr,
+                       const uint32_t *indices, const uint32_t *input,
+                       uint32_t n_max, const uint32_t *d_n, uint32_t fanout,
+                       fgnn_rng rng, uint32_t *out_src, uint32_t *out_dst,
+                       uint32_t *out_src_local, uint32_t *d_num_out,
+                       void *chain_ws, fgnn_stream_t stream);
+
+/* ---- with-replacement samplers (sort by src id + adjacent dedup) ---------- */
+/* kind 1: GPUSampleKHop1            (cuda_sampling_khop1.cu:130-234)
+ * kind 2: GPUSampleWeightedKHop     (cuda_sampling_weighted_khop.cu:132-236)
+ * kind 4: GPUSampleWeightedKHopPrefix (cuda_sampling_weighted_khop_prefix.cu:137-255)
+ * (kind values follow SampleType, common.h:50-58.)  prob/alias/prefix are the
+ * per-edge tables of Dataset (common.h:141-144); unused ones may be NULL.
+ * Output order follows the reference: rows ordered by ascending seed id, an
+ * entry is dropped when equal to its successor.  workspace: see
+ * fgnn_k_sample_replace_workspace_bytes. */
+size_t fgnn_k_sample_replace_workspace_bytes(uint32_t n_max, uint32_t fanout);
+int fgnn_k_sample_replace(int kind, const uint32_t *indptr,
+                          const uint32_t *indices, const float *prob_table,
+                          const uint32_t *alias_table,
+                          const float *prob_prefix_table, const uint32_t *input,
+                          uint32_t n_max, const uint32_t *d_n, uint32_t fanout,
+                          fgnn_rng rng, uint32_t *out_src, uint32_t *out_dst,
+                          uint32_t *out_src_local, uint32_t *d_num_out,
+                          void *workspace, size_t workspace_bytes,
+                          void *chain_ws, fgnn_stream_t stream);
+
+/* GPUSampleWeightedKHopHashDedup (cuda_sampling_weighted_khop_hash_dedup.cu:
+ * 203-279): alias sampling with rejection until `fanout` distinct; seed-major
+ * compact output like fgnn_k_sample_khop.  The reference spins forever when a
+ * row has fewer than `fanout` distinct reachable ids; here draws beyond
+ * FGNN_HASH_DEDUP_MAX_DRAWS are accepted even if duplicate. */
+#define FGNN_HASH_DEDUP_MAX_DRAWS 4096u
+int fgnn_k_sample_weighted_hash_dedup(
+    const uint32_t *indptr, const uint32_t *indices, const float *prob_table,
+    const uint32_t *alias_table, const uint32_t *input, uint32_t n_max,
+    const uint32_t *d_n, uint32_t fanout, fgnn_rng rng, uint32_t *out_src,
+    uint32_t *out_dst, uint32_t *out_src_local, uint32_t *d_num_out,
+    void *chain_ws, fgnn_stream_t stream);
+
+/* ---- PinSAGE random walk + top-K ------------------------------------------ */
+/* GPUSampleRandomWalk (cuda_sampling_random_walk.cu:113-161) followed by
+ * FrequencyHashmap::GetTopK (cuda_frequency_hashmap.cu:1143-1367), fused: the
+ * visit list of a start node never leaves the SM.  out_data[e] = visit count.
+ * If tmp_src/tmp_dst are non-NULL the raw walk COO (n_max*W*L entries, layout
+ * of random_walk.cu:60-78) is also written, for parity tests.
+ * Requires num_walk*walk_len <= 32.  workspace: see *_workspace_bytes. */
+size_t fgnn_k_sample_random_walk_workspace_bytes(uint32_t n_max, uint32_t K);
+int fgnn_k_sample_random_walk(const uint32_t *indptr, const uint32_t *indices,
+                              const uint32_t *input, uint32_t n_max,
+                              const uint32_t *d_n, uint32_t walk_len,
+                              double restart_prob, uint32_t num_walk,
+                              uint32_t K, fgnn_rng rng, uint32_t *out_src,
+                              uint32_t *out_dst, uint32_t *out_src_local,
+                              uint32_t *out_data, uint32_t *d_num_out,
+                              uint32_t *tmp_src, uint32_t *tmp_dst,
+                              void *workspace, size_t workspace_bytes,
+                              void *chain_ws, fgnn_stream_t stream);
+
+/* ---- OrderedHashTable (cuda_hashtable.cu) ---------------------------------- */
+/* Table = `capacity` (power of two) 8-byte buckets {key, local}.  `d_num_items`
+ * is the running number of unique ids (device).  `n2o` (>= max items) is the
+ * local->global list, i.e. the reference's N2O table / `unique` output. */
+size_t fgnn_k_ht_capacity(size_t max_items);
+size_t fgnn_k_ht_bytes(size_t capacity);
+/* Reset (cuda_hashtable.cu:714-723) */
+int fgnn_k_ht_reset(void *table, size_t capacity, uint32_t *d_num_items,
+                    fgnn_stream_t stream);
+/* FillWithUnique (cuda_hashtable.cu:1017-1037): local = *d_num_items + index */
+int fgnn_k_ht_fill_unique(void *table, size_t capacity, const uint32_t *input,
+                          uint32_t n_max, const uint32_t *d_n, uint32_t *n2o,
+                          uint32_t *d_num_items, fgnn_stream_t stream);
+/* FillWithDuplicates (cuda_hashtable.cu:725-807): ids not yet present get
+ * consecutive local ids in order of first occurrence in `input` (one legal
+ * outcome of the reference's atomicCAS race, and exactly CPUHashTable0's order,
+ * cpu_hashtable0.cc:37-47).  `pos` (n_max entries, scratch/out) receives the
+ * bucket position of every input item so remapping needs no second probe. */
+int fgnn_k_ht_fill_duplicates(void *table, size_t capacity,
+                              const uint32_t *input, uint32_t n_max,
+                              const uint32_t *d_n, uint32_t *pos,
+                              uint32_t *n2o, uint32_t *d_num_items,
+                              void *chain_ws, fgnn_stream_t stream);
+/* GPUMapEdges for one column (cuda_mapping.cu:32-81).  With pos != NULL the
+ * local id is read from bucket pos[i]; otherwise `global[i]` is probed. */
+int fgnn_k_ht_map(const void *table, size_t capacity, const uint32_t *global,
+                  const uint32_t *pos, uint32_t n_max, const uint32_t *d_n,
+                  uint32_t *out_local, fgnn_stream_t stream);
+
+/* ---- feature cache ---------------------------------------------------------- */
+/* SampleCacheTableInit / DistCacheManager ctor steps 1-2 (dist_engine.cc:193-229,
+ * dist_cache_manager_host.cc:84-95): table[v]=EMPTY; table[rank[i]]=i, i<num_cached */
+int fgnn_k_cache_table_build(uint32_t *table, size_t num_nodes,
+                             const uint32_t *ranking_nodes, size_t num_cached,
+                             fgnn_stream_t stream);
+/* GetMissCacheIndex (cuda_cache.cu:162-234): stable split of `nodes`.
+ * d_counts[0] <- num_miss, d_counts[1] <- num_cache. */
+int fgnn_k_cache_split(const uint32_t *table, const uint32_t *nodes,
+                       uint32_t n_max, const uint32_t *d_n, uint32_t *miss_src,
+                       uint32_t *miss_dst, uint32_t *cache_src,
+                       uint32_t *cache_dst, uint32_t *d_counts, void *chain_ws,
+                       fgnn_stream_t stream);
+
+/* ---- extraction --------------------------------------------------------------- */
+/* Generic row copy dst[dst_index?[i]] = src[src_index?[i] & src_mask] with rows
+ * of row_bytes.  One kernel covers GPUExtract (cuda_extraction.cu:74-117),
+ * combine_miss_data and combine_cache_data (dist_cache_manager_device.cu:37-82)
+ * and, with `src` in pinned host memory, extract_miss_data
+ * (dist_cache_manager_host.cc:38-56).  src_mask = ~0 normally; (1<<k)-1 for
+ * SAMGRAPH_EMPTY_FEAT=k (cuda_extraction.cu:131). */
+int fgnn_k_row_copy(void *dst, const uint32_t *dst_index, const void *src,
+                    const uint32_t *src_index, uint64_t src_mask,
+                    uint32_t n_max, const uint32_t *d_n, size_t row_bytes,
+                    fgnn_stream_t stream);
+
+/* Fused cache-aware gather, replaces GetMissCacheIndex + ExtractMissData +
+ * H2D + CombineMissData + CombineCacheData (dist_loops.cc:713-846):
+ *   slot = table[nodes[i]];
+ *   out[i] = slot != EMPTY ? shard[slot % num_shards][slot / num_shards]
+ *                          : miss_src[nodes[i] & miss_mask]
+ * `shards` is a DEVICE array of num_shards row-major cache shard base pointers
+ * (local HBM or NVLink peer mappings); num_shards == 1 is the replicated cache
+ * of the reference.  `miss_src` may be pinned host memory (UVA) or device
+ * memory.  d_stats (optional, 2 x u64): += {hit rows, miss rows}. */
+int fgnn_k_gather_cached(void *out, const uint32_t *nodes, uint32_t n_max,
+                         const uint32_t *d_n, const uint32_t *table,
+                         const void *const *shards, uint32_t num_shards,
+                         const void *miss_src, uint64_t miss_mask,
+                         size_t row_bytes, unsigned long long *d_stats,
+                         fgnn_stream_t stream);
+
+/* ---- PreSC ---------------------------------------------------------------------- */
+/* freq[nodes[i]] += 1  (cuda/pre_sampler.cc:84-88) */
+int fgnn_k_freq_count(uint32_t *freq, const uint32_t *nodes, uint32_t n_max,
+                      const uint32_t *d_n, fgnn_stream_t stream);
+/* ranking_nodes = argsort desc of u64 {freq:hi32,id:lo32}
+ * (cuda/pre_sampler.cc:44-49,97-99,121-142) */
+size_t fgnn_k_presc_rank_workspace_bytes(size_t num_nodes);
+int fgnn_k_presc_rank(const uint32_t *freq, size_t num_nodes,
+                      uint32_t *ranking_nodes, void *workspace,
+                      size_t workspace_bytes, fgnn_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FGNN_KERNELS_H */

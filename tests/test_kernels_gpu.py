@@ -1,0 +1,449 @@
+"""GPU parity tests: every kernel of the C-ABI (include/fgnn_kernels.h) against
+the CPU oracle on the same seeded inputs.  Integer/byte work -> bit-exact."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+torch = pytest.importorskip("torch")
+
+SEED = 0x1234ABCD5678EF01
+
+
+@pytest.fixture(scope="module")
+def K():
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    from fgnn_b200 import kernels
+    kernels.load()  # raises if the extension is missing: no fallback
+    return kernels
+
+
+def dev(a):
+    from fgnn_b200.synth import u32_tensor
+    return u32_tensor(np.ascontiguousarray(a, dtype=np.uint32))
+
+
+def host(t, n=None):
+    from fgnn_b200.synth import to_np_u32
+    a = to_np_u32(t)
+    return a if n is None else a[:n]
+
+
+def pick_seeds(indptr, n, seed, unique=True):
+    rng = np.random.default_rng(seed)
+    V = len(indptr) - 1
+    if unique:
+        return rng.permutation(V)[:n].astype(np.uint32)
+    return rng.integers(0, V, size=n).astype(np.uint32)
+
+
+class G:
+    def __init__(self, indptr, indices):
+        self.indptr_np, self.indices_np = indptr, indices
+        self.indptr, self.indices = dev(indptr), dev(indices)
+
+
+@pytest.fixture(scope="module")
+def gs(graph_small):
+    return G(*graph_small)
+
+
+@pytest.fixture(scope="module")
+def gm(graph_medium):
+    return G(*graph_medium)
+
+
+def run_khop(K, g, seeds, fanout, variant, batch_key=5, tag=1, d_n=None, n_max=None):
+    n_max = len(seeds) if n_max is None else n_max
+    inp = dev(np.concatenate([seeds, np.zeros(n_max - len(seeds), np.uint32)]))
+    cap = max(1, n_max * fanout)
+    out_src = torch.empty(cap, dtype=torch.int32, device="cuda")
+    out_dst = torch.empty(cap, dtype=torch.int32, device="cuda")
+    out_loc = torch.empty(cap, dtype=torch.int32, device="cuda")
+    num = torch.zeros(1, dtype=torch.int32, device="cuda")
+    ws = K.new_chain_ws()
+    dn = None
+    if d_n is not None:
+        dn = torch.tensor([d_n], dtype=torch.int32, device="cuda")
+    K.sample_khop(variant, g.indptr, g.indices, inp, n_max, dn, fanout, K.rng(SEED, batch_key, tag),
+                  out_src, out_dst, out_loc, num, ws)
+    torch.cuda.synchronize()
+    m = int(num.item())
+    assert int(ws.abs().sum().item()) == 0, "chain workspace must be left zeroed"
+    return host(out_src, m), host(out_dst, m), host(out_loc, m)
+
+
+@pytest.mark.parametrize("variant,fanout", [(2, 5), (2, 10), (2, 25), (2, 32), (2, 40), (2, 100),
+                                            (0, 5), (0, 15), (0, 25)])
+@pytest.mark.parametrize("n", [0, 1, 255, 256, 257, 2500])
+def test_sample_khop_matches_oracle(K, oracle, gs, variant, fanout, n):
+    seeds = pick_seeds(gs.indptr_np, n, 3)
+    s, d, l = run_khop(K, gs, seeds, fanout, variant)
+    fn = oracle.sample_khop2 if variant == 2 else oracle.sample_khop0
+    es, ed = fn(gs.indptr_np, gs.indices_np, seeds, fanout, SEED, 5, 1)
+    assert np.array_equal(s, es)
+    assert np.array_equal(d, ed)
+    # local src = index of the seed in the input list
+    if len(s):
+        assert np.array_equal(seeds[l], s)
+        assert np.all(np.diff(l.astype(np.int64)) >= 0)
+
+
+@pytest.mark.parametrize("variant", [0, 2])
+def test_sample_khop_device_count_and_large(K, oracle, gm, variant):
+    seeds = pick_seeds(gm.indptr_np, 40000, 9)
+    # device-side count smaller than the bound
+    s, d, _ = run_khop(K, gm, seeds[:33333], 10, variant, batch_key=77, tag=0, d_n=33333, n_max=40000)
+    fn = oracle.sample_khop2 if variant == 2 else oracle.sample_khop0
+    es, ed = fn(gm.indptr_np, gm.indices_np, seeds[:33333], 10, SEED, 77, 0)
+    assert np.array_equal(s, es) and np.array_equal(d, ed)
+
+
+def test_sample_khop_hub_rows(K, oracle):
+    """Rows far above the CTA-cooperative threshold (reservoir) and above fanout (F-Y)."""
+    rng = np.random.default_rng(5)
+    degs = np.array([0, 1, 70000, 3, 25, 26, 9000, 5000, 4121, 4122], np.uint32)
+    indptr = np.concatenate([[0], np.cumsum(degs)]).astype(np.uint32)
+    indices = rng.integers(0, len(degs), size=int(indptr[-1])).astype(np.uint32)
+    g = G(indptr, indices)
+    seeds = np.arange(len(degs), dtype=np.uint32)
+    for variant, fn in ((0, oracle.sample_khop0), (2, oracle.sample_khop2)):
+        s, d, _ = run_khop(K, g, seeds, 25, variant)
+        es, ed = fn(indptr, indices, seeds, 25, SEED, 5, 1)
+        assert np.array_equal(s, es) and np.array_equal(d, ed)
+
+
+def test_sample_khop2_without_replacement_property(K, gm):
+    """Size-independent property: positions drawn for a row are distinct -> on a graph whose
+    rows hold distinct ids, each sampled row has no duplicate and is a subset of the row."""
+    V = 5000
+    rng = np.random.default_rng(1)
+    degs = rng.integers(0, 200, size=V).astype(np.uint32)
+    indptr = np.concatenate([[0], np.cumsum(degs)]).astype(np.uint32)
+    indices = np.concatenate([rng.permutation(100000)[:d] for d in degs]).astype(np.uint32)
+    g = G(indptr, indices)
+    seeds = np.arange(V, dtype=np.uint32)
+    for variant in (0, 2):
+        s, d, l = run_khop(K, g, seeds, 15, variant)
+        counts = np.bincount(l, minlength=V)
+        assert np.array_equal(counts, np.minimum(degs, 15))
+        key = l.astype(np.uint64) << np.uint64(32) | d.astype(np.uint64)
+        assert len(np.unique(key)) == len(key)
+        # subset check
+        row_key = np.repeat(np.arange(V, dtype=np.uint64), degs) << np.uint64(32) | indices.astype(np.uint64)
+        assert np.all(np.isin(key, row_key))
+
+
+# ---------------------------------------------------------------------------
+class HT:
+    def __init__(self, K, max_items):
+        self.K = K
+        self.cap = K.ht_capacity(max_items)
+        self.table = torch.empty(K.ht_bytes(self.cap) // 4, dtype=torch.int32, device="cuda")
+        self.n2o = torch.empty(max_items + 1, dtype=torch.int32, device="cuda")
+        self.num = torch.zeros(1, dtype=torch.int32, device="cuda")
+        self.ws = K.new_chain_ws()
+        K.ht_reset(self.table, self.cap, self.num)
+
+    def reset(self):
+        self.K.ht_reset(self.table, self.cap, self.num)
+
+    def fill_unique(self, ids):
+        self.K.ht_fill_unique(self.table, self.cap, dev(ids), len(ids), None, self.n2o, self.num)
+
+    def fill_duplicates(self, ids):
+        d = dev(ids)
+        pos = torch.empty(max(1, len(ids)), dtype=torch.int32, device="cuda")
+        self.K.ht_fill_duplicates(self.table, self.cap, d, len(ids), None, pos, self.n2o, self.num, self.ws)
+        return d, pos
+
+    def num_items(self):
+        torch.cuda.synchronize()
+        return int(self.num.item())
+
+    def unique(self):
+        return host(self.n2o, self.num_items())
+
+    def map(self, d=None, pos=None, n=None):
+        out = torch.empty(max(1, n), dtype=torch.int32, device="cuda")
+        self.K.ht_map(self.table, self.cap, d, pos, n, None, out)
+        torch.cuda.synchronize()
+        return host(out, n)
+
+
+@pytest.mark.parametrize("n_seed,n_dup,universe", [(0, 0, 10), (8, 0, 100), (100, 5000, 300), (8000, 200000, 50000),
+                                                   (1000, 300000, 1 << 20), (1, 100000, 3)])
+def test_hashtable_matches_oracle(K, oracle, n_seed, n_dup, universe):
+    rng = np.random.default_rng(n_seed + n_dup)
+    seeds = rng.permutation(universe)[:n_seed].astype(np.uint32)
+    max_items = n_seed + 3 * n_dup + 16
+    ht = HT(K, max_items)
+    oh = oracle.hashtable(max_items)
+    ht.fill_unique(seeds)
+    oh.fill_unique(seeds)
+    for rnd in range(3):  # three "layers"
+        ids = rng.integers(0, universe, size=n_dup).astype(np.uint32)
+        d, pos = ht.fill_duplicates(ids)
+        oh.fill_duplicates(ids)
+        assert ht.num_items() == oh.num_items
+        assert np.array_equal(ht.unique(), oh.unique())
+        if n_dup:
+            exp = oh.map(ids)
+            assert np.array_equal(ht.map(None, pos, n_dup), exp)   # via remembered bucket
+            assert np.array_equal(ht.map(d, None, n_dup), exp)     # via probe
+        assert int(ht.ws.abs().sum().item()) == 0
+    # reset -> empty again, local ids restart at 0
+    ht.reset()
+    assert ht.num_items() == 0
+    ht.fill_unique(seeds)
+    assert np.array_equal(ht.unique(), seeds)
+
+
+def test_hashtable_map_absent_is_empty(K):
+    ht = HT(K, 100)
+    ht.fill_unique(np.array([5, 6, 7], np.uint32))
+    q = dev(np.array([7, 8, 5], np.uint32))
+    out = ht.map(q, None, 3)
+    assert out.tolist() == [2, 0xFFFFFFFF, 0]
+
+
+# ---------------------------------------------------------------------------
+@pytest.mark.parametrize("n,V,pct", [(0, 100, 0.5), (1, 100, 0.0), (1000, 5000, 0.25), (100000, 70000, 0.1),
+                                     (5000, 5000, 1.0)])
+def test_cache_table_and_split(K, oracle, n, V, pct):
+    rng = np.random.default_rng(n + V)
+    rank = rng.permutation(V).astype(np.uint32)
+    nc = oracle.num_cached(V, pct)
+    table_ref = oracle.cache_table_build(rank, V, nc)
+    table = torch.empty(V, dtype=torch.int32, device="cuda")
+    K.cache_table_build(table, V, dev(rank), nc)
+    torch.cuda.synchronize()
+    assert np.array_equal(host(table), table_ref)
+    nodes = rng.integers(0, V, size=n).astype(np.uint32)
+    bufs = [torch.empty(max(1, n), dtype=torch.int32, device="cuda") for _ in range(4)]
+    counts = torch.zeros(2, dtype=torch.int32, device="cuda")
+    ws = K.new_chain_ws()
+    K.cache_split(table, dev(nodes), n, None, bufs[0], bufs[1], bufs[2], bufs[3], counts, ws)
+    torch.cuda.synchronize()
+    nm, nh = counts.tolist()
+    ms, md, cs, cd = oracle.cache_split(table_ref, nodes)
+    assert (nm, nh) == (len(ms), len(cs)) and nm + nh == n   # cuda_loops.cc:999 invariant
+    assert np.array_equal(host(bufs[0], nm), ms) and np.array_equal(host(bufs[1], nm), md)
+    assert np.array_equal(host(bufs[2], nh), cs) and np.array_equal(host(bufs[3], nh), cd)
+    assert int(ws.abs().sum().item()) == 0
+
+
+# ---------------------------------------------------------------------------
+@pytest.mark.parametrize("dtype,dim", [(np.float32, 128), (np.float32, 100), (np.float32, 256), (np.float32, 1),
+                                       (np.int64, 1), (np.uint8, 7), (np.float64, 3), (np.int16, 5), (np.float32, 602)])
+@pytest.mark.parametrize("n", [0, 1, 1000, 33333])
+def test_row_copy_extract(K, oracle, dtype, dim, n):
+    rng = np.random.default_rng(dim + n)
+    V = 5000
+    if np.issubdtype(dtype, np.floating):
+        src = rng.standard_normal((V, dim)).astype(dtype)
+    else:
+        src = rng.integers(0, 100, size=(V, dim)).astype(dtype)
+    idx = rng.integers(0, V, size=n).astype(np.uint32)
+    exp = oracle.extract(src, idx)
+    d_src = torch.from_numpy(src.view(np.uint8).reshape(V, -1)).cuda()
+    row_bytes = d_src.shape[1]
+    out = torch.zeros((max(1, n), row_bytes), dtype=torch.uint8, device="cuda")
+    K.row_copy(out, None, d_src, dev(idx), n, None, row_bytes)
+    torch.cuda.synchronize()
+    got = out[:n].cpu().numpy().reshape(n, -1).view(dtype).reshape(n, dim)
+    assert np.array_equal(got.view(np.uint8), exp.view(np.uint8))
+
+
+def test_row_copy_scatter_and_mask(K, oracle):
+    rng = np.random.default_rng(0)
+    V, n, dim = 1 << 10, 3000, 64
+    src = rng.standard_normal((V, dim)).astype(np.float32)
+    idx = rng.integers(0, 1 << 20, size=n).astype(np.uint32)       # masked like SAMGRAPH_EMPTY_FEAT=10
+    dst_idx = rng.permutation(n).astype(np.uint32)
+    exp = np.zeros((n, dim), np.float32)
+    oracle.row_copy(exp, dst_idx, src, idx, n, dim * 4, mask=(1 << 10) - 1)
+    out = torch.zeros((n, dim), dtype=torch.float32, device="cuda")
+    K.row_copy(out, dev(dst_idx), torch.from_numpy(src).cuda(), dev(idx), n, None, dim * 4, src_mask=(1 << 10) - 1)
+    torch.cuda.synchronize()
+    assert np.array_equal(out.cpu().numpy().view(np.uint32), exp.view(np.uint32))
+
+
+@pytest.mark.parametrize("num_shards", [1, 2, 4])
+@pytest.mark.parametrize("dim,pct", [(128, 0.3), (100, 0.0), (256, 1.0)])
+def test_gather_cached_matches_reference_pipeline(K, oracle, num_shards, dim, pct):
+    """Fused gather == GetMissCacheIndex + ExtractMissData + CombineMiss + CombineCache."""
+    rng = np.random.default_rng(dim)
+    V, n = 20000, 50000
+    feat = rng.standard_normal((V, dim)).astype(np.float32)
+    rank = rng.permutation(V).astype(np.uint32)
+    nc = oracle.num_cached(V, pct)
+    table_ref = oracle.cache_table_build(rank, V, nc)
+    nodes = rng.integers(0, V, size=n).astype(np.uint32)
+    # reference pipeline on the CPU oracle
+    ms, md, cs, cd = oracle.cache_split(table_ref, nodes)
+    cache = oracle.extract(feat, rank[:nc])                    # dist_cache_manager_host.cc:98-109
+    exp = np.zeros((n, dim), np.float32)
+    miss_rows = oracle.extract(feat, ms)
+    oracle.row_copy(exp, md, miss_rows, None, len(ms), dim * 4)
+    oracle.row_copy(exp, cd, cache, cs, len(cs), dim * 4)
+    assert np.array_equal(exp, feat[nodes])
+    # device: cache striped over `num_shards` buffers (owner = slot % T, row = slot // T)
+    shards = []
+    for t in range(num_shards):
+        rows = cache[t::num_shards]
+        shards.append(torch.from_numpy(np.ascontiguousarray(rows)).cuda() if len(rows) else
+                      torch.zeros((1, dim), dtype=torch.float32, device="cuda"))
+    ptrs = torch.tensor([s.data_ptr() for s in shards], dtype=torch.int64, device="cuda")
+    table = dev(table_ref)
+    host_feat = torch.from_numpy(feat).pin_memory()             # misses read over UVA
+    out = torch.zeros((n, dim), dtype=torch.float32, device="cuda")
+    stats = torch.zeros(2, dtype=torch.int64, device="cuda")
+    K.gather_cached(out, dev(nodes), n, None, table, ptrs, num_shards, host_feat, dim * 4, stats)
+    torch.cuda.synchronize()
+    assert np.array_equal(out.cpu().numpy().view(np.uint32), exp.view(np.uint32))
+    assert stats.tolist() == [len(cs), len(ms)]
+
+
+# ---------------------------------------------------------------------------
+def test_presc_count_and_rank(K, oracle):
+    rng = np.random.default_rng(3)
+    V = 100000
+    freq_ref = np.zeros(V, np.uint32)
+    freq = torch.zeros(V, dtype=torch.int32, device="cuda")
+    for _ in range(4):
+        nodes = (rng.zipf(1.3, size=60000) % V).astype(np.uint32)
+        oracle.freq_count(freq_ref, nodes)
+        K.freq_count(freq, dev(nodes), len(nodes), None)
+    torch.cuda.synchronize()
+    assert np.array_equal(host(freq), freq_ref)
+    ws = torch.empty(K.presc_rank_workspace_bytes(V), dtype=torch.uint8, device="cuda")
+    rank = torch.empty(V, dtype=torch.int32, device="cuda")
+    K.presc_rank(freq, V, rank, ws)
+    torch.cuda.synchronize()
+    assert np.array_equal(host(rank), oracle.presc_rank(freq_ref))
+
+
+# ---------------------------------------------------------------------------
+def weight_tables(oracle, indptr, indices, seed=2):
+    rng = np.random.default_rng(seed)
+    w = rng.integers(1, 11, size=len(indices)).astype(np.float32)
+    prob, alias = oracle.build_alias_table(indptr, indices, w)
+    prefix = oracle.build_prefix_table(indptr, w)
+    return prob, alias, prefix
+
+
+@pytest.mark.parametrize("kind", [1, 2, 4])
+@pytest.mark.parametrize("n,fanout,unique", [(0, 5, True), (1, 10, True), (700, 10, True), (2500, 25, True),
+                                             (500, 7, False)])
+def test_sample_replace_matches_oracle(K, oracle, gs, kind, n, fanout, unique):
+    prob, alias, prefix = weight_tables(oracle, gs.indptr_np, gs.indices_np)
+    seeds = pick_seeds(gs.indptr_np, n, 4, unique)
+    n_max = n + 13
+    inp = dev(np.concatenate([seeds, np.zeros(n_max - n, np.uint32)]))
+    cap = n_max * fanout
+    outs = [torch.empty(cap, dtype=torch.int32, device="cuda") for _ in range(3)]
+    num = torch.zeros(1, dtype=torch.int32, device="cuda")
+    dn = torch.tensor([n], dtype=torch.int32, device="cuda")
+    wsb = torch.empty(K.sample_replace_workspace_bytes(n_max, fanout), dtype=torch.uint8, device="cuda")
+    ws = K.new_chain_ws()
+    fprob, falias, fprefix = (torch.from_numpy(prob).cuda(), dev(alias), torch.from_numpy(prefix).cuda())
+    K.sample_replace(kind, gs.indptr, gs.indices, fprob, falias, fprefix, inp, n_max, dn, fanout,
+                     K.rng(SEED, 9, 2), outs[0], outs[1], outs[2], num, wsb, ws)
+    torch.cuda.synchronize()
+    m = int(num.item())
+    if kind == 1:
+        es, ed = oracle.sample_khop1(gs.indptr_np, gs.indices_np, seeds, fanout, SEED, 9, 2)
+    elif kind == 2:
+        es, ed = oracle.sample_weighted_khop(gs.indptr_np, gs.indices_np, prob, alias, seeds, fanout, SEED, 9, 2)
+    else:
+        es, ed = oracle.sample_weighted_khop_prefix(gs.indptr_np, gs.indices_np, prefix, seeds, fanout, SEED, 9, 2)
+    assert m == len(es)
+    assert np.array_equal(host(outs[0], m), es) and np.array_equal(host(outs[1], m), ed)
+    if m:
+        assert np.array_equal(seeds[host(outs[2], m)], es)
+    assert int(ws.abs().sum().item()) == 0
+
+
+@pytest.mark.parametrize("n,fanout", [(0, 5), (3, 5), (900, 10), (2500, 25)])
+def test_sample_weighted_hash_dedup_matches_oracle(K, oracle, gs, n, fanout):
+    prob, alias, _ = weight_tables(oracle, gs.indptr_np, gs.indices_np)
+    seeds = pick_seeds(gs.indptr_np, n, 6)
+    cap = max(1, n * fanout)
+    outs = [torch.empty(cap, dtype=torch.int32, device="cuda") for _ in range(3)]
+    num = torch.zeros(1, dtype=torch.int32, device="cuda")
+    ws = K.new_chain_ws()
+    K.sample_weighted_hash_dedup(gs.indptr, gs.indices, torch.from_numpy(prob).cuda(), dev(alias), dev(seeds), n,
+                                 None, fanout, K.rng(SEED, 3, 0), outs[0], outs[1], outs[2], num, ws)
+    torch.cuda.synchronize()
+    m = int(num.item())
+    es, ed = oracle.sample_weighted_khop(gs.indptr_np, gs.indices_np, prob, alias, seeds, fanout, SEED, 3, 0,
+                                         hash_dedup=True)
+    assert m == len(es)
+    assert np.array_equal(host(outs[0], m), es) and np.array_equal(host(outs[1], m), ed)
+
+
+@pytest.mark.parametrize("n,W,L,Kn,p", [(0, 4, 3, 5, 0.5), (1, 4, 3, 5, 0.5), (3000, 4, 3, 5, 0.5), (777, 3, 3, 4, 0.3),
+                                        (500, 8, 4, 10, 0.0), (500, 1, 1, 1, 0.9), (300, 5, 2, 3, 1.0)])
+def test_random_walk_topk_matches_oracle(K, oracle, gs, n, W, L, Kn, p):
+    seeds = pick_seeds(gs.indptr_np, n, 8)
+    cap = max(1, n * max(Kn, W * L))
+    outs = [torch.empty(cap, dtype=torch.int32, device="cuda") for _ in range(4)]
+    tmps = [torch.empty(cap, dtype=torch.int32, device="cuda") for _ in range(2)]
+    num = torch.zeros(1, dtype=torch.int32, device="cuda")
+    wsb = torch.empty(K.sample_random_walk_workspace_bytes(max(1, n), Kn), dtype=torch.uint8, device="cuda")
+    ws = K.new_chain_ws()
+    K.sample_random_walk(gs.indptr, gs.indices, dev(seeds), n, None, L, p, W, Kn, K.rng(SEED, 21, 2), outs[0],
+                         outs[1], outs[2], outs[3], num, tmps[0], tmps[1], wsb, ws)
+    torch.cuda.synchronize()
+    m = int(num.item())
+    ts, td = oracle.random_walk(gs.indptr_np, gs.indices_np, seeds, L, p, W, SEED, 21, 2)
+    assert np.array_equal(host(tmps[0], n * W * L), ts)
+    live = ts != 0xFFFFFFFF
+    assert np.array_equal(host(tmps[1], n * W * L)[live], td[live])
+    es, ed, ew = oracle.topk(ts, td, seeds, W * L, Kn)
+    assert m == len(es)
+    assert np.array_equal(host(outs[0], m), es) and np.array_equal(host(outs[1], m), ed)
+    assert np.array_equal(host(outs[3], m), ew)
+    assert int(ws.abs().sum().item()) == 0
+
+
+# ---------------------------------------------------------------------------
+def test_full_batch_pipeline_matches_oracle_driver(K, oracle, gm):
+    """sample -> unique -> remap for 3 layers, all counts device-resident, one sync at the end;
+    compared with the numpy restatement of DoGPUSample (cuda_loops.cc:50-267)."""
+    from oracle.oracle import sample_batch_oracle
+    fanouts = [5, 10, 15]
+    seeds = pick_seeds(gm.indptr_np, 2000, 12)
+    exp = sample_batch_oracle(oracle, dict(indptr=gm.indptr_np, indices=gm.indices_np), seeds, fanouts, "khop2",
+                              SEED, 42)
+    bound = oracle.predict_num_nodes(len(seeds), fanouts)
+    ht = HT(K, bound)
+    ht.fill_unique(seeds)
+    ws = K.new_chain_ws()
+    cur, cur_n_dev, cur_max = ht.n2o, ht.num, len(seeds)
+    layers = [None] * 3
+    for i in (2, 1, 0):
+        f = fanouts[i]
+        cap = cur_max * f
+        dst = torch.empty(cap, dtype=torch.int32, device="cuda")
+        col = torch.empty(cap, dtype=torch.int32, device="cuda")
+        row = torch.empty(cap, dtype=torch.int32, device="cuda")
+        pos = torch.empty(cap, dtype=torch.int32, device="cuda")
+        ne = torch.zeros(1, dtype=torch.int32, device="cuda")
+        # layer input = the first *cur_n_dev entries of the running unique list
+        n_in = cur_n_dev.clone()
+        K.sample_khop(2, gm.indptr, gm.indices, cur, cur_max, n_in, f, K.rng(SEED, 42, i), None, dst, col, ne, ws)
+        K.ht_fill_duplicates(ht.table, ht.cap, dst, cap, ne, pos, ht.n2o, ht.num, ws)
+        K.ht_map(ht.table, ht.cap, None, pos, cap, ne, row)
+        layers[i] = (row, col, ne, n_in, ht.num.clone())
+        cur_max = min(bound, cur_max * (f + 1))
+    torch.cuda.synchronize()
+    for i in range(3):
+        row, col, ne, n_in, n_src = layers[i]
+        m = int(ne.item())
+        e = exp["layers"][i]
+        assert m == e["num_edge"] and int(n_in.item()) == e["num_dst"] and int(n_src.item()) == e["num_src"]
+        assert np.array_equal(host(row, m), e["row"]) and np.array_equal(host(col, m), e["col"])
+    assert np.array_equal(ht.unique(), exp["input_nodes"])
