@@ -252,7 +252,7 @@ def test_row_copy_extract(K, oracle, dtype, dim, n):
     out = torch.zeros((max(1, n), row_bytes), dtype=torch.uint8, device="cuda")
     K.row_copy(out, None, d_src, dev(idx), n, None, row_bytes)
     torch.cuda.synchronize()
-    got = out[:n].cpu().numpy().reshape(n, -1).view(dtype).reshape(n, dim)
+    got = out[:n].cpu().numpy().reshape(n, row_bytes).view(dtype).reshape(n, dim)
     assert np.array_equal(got.view(np.uint8), exp.view(np.uint8))
 
 
