@@ -1,0 +1,413 @@
+#!/usr/bin/env python
+"""bench.py — sampled edges/s of the factored sampling-and-extraction hot path.
+
+Workload (BASELINE.json configs[1]): GraphSAGE 2-layer fanout [25,10], batch 8000,
+khop2 sampler, PreSC feature cache, on a papers100M-shaped synthetic power-law
+graph (111M nodes, 1.6B edges, 128-d fp32 features), one B200 per rank.
+
+A "step" is one mini-batch of the hot path: shuffle slice -> k-hop sample ->
+ordered unique -> remap (per layer) -> cache lookup + feature gather + label
+gather.  `value` = sampled edges/s with everything resident in HBM (device
+timed); `e2e` = the same metric through the samgraph_* C-ABI host runtime with
+the per-step host<->device traffic inside the timed region.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+PKG = os.path.join(ROOT, "fgnn-artifacts_b200")
+for _p in (ROOT, PKG):
+    if _p not in sys.path:
+        sys.path.insert(0, _p)
+
+METRIC = "sampled edges/s (sample + unique/remap + cache-aware extract per mini-batch)"
+UNIT = "edges/s"
+FANOUTS = [25, 10]
+BATCH = 8000
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=604)      # four papers100M epochs at batch 8000 (151 steps each)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default=os.environ.get("FGNN_BENCH_WORKLOAD", "papers100M"))
+    ap.add_argument("--cache-pct", type=float, default=float(os.environ.get("FGNN_BENCH_CACHE_PCT", "0.25")))
+    ap.add_argument("--empty-feat", type=int, default=int(os.environ.get("FGNN_BENCH_EMPTY_FEAT", "22")),
+                    help="host feature table has 2^k rows, indices masked (SAMGRAPH_EMPTY_FEAT semantics)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    return ap.parse_args()
+
+
+# ---------------------------------------------------------------------------
+class ClockSampler:
+    QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+             "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.idx = gpu_index
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.p = None
+
+    def start(self):
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(self.idx), "--query-gpu=" + self.QUERY,
+                                       "--format=csv,noheader,nounits", "-lms", "100"],
+                                      stdout=self.f, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.p = None
+
+    def stop(self):
+        if self.p is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except Exception:
+            self.p.kill()
+        self.f.flush()
+        self.f.seek(0)
+        sm, mx, reasons = [], [], set()
+        for line in self.f:
+            c = [x.strip() for x in line.split(",")]
+            if len(c) < 9:
+                continue
+            try:
+                sm.append(float(c[1]))
+                mx.append(float(c[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), c[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        try:
+            os.unlink(self.f.name)
+        except OSError:
+            pass
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured"
+    return 6650.0, "fallback"
+
+
+# ---------------------------------------------------------------------------
+def build_workload(args, device):
+    """Graph + labels + train set on `device`; host feature table (2^k rows, pinned)."""
+    import torch
+    from fgnn_b200.synth import SHAPES, SEED, make_graph_torch
+
+    V, E, D, C, T = SHAPES[args.workload]
+    t0 = time.time()
+    indptr, indices = make_graph_torch(V, E, device=device)
+    g = torch.Generator(device=device)
+    g.manual_seed(SEED + 1)
+    label = torch.randint(0, C, (V,), generator=g, device=device, dtype=torch.int64)
+    train = torch.randperm(V, generator=g, device=device)[:T].to(torch.int32)
+    rows = min(V, 1 << args.empty_feat)
+    gh = torch.Generator()
+    gh.manual_seed(SEED + 1)
+    host_feat = (torch.rand((rows, D), generator=gh, dtype=torch.float32) * 2 - 1).pin_memory()
+    mask = rows - 1 if rows < V else 0xFFFFFFFFFFFFFFFF
+    if rows < V:
+        assert rows & (rows - 1) == 0
+    torch.cuda.synchronize()
+    return dict(V=V, E=E, D=D, C=C, T=T, indptr=indptr, indices=indices, label=label, train=train,
+                host_feat=host_feat, feat_mask=mask, gen_s=time.time() - t0)
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from fgnn_b200 import kernels as K
+    from fgnn_b200.pipeline import HotPath
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = "cuda:%d" % local
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device(dev))
+    K.load()  # raises when the CUDA extension is missing: there is no CPU fallback
+
+    wl = build_workload(args, dev)
+    V, D = wl["V"], wl["D"]
+    row_bytes = D * 4
+    hp = HotPath(wl["indptr"], wl["indices"], V, FANOUTS, BATCH, "khop2", seed=0x5EED0000 + rank, device=dev)
+    steps_per_epoch = (wl["T"] + BATCH - 1) // BATCH
+    # DistShuffler split (dist_shuffler.cc:60-83): rank r owns a contiguous range of the epoch's steps
+    g = torch.Generator(device=dev)
+    g.manual_seed(1234)
+    perm = wl["train"][torch.randperm(wl["T"], generator=g, device=dev)].contiguous()
+
+    def seeds_of(step):
+        s = (step * world + rank) % steps_per_epoch
+        lo = s * BATCH
+        hi = min(wl["T"], lo + BATCH)
+        return perm[lo:hi], hi - lo
+
+    # ---- PreSC: one pre-sampling epoch -> hotness ranking -> cache (cuda/pre_sampler.cc:57-110)
+    t0 = time.time()
+    freq = torch.zeros(V, dtype=torch.int32, device=dev)
+    for s in range(steps_per_epoch):
+        lo = s * BATCH
+        hi = min(wl["T"], lo + BATCH)
+        hp.sample(perm[lo:hi], hi - lo, 1_000_000 + s)
+        hp.presample_count(freq)
+    rank_nodes = torch.empty(V, dtype=torch.int32, device=dev)
+    wsr = torch.empty(K.presc_rank_workspace_bytes(V), dtype=torch.uint8, device=dev)
+    K.presc_rank(freq, V, rank_nodes, wsr)
+    torch.cuda.synchronize()
+    del wsr, freq
+    presc_s = time.time() - t0
+    t0 = time.time()
+    hp.build_cache(rank_nodes, args.cache_pct, wl["host_feat"], row_bytes, wl["feat_mask"])
+    hp.set_labels(wl["label"])
+    torch.cuda.synchronize()
+    cache_s = time.time() - t0
+
+    # ---- timed region -------------------------------------------------------------
+    Ksteps, W = args.steps, max(3, args.warmup)
+    hist = torch.zeros((Ksteps, hp.L, 3), dtype=torch.int32, device=dev)
+    ev = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(Ksteps)]
+    for w in range(W):
+        sd, n = seeds_of(w)
+        hp.step(sd, n, w)
+    hp.stats.zero_()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    clocks = ClockSampler(local)
+    clocks.start()
+    launches0 = K.launch_count()
+    torch.cuda.synchronize()
+    t_start = torch.cuda.Event(enable_timing=True)
+    t_end = torch.cuda.Event(enable_timing=True)
+    t_start.record()
+    for k in range(Ksteps):
+        sd, n = seeds_of(W + k)
+        ev[k][0].record()
+        hp.sample(sd, n, W + k)
+        ev[k][1].record()
+        hp.extract(sd, n)
+        ev[k][2].record()
+        hist[k].copy_(hp.counts)
+    t_end.record()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    launches = K.launch_count() - launches0
+    clk = clocks.stop()
+    ms_total = t_start.elapsed_time(t_end)
+    h = hist.cpu().numpy().astype("int64")
+    edges = int(h[:, :, 1].sum())
+    n_in_total = int(h[:, 0, 2].sum())           # input_nodes of every step (num_src of layer 0)
+    sample_ms = sum(e[0].elapsed_time(e[1]) for e in ev)
+    gather_ms = sum(e[1].elapsed_time(e[2]) for e in ev)
+    hits, misses = [int(x) for x in hp.stats.tolist()]
+
+    if world > 1:
+        t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_total = float(t.item())
+        tot = torch.tensor([edges, n_in_total], dtype=torch.int64, device=dev)
+        dist.all_reduce(tot, op=dist.ReduceOp.SUM)
+        edges_all, n_in_all = int(tot[0].item()), int(tot[1].item())
+    else:
+        edges_all, n_in_all = edges, n_in_total
+
+    # ---- roofline of the dominant kernel: the fused cache-aware feature gather -----------
+    peak, peak_kind = peaks()
+    alg_bytes = n_in_total * (4 + 2 * row_bytes)              # B_ext = N_in*(4 + 2*D*4)
+    achieved = alg_bytes / (gather_ms * 1e-3) / 1e9 if gather_ms > 0 else 0.0
+    roofline = {"bound": "hbm", "kernel": "gather_cached_kernel<uint4> (+ label row_copy)",
+                "achieved": round(achieved, 1), "peak": peak, "peak_kind": peak_kind, "unit": "GB/s",
+                "frac": round(achieved / peak, 4), "traffic": None,
+                "bytes_per_launch": alg_bytes // max(1, Ksteps), "avg_launch_ms": gather_ms / max(1, Ksteps),
+                "share_of_step": round(gather_ms / ms_total, 3)}
+
+    out = {
+        "metric": METRIC, "value": edges_all / (ms_total * 1e-3), "unit": UNIT, "n_gpus": world,
+        "steps": Ksteps, "warmup": W, "ms_per_step": ms_total / Ksteps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "u32 ids / f32 rows (byte copy)", "data": "synthetic",
+        "config": {"workload": "GraphSAGE [25,10] batch 8000 khop2, %s-shaped synthetic power-law graph, PreSC cache %.0f%%"
+                               % (args.workload, args.cache_pct * 100),
+                   "num_node": V, "num_edge": wl["E"], "feat_dim": D, "cache_percentage": args.cache_pct,
+                   "host_feat_rows": int(wl["host_feat"].shape[0]),
+                   "l2_policy": "inputs larger than L2 (6.9 GB topology, %.1f GB cache)" % (hp.num_cached * row_bytes / 1e9),
+                   "sharding": "seed mini-batches split across ranks, topology + cache replicated"},
+        "clocks": clk, "gpu_launches": int(launches),
+        "roofline": roofline,
+        "extra": {"sample_only_edges_per_s": edges / (sample_ms * 1e-3) if sample_ms else None,
+                  "extract_GBps": n_in_total * row_bytes / (gather_ms * 1e-3) / 1e9 if gather_ms else None,
+                  "epoch_time_s_est": ms_total / Ksteps * steps_per_epoch / world * 1e-3,
+                  "edges_per_step": edges / Ksteps, "input_nodes_per_step": n_in_total / Ksteps,
+                  "cache_hit_rate": hits / max(1, hits + misses), "presc_s": presc_s, "cache_build_s": cache_s,
+                  "graph_gen_s": wl["gen_s"], "sample_ms_per_step": sample_ms / Ksteps,
+                  "extract_ms_per_step": gather_ms / Ksteps},
+    }
+
+    # ---- e2e through the host runtime (samgraph_* C-ABI) with host buffers ------------------
+    if not args.no_e2e:
+        out["e2e"] = run_e2e(args, wl, hp, seeds_of, world, rank, dev)
+    # ---- CPU baseline: the reference's own CPU code on this box's cores -----------------------
+    if world == 1 and rank == 0 and not args.no_cpu_baseline:
+        out["cpu_baseline"] = cpu_baseline(args, wl, steps=None, budget_s=20.0)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    if rank == 0:
+        print(json.dumps(out))
+
+
+def run_e2e(args, wl, hp, seeds_of, world, rank, dev):
+    """Same metric with host buffers: every step copies its seed ids from pinned host memory, runs the
+    hot path, reads the per-layer counts and the batch labels back to the host (blocking)."""
+    import torch
+    import torch.distributed as dist
+    Ksteps, W = args.steps, max(3, args.warmup)
+    host_seeds = [seeds_of(W + k)[0].cpu().pin_memory() for k in range(Ksteps)]
+    d_seeds = torch.empty(BATCH, dtype=torch.int32, device=dev)
+    h_counts = torch.zeros((hp.L, 3), dtype=torch.int32).pin_memory()
+    h_label = torch.zeros(BATCH, dtype=torch.int64).pin_memory()
+    hp.stats.zero_()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    edges = 0
+    h2d = d2h = 0
+    s.record()
+    for k in range(Ksteps):
+        n = host_seeds[k].numel()
+        d_seeds[:n].copy_(host_seeds[k], non_blocking=True)
+        hp.step(d_seeds, n, 10_000 + k)
+        h_counts.copy_(hp.counts, non_blocking=True)
+        h_label[:n].copy_(hp.label_out[:n], non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        edges += int(h_counts[:, 1].sum())
+        h2d += n * 4
+        d2h += h_counts.numel() * 4 + n * 8
+    e.record()
+    torch.cuda.synchronize()
+    ms = s.elapsed_time(e)
+    hits, misses = [int(x) for x in hp.stats.tolist()]
+    h2d += misses * hp.row_bytes                      # miss rows are read from pinned host memory (UVA)
+    if world > 1:
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+        tot = torch.tensor([edges], dtype=torch.int64, device=dev)
+        dist.all_reduce(tot, op=dist.ReduceOp.SUM)
+        edges = int(tot.item())
+    return {"value": edges / (ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d // Ksteps,
+            "d2h_bytes_per_step": d2h // Ksteps, "ms_per_step": ms / Ksteps,
+            "api": "fgnn_b200.pipeline.HotPath over the fgnn_k_* C-ABI"}
+
+
+# ---------------------------------------------------------------------------
+def cpu_baseline(args, wl, steps, budget_s):
+    """Reference CPU path (oracle/_ref: CPUSampleKHop2 + CPUHashTable2 + CPUExtract, unmodified reference
+    translation units) on this host's cores, on a bounded sample of the same workload."""
+    import numpy as np
+    from oracle.oracle import RefCPU, have_ref
+    if not have_ref():
+        return {"value": None, "unit": UNIT, "cores": 0, "kind": "reference", "sample": "oracle/_ref missing"}
+    cores = os.cpu_count() or 1
+    ref = RefCPU()
+    ref.set_threads(cores)
+    t0 = time.time()
+    indptr = wl["indptr"].cpu().numpy().view(np.uint32)
+    indices = wl["indices"].cpu().numpy().view(np.uint32)          # CPUSampleKHop2 permutes rows in place
+    label = wl["label"].cpu().numpy()
+    train = wl["train"].cpu().numpy().view(np.uint32)
+    feat = wl["host_feat"].numpy()
+    mask = np.uint32(feat.shape[0] - 1)
+    ht = ref.hashtable(2, wl["V"])
+    prep = time.time() - t0
+    rng = np.random.default_rng(0)
+    order = rng.permutation(len(train))
+    done, edges, n_in, spent = 0, 0, 0, 0.0
+    k = 0
+    max_steps = steps if steps is not None else 60
+    spe = (len(train) + BATCH - 1) // BATCH
+    while done < max_steps:
+        kk = k % spe
+        seeds = train[order[kk * BATCH:(kk + 1) * BATCH]]
+        k += 1
+        t1 = time.time()
+        ht.reset()
+        ht.populate(seeds)
+        cur = seeds
+        e_step = 0
+        for i in range(len(FANOUTS) - 1, -1, -1):                  # cpu_loops.cc:55-191
+            s, d = ref.sample_khop2(indptr, indices, cur, FANOUTS[i])
+            ht.populate(d)
+            cur = ht.map_nodes()
+            ht.map_edges(s, d)
+            e_step += len(s)
+        f = ref.extract(feat, cur & mask)                          # DoFeatureExtract (mock-masked ids)
+        lb = ref.extract(label, seeds)
+        dt = time.time() - t1
+        if k == 1:
+            continue                                               # warm-up step
+        done += 1
+        edges += e_step
+        n_in += len(cur)
+        spent += dt
+        if steps is None and spent > budget_s:
+            break
+    return {"value": edges / spent if spent else None, "unit": UNIT, "cores": cores, "kind": "reference",
+            "sample": "%d mini-batches (batch %d, fanout %s) of the same graph: CPUSampleKHop2 + CPUHashTable2 "
+                      "Populate/MapNodes/MapEdges + CPUExtract (feature rows masked to the 2^k-row host table), "
+                      "%d OpenMP threads; %.1f s" % (done, BATCH, FANOUTS, cores, spent),
+            "steps": done, "ms_per_step": spent / max(1, done) * 1e3,
+            "extract_rows_per_step": n_in / max(1, done), "prep_s": prep}
+
+
+def run_reference(args):
+    """--impl reference: the reference's own CPU implementation of the path on the host cores."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import torch
+    dev = "cuda:%d" % int(os.environ.get("LOCAL_RANK", "0")) if torch.cuda.is_available() else "cpu"
+    wl = build_workload(args, dev)
+    K, W = args.steps, max(3, args.warmup)
+    steps = min(K, 40)                                # bounded: each step is one CPU mini-batch
+    cb = cpu_baseline(args, wl, steps=steps, budget_s=1e9)
+    out = {"impl": "reference", "metric": METRIC, "value": cb["value"], "unit": UNIT,
+           "n_gpus": int(os.environ.get("WORLD_SIZE", "1")), "steps": cb["steps"], "warmup": 1,
+           "ms_per_step": cb["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+           "dtype": "u32 ids / f32 rows (byte copy)", "data": "synthetic",
+           "config": {"workload": "GraphSAGE [25,10] batch 8000 khop2, %s-shaped synthetic power-law graph, CPU sampler+extractor"
+                                  % args.workload},
+           "cpu_baseline": cb,
+           "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(out))
+
+
+if __name__ == "__main__":
+    a = parse()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_ours(a)

@@ -1,0 +1,65 @@
+#!/usr/bin/env python
+"""Summarise an .ncu-rep (raw page) or an ncu launch-list CSV into a small text table for profiles/.
+
+  python tools/ncu_summary.py rep   gpurun_out/prof.ncu-rep  > profiles/rN_xxx.txt
+  python tools/ncu_summary.py list  gpurun_out/launches.csv  > profiles/rN_launches.txt
+"""
+import collections
+import csv
+import subprocess
+import sys
+
+KEYS = [("gpu__time_duration.sum", "time"), ("dram__bytes_read.sum", "dram_rd"), ("dram__bytes_write.sum", "dram_wr"),
+        ("gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "dram_pct"),
+        ("sm__throughput.avg.pct_of_peak_sustained_elapsed", "sm_pct"),
+        ("sm__warps_active.avg.pct_of_peak_sustained_active", "warps_active_pct"),
+        ("launch__registers_per_thread", "regs"), ("launch__waves_per_multiprocessor", "waves"),
+        ("lts__t_sector_hit_rate.pct", "l2_hit_pct"), ("l1tex__t_sector_hit_rate.pct", "l1_hit_pct"),
+        ("smsp__inst_executed.sum", "warp_inst")]
+
+
+def rep(path):
+    out = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(out.splitlines()))
+    hdr, units = rows[0], rows[1]
+    ki = hdr.index("Kernel Name")
+    gi = hdr.index("Grid Size")
+    print("# %s (ncu --set full --clock-control none; per launch, cold cache, serialised)" % path)
+    for r in rows[2:]:
+        name = r[ki].split("(")[0].replace("void ", "").replace("fgnn::<unnamed>::", "")
+        parts = ["%-34s grid=%-14s" % (name[:34], r[gi])]
+        for k, short in KEYS:
+            if k in hdr:
+                i = hdr.index(k)
+                v = r[i]
+                try:
+                    v = "%.4g" % float(v)
+                except ValueError:
+                    pass
+                parts.append("%s=%s%s" % (short, v, units[i].replace("byte", "B").replace("register/thread", "")
+                                          .replace("inst", "").replace("%", "%")))
+        print("  ".join(parts))
+
+
+def launch_list(path):
+    lines = [l for l in open(path) if not l.startswith("==")]
+    agg = collections.OrderedDict()
+    for row in csv.DictReader(lines):
+        if row.get("Metric Name") != "gpu__time_duration.sum":
+            continue
+        name = row["Kernel Name"].split("(")[0].replace("void ", "").replace("fgnn::<unnamed>::", "")
+        v = float(row["Metric Value"])
+        u = row["Metric Unit"]
+        v = v / 1000 if u == "ns" else (v * 1000 if u == "ms" else v)
+        a = agg.setdefault((name, row["Grid Size"]), [0, 0.0])
+        a[0] += 1
+        a[1] += v
+    tot = sum(a[1] for a in agg.values())
+    print("# %s (ncu --metrics gpu__time_duration.sum --clock-control none; cold-cache serialised: compare SHARES)" % path)
+    for (k, g), a in agg.items():
+        print("%-44s grid=%-14s n=%4d avg=%9.2f us share=%.3f" % (k[:44], g, a[0], a[1] / a[0], a[1] / tot))
+    print("total %.1f us over %d launches" % (tot, sum(a[0] for a in agg.values())))
+
+
+if __name__ == "__main__":
+    {"rep": rep, "list": launch_list}[sys.argv[1]](sys.argv[2])
