@@ -24,6 +24,15 @@ inline int check_last() {
   return (int)e;
 }
 
+// resident CTAs per SM for a kernel (cached by the caller in a static)
+template <typename Kern>
+inline int occupancy(Kern kern, int block, size_t smem) {
+  int occ = 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, block, smem) != cudaSuccess || occ < 1)
+    occ = 1;
+  return occ;
+}
+
 // persistent grid: enough CTAs to cover n_max at `min_items` per CTA, capped
 // at sm_count * ctas_per_sm (and the chain limit when chained).
 inline int persistent_grid(uint64_t n_max, uint32_t min_items, int ctas_per_sm,
@@ -130,7 +139,8 @@ __device__ __forceinline__ uint32_t warp_incl_scan(uint32_t v) {
 }
 
 // exclusive scan over the block; returns this thread's exclusive prefix and
-// the block total through *total.  `s_warp` = kBlock/32 + 1 words of smem.
+// the block total through *total.  `s_warp` = NT/32 + 1 words of smem.
+template <int NT = kBlock>
 __device__ __forceinline__ uint32_t block_excl_scan(uint32_t v, uint32_t *s_warp,
                                                     uint32_t *total) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -139,16 +149,17 @@ __device__ __forceinline__ uint32_t block_excl_scan(uint32_t v, uint32_t *s_warp
   if (lane == 31) s_warp[warp] = incl;
   __syncthreads();
   if (warp == 0) {
-    uint32_t w = lane < (kBlock / 32) ? s_warp[lane] : 0u;
+    uint32_t w = lane < (NT / 32) ? s_warp[lane] : 0u;
     uint32_t wi = warp_incl_scan(w);
-    if (lane < (kBlock / 32)) s_warp[lane] = wi - w;
-    if (lane == (kBlock / 32) - 1) s_warp[kBlock / 32] = wi;
+    if (lane < (NT / 32)) s_warp[lane] = wi - w;
+    if (lane == (NT / 32) - 1) s_warp[NT / 32] = wi;
   }
   __syncthreads();
-  *total = s_warp[kBlock / 32];
+  *total = s_warp[NT / 32];
   return s_warp[warp] + incl - v;
 }
 
+template <int NT = kBlock>
 __device__ __forceinline__ unsigned long long block_sum_u64(
     unsigned long long v, unsigned long long *s_warp64) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -159,7 +170,7 @@ __device__ __forceinline__ unsigned long long block_sum_u64(
   __syncthreads();
   unsigned long long t = 0;
 #pragma unroll
-  for (int w = 0; w < kBlock / 32; ++w) t += s_warp64[w];
+  for (int w = 0; w < NT / 32; ++w) t += s_warp64[w];
   return t;
 }
 
@@ -195,13 +206,14 @@ __device__ __forceinline__ uint32_t chain_ticket(ChainWs *ws, ChainSmem *sm) {
 
 // all threads pass their partial; returns exclusive prefix over lower tickets
 // and publishes this chunk's aggregate.
+template <int NT = kBlock>
 __device__ __forceinline__ unsigned long long chain_scan(
     ChainWs *ws, ChainSmem *sm, uint32_t p, unsigned long long thread_partial,
     unsigned long long *chunk_total) {
-  const unsigned long long total = block_sum_u64(thread_partial, sm->warp64);
+  const unsigned long long total = block_sum_u64<NT>(thread_partial, sm->warp64);
   if (threadIdx.x == 0) st_relaxed_u64(&ws->agg[p], (1ull << 63) | total);
   unsigned long long sum = 0;
-  for (uint32_t t = threadIdx.x; t < p; t += kBlock) {
+  for (uint32_t t = threadIdx.x; t < p; t += NT) {
     unsigned long long v;
     do {
       v = ld_relaxed_u64(&ws->agg[t]);
@@ -209,9 +221,10 @@ __device__ __forceinline__ unsigned long long chain_scan(
     sum += v & ~(1ull << 63);
   }
   *chunk_total = total;
-  return block_sum_u64(sum, sm->warp64);
+  return block_sum_u64<NT>(sum, sm->warp64);
 }
 
+template <int NT = kBlock>
 __device__ __forceinline__ void chain_finish(ChainWs *ws, ChainSmem *sm) {
   __syncthreads();
   if (threadIdx.x == 0) {
@@ -221,7 +234,7 @@ __device__ __forceinline__ void chain_finish(ChainWs *ws, ChainSmem *sm) {
   }
   __syncthreads();
   if (sm->last) {
-    for (uint32_t t = threadIdx.x; t < gridDim.x; t += kBlock) ws->agg[t] = 0ull;
+    for (uint32_t t = threadIdx.x; t < gridDim.x; t += NT) ws->agg[t] = 0ull;
     if (threadIdx.x == 0) {
       ws->ticket = 0u;
       ws->done = 0u;

@@ -140,9 +140,10 @@ inline int vec_width(size_t row_bytes, const void *a, const void *b, const void 
   return 1;
 }
 
-inline int copy_grid(uint64_t chunks) {
-  // 8 resident CTAs/SM x 4 chunks in flight per thread
-  return persistent_grid(chunks, kBlock * kUnroll, 8, false);
+// exactly one resident wave (ncu r1_a: a fixed 8 CTAs/SM grid ran 1.33 waves
+// because only 6 CTAs of the 40-register uint4 kernel fit -> 25 % tail)
+inline int copy_grid(uint64_t chunks, int occ) {
+  return persistent_grid(chunks, kBlock * kUnroll, occ, false);
 }
 
 }  // namespace
@@ -158,10 +159,13 @@ extern "C" int fgnn_k_row_copy(void *dst, const uint32_t *dst_index, const void 
   cudaStream_t st = (cudaStream_t)stream;
   const int w = vec_width(row_bytes, dst, src);
   const uint32_t cpr = (uint32_t)(row_bytes / w);
-  const int grid = copy_grid((uint64_t)n_max * cpr);
 #define FGNN_RC(V)                                                                              \
-  row_copy_kernel<V><<<grid, kBlock, 0, st>>>((char *)dst, dst_index, (const char *)src,        \
-                                              src_index, src_mask, n_max, d_n, row_bytes, cpr)
+  do {                                                                                          \
+    static const int occ = occupancy(row_copy_kernel<V>, kBlock, 0);                            \
+    const int grid = copy_grid((uint64_t)n_max * cpr, occ);                                     \
+    row_copy_kernel<V><<<grid, kBlock, 0, st>>>((char *)dst, dst_index, (const char *)src,      \
+                                                src_index, src_mask, n_max, d_n, row_bytes, cpr); \
+  } while (0)
   if (w == 16) FGNN_RC(uint4);
   else if (w == 8) FGNN_RC(uint2);
   else if (w == 4) FGNN_RC(uint32_t);
@@ -182,11 +186,14 @@ extern "C" int fgnn_k_gather_cached(void *out, const uint32_t *nodes, uint32_t n
   // shard bases are cudaMalloc'ed (256-B aligned); only out/miss_src/row_bytes decide
   const int w = vec_width(row_bytes, out, miss_src);
   const uint32_t cpr = (uint32_t)(row_bytes / w);
-  const int grid = copy_grid((uint64_t)n_max * cpr);
 #define FGNN_GC(V)                                                                               \
-  gather_cached_kernel<V><<<grid, kBlock, 0, st>>>((char *)out, nodes, n_max, d_n, table, shards, \
-                                                   num_shards, (const char *)miss_src, miss_mask, \
-                                                   row_bytes, cpr, d_stats)
+  do {                                                                                           \
+    static const int occ = occupancy(gather_cached_kernel<V>, kBlock, 0);                        \
+    const int grid = copy_grid((uint64_t)n_max * cpr, occ);                                      \
+    gather_cached_kernel<V><<<grid, kBlock, 0, st>>>((char *)out, nodes, n_max, d_n, table,      \
+                                                     shards, num_shards, (const char *)miss_src, \
+                                                     miss_mask, row_bytes, cpr, d_stats);        \
+  } while (0)
   if (w == 16) FGNN_GC(uint4);
   else if (w == 8) FGNN_GC(uint2);
   else if (w == 4) FGNN_GC(uint32_t);

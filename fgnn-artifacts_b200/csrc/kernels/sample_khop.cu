@@ -201,6 +201,151 @@ sample_khop_kernel(const uint32_t *__restrict__ indptr, const uint32_t *__restri
   chain_finish(ws, &sm.chain);
 }
 
+// ---------------------------------------------------------------------------
+// variant 2, production path: thread-per-seed Fisher-Yates.
+//
+// The warp-cooperative selection above costs a chain of dependent shuffles per
+// step and processes a warp's 32 seeds one after another (ncu r1_a: 48-52 us for
+// 8k and 100k seeds alike, 12-27 % warps active).  Here every thread runs the
+// f-step virtual Fisher-Yates of its own seed against a per-thread (key,value)
+// log in shared memory ([step][thread] layout, conflict free): ~f^2/2 LDS pairs
+// with no cross-lane dependency, 32 seeds per warp in flight.  The neighbour
+// gather stays edge-parallel (coalesced compact writes, 4 loads in flight per
+// thread).  Tiles are NT seeds (64 or 128) so small layers still spread over
+// the whole chip.
+// ---------------------------------------------------------------------------
+template <int NT>
+struct Tile2Smem {
+  uint32_t rid[NT];
+  uint32_t off[NT];
+  uint32_t deg[NT];
+  uint32_t out[NT + 1];
+  uint32_t warp[NT / 32 + 1];
+  ChainSmem chain;
+};
+
+template <int NT>
+__global__ void __launch_bounds__(NT)
+sample_khop2_kernel(const uint32_t *__restrict__ indptr, const uint32_t *__restrict__ indices,
+                    const uint32_t *__restrict__ input, uint32_t n_max,
+                    const uint32_t *__restrict__ d_n, uint32_t fanout, RngKey key,
+                    uint32_t *__restrict__ out_src, uint32_t *__restrict__ out_dst,
+                    uint32_t *__restrict__ out_src_local, uint32_t *__restrict__ d_num_out,
+                    ChainWs *ws) {
+  extern __shared__ uint32_t dyn[];
+  __shared__ Tile2Smem<NT> sm;
+  const uint32_t fs = fanout | 1u;            // odd row stride: conflict-free [seed][j]
+  uint32_t *s_choice = dyn;                   // [NT][fs]
+  uint32_t *s_mkey = dyn + NT * fs;           // [fanout][NT]
+  uint32_t *s_mval = s_mkey + NT * fanout;    // [fanout][NT]
+
+  const uint32_t n = load_count(n_max, d_n);
+  const uint32_t p = chain_ticket(ws, &sm.chain);
+  uint32_t begin, end;
+  chunk_range(n, p, gridDim.x, NT, &begin, &end);
+
+  unsigned long long partial = 0;
+  for (uint32_t i = begin + threadIdx.x; i < end; i += NT) {
+    const uint32_t v = __ldg(input + i);
+    const uint32_t deg = __ldg(indptr + v + 1) - __ldg(indptr + v);
+    partial += deg < fanout ? deg : fanout;
+  }
+  unsigned long long chunk_total;
+  unsigned long long base = chain_scan<NT>(ws, &sm.chain, p, partial, &chunk_total);
+  if (p == gridDim.x - 1 && threadIdx.x == 0) *d_num_out = (uint32_t)(base + chunk_total);
+
+  const uint32_t tid = threadIdx.x;
+  for (uint32_t t0 = begin; t0 < end; t0 += NT) {
+    const uint32_t i = t0 + tid;
+    uint32_t cnt = 0, deg = 0;
+    if (i < end) {
+      const uint32_t v = __ldg(input + i);
+      const uint32_t o = __ldg(indptr + v);
+      deg = __ldg(indptr + v + 1) - o;
+      sm.rid[tid] = v;
+      sm.off[tid] = o;
+      cnt = deg < fanout ? deg : fanout;
+    }
+    sm.deg[tid] = deg;
+    uint32_t tile_total;
+    const uint32_t excl = block_excl_scan<NT>(cnt, sm.warp, &tile_total);
+    sm.out[tid] = excl;
+    if (tid == NT - 1) sm.out[NT] = tile_total;
+
+    uint32_t *choice = s_choice + tid * fs;
+    if (deg > fanout) {  // cuda_sampling_khop2.cu:72-83 on a virtual copy of the row
+      uint4 blk = make_uint4(0, 0, 0, 0);
+      for (uint32_t j = 0; j < fanout; ++j) {
+        if ((j & 3u) == 0) blk = philox_block(key, i, j >> 2);
+        const uint32_t k = pick_word(blk, j & 3u) % (deg - j);
+        const uint32_t last = deg - j - 1;
+        uint32_t vk = k, vlast = last;
+#pragma unroll 4
+        for (uint32_t t = 0; t < j; ++t) {  // latest write wins
+          const uint32_t kk = s_mkey[t * NT + tid];
+          const uint32_t vv = s_mval[t * NT + tid];
+          if (kk == k) vk = vv;
+          if (kk == last) vlast = vv;
+        }
+        s_mkey[j * NT + tid] = k;
+        s_mval[j * NT + tid] = vlast;
+        choice[j] = vk;
+      }
+    } else {
+      for (uint32_t j = 0; j < cnt; ++j) choice[j] = j;
+    }
+    __syncthreads();
+
+    for (uint32_t e0 = tid; e0 < tile_total; e0 += NT * 4) {
+      uint32_t nbr[4], ss[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const uint32_t e = e0 + u * NT;
+        ss[u] = kEmpty;
+        if (e < tile_total) {
+          uint32_t lo = 0, hi = NT;
+          while (hi - lo > 1) {
+            const uint32_t mid = (lo + hi) >> 1;
+            if (sm.out[mid] <= e) lo = mid; else hi = mid;
+          }
+          const uint32_t k = s_choice[lo * fs + (e - sm.out[lo])];
+          nbr[u] = __ldg(indices + (size_t)sm.off[lo] + k);
+          ss[u] = lo;
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        if (ss[u] != kEmpty) {
+          const size_t o = (size_t)base + e0 + u * NT;
+          out_dst[o] = nbr[u];
+          if (out_src) out_src[o] = sm.rid[ss[u]];
+          if (out_src_local) out_src_local[o] = t0 + ss[u];
+        }
+      }
+    }
+    base += tile_total;
+    __syncthreads();
+  }
+  chain_finish<NT>(ws, &sm.chain);
+}
+
+template <int NT>
+int launch2(const uint32_t *indptr, const uint32_t *indices, const uint32_t *input, uint32_t n_max,
+            const uint32_t *d_n, uint32_t fanout, RngKey key, uint32_t *out_src, uint32_t *out_dst,
+            uint32_t *out_src_local, uint32_t *d_num_out, void *chain_ws, cudaStream_t stream) {
+  const size_t smem = ((size_t)NT * (fanout | 1u) + 2 * (size_t)NT * fanout) * sizeof(uint32_t);
+  auto kern = sample_khop2_kernel<NT>;
+  if (smem > 48 * 1024) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+  }
+  const int grid = persistent_grid(n_max, NT, occupancy(kern, NT, smem), true);
+  kern<<<grid, NT, smem, stream>>>(indptr, indices, input, n_max, d_n, fanout, key, out_src, out_dst,
+                                   out_src_local, d_num_out, (ChainWs *)chain_ws);
+  note_launch();
+  return check_last();
+}
+
 template <int VARIANT, int NS>
 int launch(const uint32_t *indptr, const uint32_t *indices, const uint32_t *input,
            uint32_t n_max, const uint32_t *d_n, uint32_t fanout, RngKey key,
@@ -241,6 +386,15 @@ extern "C" int fgnn_k_sample_khop(int variant, const uint32_t *indptr, const uin
   return launch<V, NS>(indptr, indices, input, n_max, d_n, fanout, key, out_src, out_dst,   \
                        out_src_local, d_num_out, chain_ws, st)
   if (variant == 2) {
+    // thread-per-seed Fisher-Yates; 64-seed tiles when the layer is small or the
+    // per-thread log would not fit next to a 128-seed tile
+    const bool small = (uint64_t)n_max <= (uint64_t)sm_count() * 128ull || fanout > 48;
+    if (small)
+      return launch2<64>(indptr, indices, input, n_max, d_n, fanout, key, out_src, out_dst,
+                         out_src_local, d_num_out, chain_ws, st);
+    return launch2<128>(indptr, indices, input, n_max, d_n, fanout, key, out_src, out_dst,
+                        out_src_local, d_num_out, chain_ws, st);
+  } else if (variant == 22) {  // warp-cooperative Fisher-Yates (kept for A/B profiling)
     if (fanout <= 32) FGNN_GO(2, 1);
     if (fanout <= 64) FGNN_GO(2, 2);
     FGNN_GO(2, 4);
