@@ -1,4 +1,6 @@
 // Library-level entry points of the kernel C-ABI.
+#include <string.h>
+
 #include "common.cuh"
 
 namespace fgnn {
@@ -28,4 +30,39 @@ extern "C" const char *fgnn_k_error_string(int code) {
   if (code == FGNN_ERR_UNSUPPORTED) return "fgnn: unsupported configuration";
   if (code > 0) return cudaGetErrorString((cudaError_t)code);
   return "fgnn: unknown error";
+}
+
+// ---- device-memory plumbing for partitioned cache shards ----------------------------------
+extern "C" int fgnn_k_shard_alloc(void **ptr, size_t bytes) {
+  if (!ptr) return FGNN_ERR_BAD_ARG;
+  return (int)cudaMalloc(ptr, bytes ? bytes : 256);  // plain cudaMalloc: exportable through CUDA IPC
+}
+extern "C" int fgnn_k_shard_free(void *ptr) { return (int)cudaFree(ptr); }
+extern "C" int fgnn_k_ipc_export(void *ptr, void *handle64) {
+  if (!ptr || !handle64) return FGNN_ERR_BAD_ARG;
+  static_assert(sizeof(cudaIpcMemHandle_t) == FGNN_IPC_HANDLE_BYTES, "ipc handle size");
+  return (int)cudaIpcGetMemHandle((cudaIpcMemHandle_t *)handle64, ptr);
+}
+extern "C" int fgnn_k_ipc_open(const void *handle64, void **ptr) {
+  if (!ptr || !handle64) return FGNN_ERR_BAD_ARG;
+  cudaIpcMemHandle_t h;
+  memcpy(&h, handle64, sizeof(h));
+  return (int)cudaIpcOpenMemHandle(ptr, h, cudaIpcMemLazyEnablePeerAccess);
+}
+extern "C" int fgnn_k_ipc_close(void *ptr) { return (int)cudaIpcCloseMemHandle(ptr); }
+extern "C" int fgnn_k_enable_peer(int peer_device) {
+  int cur = 0;
+  cudaError_t e = cudaGetDevice(&cur);
+  if (e != cudaSuccess) return (int)e;
+  if (cur == peer_device) return 0;
+  int can = 0;
+  e = cudaDeviceCanAccessPeer(&can, cur, peer_device);
+  if (e != cudaSuccess) return (int)e;
+  if (!can) return FGNN_ERR_UNSUPPORTED;
+  e = cudaDeviceEnablePeerAccess(peer_device, 0);
+  if (e == cudaErrorPeerAccessAlreadyEnabled) {
+    cudaGetLastError();
+    return 0;
+  }
+  return (int)e;
 }

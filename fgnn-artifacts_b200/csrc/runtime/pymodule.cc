@@ -1,0 +1,163 @@
+// Python module `samgraph.torch.c_lib`: the tensor hand-off of the reference's pybind adapter
+// (samgraph/torch/adapter.cc:48-192) without compiling against torch.  Every getter returns a
+// DLPack capsule that aliases the engine's buffer (zero copy); samgraph/torch/adapter.py turns it
+// into a torch.Tensor with torch.from_dlpack.  Ownership follows adapter.cc:54-62: the capsule
+// keeps the engine Tensor alive until Python drops the torch tensor, then the memory returns to
+// the stream-ordered pool.
+#define PY_SSIZE_T_CLEAN
+#include <Python.h>
+
+#include "rt_engine.h"
+
+using namespace fgnn::rt;
+
+namespace {
+
+// ---- DLPack v0.8 ABI (dlpack.h), declared locally: the structs are a stable C ABI ----
+typedef enum { kDLCPU = 1, kDLCUDA = 2, kDLCUDAHost = 3 } DLDeviceType;
+typedef struct { int32_t device_type; int32_t device_id; } DLDevice;
+typedef struct { uint8_t code; uint8_t bits; uint16_t lanes; } DLDataType;
+typedef struct {
+  void *data;
+  DLDevice device;
+  int32_t ndim;
+  DLDataType dtype;
+  int64_t *shape;
+  int64_t *strides;
+  uint64_t byte_offset;
+} DLTensor;
+typedef struct DLManagedTensor {
+  DLTensor dl_tensor;
+  void *manager_ctx;
+  void (*deleter)(struct DLManagedTensor *self);
+} DLManagedTensor;
+
+struct Holder {
+  TensorPtr tensor;
+  TaskPtr task;  // keeps the `ready` event and sibling tensors valid
+  int64_t shape[4];
+};
+
+void ManagedDeleter(DLManagedTensor *self) {
+  delete static_cast<Holder *>(self->manager_ctx);
+  delete self;
+}
+
+void CapsuleDestructor(PyObject *cap) {
+  // consumed capsules are renamed "used_dltensor" by the importer and must not be freed here
+  if (!PyCapsule_IsValid(cap, "dltensor")) return;
+  auto *m = static_cast<DLManagedTensor *>(PyCapsule_GetPointer(cap, "dltensor"));
+  if (m && m->deleter) m->deleter(m);
+}
+
+PyObject *ToCapsule(const TensorPtr &t, const TaskPtr &task, DataType view_as) {
+  if (!t || (!t->data && t->nbytes)) {
+    PyErr_SetString(PyExc_RuntimeError, "samgraph: tensor is not available for this batch");
+    return nullptr;
+  }
+  auto *h = new Holder();
+  h->tensor = t;
+  h->task = task;
+  auto *m = new DLManagedTensor();
+  m->dl_tensor.data = t->data;
+  m->dl_tensor.device.device_type = (t->ctx.device_type == kGPU) ? kDLCUDA : kDLCPU;
+  m->dl_tensor.device.device_id = (t->ctx.device_type == kGPU) ? t->ctx.device_id : 0;
+  m->dl_tensor.ndim = (int32_t)t->shape.size();
+  for (size_t i = 0; i < t->shape.size() && i < 4; ++i) h->shape[i] = (int64_t)t->shape[i];
+  m->dl_tensor.shape = h->shape;
+  m->dl_tensor.strides = nullptr;
+  m->dl_tensor.byte_offset = 0;
+  DLDataType dt;
+  dt.lanes = 1;
+  switch (view_as) {
+    case kF32: dt.code = 2; dt.bits = 32; break;
+    case kF64: dt.code = 2; dt.bits = 64; break;
+    case kF16: dt.code = 2; dt.bits = 16; break;
+    case kU8: dt.code = 1; dt.bits = 8; break;
+    case kI8: dt.code = 0; dt.bits = 8; break;
+    case kI32: dt.code = 0; dt.bits = 32; break;   // ids are exposed as int32, like adapter.cc (kI32)
+    case kI64: dt.code = 0; dt.bits = 64; break;
+  }
+  m->dl_tensor.dtype = dt;
+  m->manager_ctx = h;
+  m->deleter = ManagedDeleter;
+  return PyCapsule_New(m, "dltensor", CapsuleDestructor);
+}
+
+TaskPtr Batch(unsigned long long key) {
+  TaskPtr b = Engine::Get()->CurrentBatch();
+  if (!b) {
+    PyErr_SetString(PyExc_RuntimeError, "samgraph: no current batch (call get_next_batch first)");
+    return nullptr;
+  }
+  FCHECK_EQ((uint64_t)key, b->key);  // adapter.cc:54
+  return b;
+}
+
+PyObject *GetGraphFeat(PyObject *, PyObject *args) {
+  unsigned long long key;
+  if (!PyArg_ParseTuple(args, "K", &key)) return nullptr;
+  TaskPtr b = Batch(key);
+  return b ? ToCapsule(b->input_feat, b, kF32) : nullptr;
+}
+PyObject *GetGraphLabel(PyObject *, PyObject *args) {
+  unsigned long long key;
+  if (!PyArg_ParseTuple(args, "K", &key)) return nullptr;
+  TaskPtr b = Batch(key);
+  return b ? ToCapsule(b->output_label, b, kI64) : nullptr;
+}
+template <int WHICH>
+PyObject *GetGraphEdge(PyObject *, PyObject *args) {
+  unsigned long long key;
+  int layer;
+  if (!PyArg_ParseTuple(args, "Ki", &key, &layer)) return nullptr;
+  TaskPtr b = Batch(key);
+  if (!b) return nullptr;
+  if (layer < 0 || layer >= (int)b->graphs.size()) {
+    PyErr_SetString(PyExc_IndexError, "samgraph: layer index out of range");
+    return nullptr;
+  }
+  const TrainGraph &g = b->graphs[layer];
+  return ToCapsule(WHICH == 0 ? g.row : (WHICH == 1 ? g.col : g.data), b, kI32);
+}
+PyObject *GetInputNodes(PyObject *, PyObject *args) {
+  unsigned long long key;
+  if (!PyArg_ParseTuple(args, "K", &key)) return nullptr;
+  TaskPtr b = Batch(key);
+  return b ? ToCapsule(b->input_nodes, b, kI32) : nullptr;
+}
+PyObject *GetOutputNodes(PyObject *, PyObject *args) {
+  unsigned long long key;
+  if (!PyArg_ParseTuple(args, "K", &key)) return nullptr;
+  TaskPtr b = Batch(key);
+  return b ? ToCapsule(b->output_nodes, b, kI32) : nullptr;
+}
+PyObject *GetDatasetFeat(PyObject *, PyObject *) {
+  const Dataset *ds = Engine::Get()->GetDataset();
+  if (!ds) { PyErr_SetString(PyExc_RuntimeError, "samgraph: dataset not loaded"); return nullptr; }
+  return ToCapsule(ds->feat, nullptr, kF32);
+}
+PyObject *GetDatasetLabel(PyObject *, PyObject *) {
+  const Dataset *ds = Engine::Get()->GetDataset();
+  if (!ds) { PyErr_SetString(PyExc_RuntimeError, "samgraph: dataset not loaded"); return nullptr; }
+  return ToCapsule(ds->label, nullptr, kI64);
+}
+
+PyMethodDef kMethods[] = {
+    {"samgraph_torch_get_graph_feat", GetGraphFeat, METH_VARARGS, "DLPack capsule: f32 [num_input, feat_dim] on the trainer GPU"},
+    {"samgraph_torch_get_graph_label", GetGraphLabel, METH_VARARGS, "DLPack capsule: i64 [batch] on the trainer GPU"},
+    {"samgraph_torch_get_graph_row", GetGraphEdge<0>, METH_VARARGS, "DLPack capsule: i32 [num_edge] (neighbour local ids)"},
+    {"samgraph_torch_get_graph_col", GetGraphEdge<1>, METH_VARARGS, "DLPack capsule: i32 [num_edge] (seed local ids)"},
+    {"samgraph_torch_get_graph_data", GetGraphEdge<2>, METH_VARARGS, "DLPack capsule: i32 [num_edge] (random-walk visit counts)"},
+    {"samgraph_torch_get_dataset_feat", GetDatasetFeat, METH_NOARGS, "DLPack capsule: host feature table"},
+    {"samgraph_torch_get_dataset_label", GetDatasetLabel, METH_NOARGS, "DLPack capsule: host label table"},
+    {"samgraph_torch_get_graph_input_nodes", GetInputNodes, METH_VARARGS, "DLPack capsule: i32 [num_input]"},
+    {"samgraph_torch_get_graph_output_nodes", GetOutputNodes, METH_VARARGS, "DLPack capsule: i32 [batch]"},
+    {nullptr, nullptr, 0, nullptr}};
+
+PyModuleDef kModule = {PyModuleDef_HEAD_INIT, "c_lib", "samgraph B200 runtime: tensor hand-off", -1, kMethods,
+                       nullptr, nullptr, nullptr, nullptr};
+
+}  // namespace
+
+PyMODINIT_FUNC PyInit_c_lib(void) { return PyModule_Create(&kModule); }

@@ -1,0 +1,985 @@
+#include "rt_engine.h"
+
+#include <sys/mman.h>
+#include <sys/stat.h>
+#include <unistd.h>
+
+#include <algorithm>
+#include <cstring>
+#include <fstream>
+#include <iterator>
+
+namespace fgnn {
+namespace rt {
+
+// =============================================================================================
+// TaskPool
+// =============================================================================================
+bool TaskPool::Full() {
+  std::lock_guard<std::mutex> lk(mu_);
+  return q_.size() >= max_;
+}
+void TaskPool::Submit(TaskPtr t) {
+  std::lock_guard<std::mutex> lk(mu_);
+  q_.push_back(std::move(t));
+}
+TaskPtr TaskPool::TryGet() {
+  std::lock_guard<std::mutex> lk(mu_);
+  if (q_.empty()) return nullptr;
+  TaskPtr t = q_.front();
+  q_.pop_front();
+  return t;
+}
+TaskPtr TaskPool::Get(std::atomic<bool> *stop) {
+  while (true) {
+    TaskPtr t = TryGet();
+    if (t) return t;
+    if (stop && stop->load()) return nullptr;
+    std::this_thread::sleep_for(std::chrono::microseconds(1));
+  }
+}
+
+// =============================================================================================
+// Shared ring (arch5): sampler processes -> trainer processes through pinned host memory.
+// Record layout follows TransData/GraphData (task_queue.cc:68-88): a header, then
+// [input_nodes][output_nodes] and per layer {num_src,num_dst,num_edge,row,col[,data]}.
+// =============================================================================================
+struct SlotHeader {
+  std::atomic<uint32_t> ready;
+  uint32_t num_layer, have_data;
+  uint64_t key;
+  uint64_t input_size, output_size;
+  uint64_t num_src[8], num_dst[8], num_edge[8];
+};
+
+struct SharedRing {
+  pthread_mutex_t mu;
+  sem_t free_slots, used_slots;
+  pthread_barrier_t sampler_barrier, trainer_barrier;
+  uint64_t head, tail;
+  uint32_t num_slots;
+  uint64_t slot_bytes;
+  uint64_t ranking_off, slots_off;
+  std::atomic<uint32_t> presample_done;
+  // partitioned cache: one IPC handle per trainer
+  unsigned char ipc_handle[16][FGNN_IPC_HANDLE_BYTES];
+  uint64_t shard_rows[16];
+  char *base() { return reinterpret_cast<char *>(this); }
+  IdType *ranking() { return reinterpret_cast<IdType *>(base() + ranking_off); }
+  char *slot(uint64_t i) { return base() + slots_off + (i % num_slots) * slot_bytes; }
+};
+
+// =============================================================================================
+// Sampler: DoShuffle + DoGPUSample (cuda_loops.cc:30-267 == dist_loops.cc:35-269)
+// =============================================================================================
+class Sampler {
+ public:
+  Sampler(const Dataset *ds, Context ctx, int worker_id, int num_worker, size_t num_epoch);
+  ~Sampler();
+  // next mini-batch of this sampler's share of the epoch; nullptr when all epochs are done
+  TaskPtr Next();
+  void Sample(const TaskPtr &task);
+  void CountFrequency(uint32_t *d_freq);          // PreSC: freq[input_nodes] += 1
+  void ResetShuffler() { cur_epoch_ = 0; cur_step_ = 0; shuffled_epoch_ = (uint64_t)-1; }
+  size_t NumStep() const { return num_step_; }
+  size_t NumLocalStep() const { return local_steps_; }
+  cudaStream_t stream() const { return stream_; }
+  int device() const { return dev_; }
+  const IdType *d_indptr() const { return (const IdType *)indptr_->data; }
+  const IdType *d_indices() const { return (const IdType *)indices_->data; }
+  IdType *n2o() { return (IdType *)n2o_->data; }
+  uint32_t *d_num_items() { return (uint32_t *)num_items_->data; }
+  size_t max_nodes() const { return max_nodes_; }
+
+ private:
+  void Reshuffle(uint64_t epoch);
+  const Dataset *ds_;
+  int dev_;
+  cudaStream_t stream_ = nullptr;
+  RunConfig &rc_;
+  std::vector<size_t> fanout_;
+  size_t L_, batch_;
+  // topology + weights in HBM (dist_engine.cc:176-191)
+  TensorPtr indptr_, indices_, prob_, alias_, prefix_;
+  // shuffler (dist_shuffler.cc:37-96 split; permutation drawn on the GPU, shuffle.cu)
+  TensorPtr train_dev_, perm_dev_, shuffle_ws_;
+  size_t num_train_, num_step_, local_steps_, step_begin_;
+  uint64_t cur_epoch_ = 0, cur_step_ = 0, shuffled_epoch_ = (uint64_t)-1, num_epoch_;
+  // hash table + scratch sized from PredictNumNodes
+  size_t max_nodes_, ht_cap_;
+  TensorPtr table_, n2o_, num_items_, chain_, counts_dev_, counts_host_, ws_;
+  std::vector<size_t> in_max_, edge_max_;
+  std::vector<TensorPtr> dst_, col_, row_, pos_, data_;
+};
+
+Sampler::Sampler(const Dataset *ds, Context ctx, int worker_id, int num_worker, size_t num_epoch)
+    : ds_(ds), dev_(ctx.device_id), rc_(RunConfig::Get()), num_epoch_(num_epoch) {
+  FCHECK(ctx.device_type == kGPU) << "the sampler must live on a GPU: there is no CPU sampling path";
+  CUDA_CALL(cudaSetDevice(dev_));
+  CUDA_CALL(cudaStreamCreateWithFlags(&stream_, cudaStreamNonBlocking));
+  fanout_ = rc_.fanout;
+  L_ = fanout_.size();
+  batch_ = rc_.batch_size;
+
+  auto upload = [&](const TensorPtr &h, const char *name) -> TensorPtr {
+    if (!h || !h->data) return nullptr;
+    auto d = Tensor::Device(h->dtype, h->shape, dev_, stream_, name);
+    CUDA_CALL(cudaMemcpyAsync(d->data, h->data, h->nbytes, cudaMemcpyHostToDevice, stream_));
+    return d;
+  };
+  indptr_ = upload(ds->indptr, "indptr");
+  indices_ = upload(ds->indices, "indices");
+  prob_ = upload(ds->prob_table, "prob_table");
+  alias_ = upload(ds->alias_table, "alias_table");
+  prefix_ = upload(ds->prob_prefix_table, "prob_prefix_table");
+
+  // ---- shuffler split (dist_shuffler.cc:60-83): worker w owns steps [w*floor(N/S), ...) ----
+  num_train_ = ds->train_set->NumItems();
+  num_step_ = (num_train_ + batch_ - 1) / batch_;
+  const size_t per = num_step_ / num_worker;
+  step_begin_ = per * worker_id;
+  local_steps_ = (worker_id == num_worker - 1) ? num_step_ - step_begin_ : per;
+  train_dev_ = upload(ds->train_set, "train_set");
+  perm_dev_ = Tensor::Device(kI32, {num_train_}, dev_, stream_, "train_perm");
+  shuffle_ws_ = Tensor::Device(kU8, {fgnn_k_shuffle_workspace_bytes(num_train_)}, dev_, stream_, "shuffle_ws");
+
+  // ---- per-batch scratch at the PredictNumNodes bounds (common.cc:330-339) ----
+  max_nodes_ = PredictNumNodes(batch_, fanout_, L_);
+  ht_cap_ = fgnn_k_ht_capacity(max_nodes_);
+  table_ = Tensor::Device(kU8, {fgnn_k_ht_bytes(ht_cap_)}, dev_, stream_, "hashtable");
+  n2o_ = Tensor::Device(kI32, {max_nodes_ + 1}, dev_, stream_, "n2o");
+  num_items_ = Tensor::Device(kI32, {4}, dev_, stream_, "num_items");
+  chain_ = Tensor::Device(kU8, {FGNN_CHAIN_WS_BYTES}, dev_, stream_, "chain_ws");
+  CUDA_CALL(cudaMemsetAsync(chain_->data, 0, FGNN_CHAIN_WS_BYTES, stream_));
+  counts_dev_ = Tensor::Device(kI32, {L_ * 3 + 1}, dev_, stream_, "counts");
+  counts_host_ = Tensor::Pinned(kI32, {L_ * 3 + 1}, "counts_host");
+  in_max_.resize(L_);
+  edge_max_.resize(L_);
+  size_t cur = batch_;
+  size_t ws_bytes = 16;
+  for (int i = (int)L_ - 1; i >= 0; --i) {
+    in_max_[i] = cur;
+    edge_max_[i] = cur * fanout_[i];
+    FCHECK_LT(edge_max_[i], (size_t)0x7FFFFFFF) << "layer too large for 32-bit edge counts";
+    cur += cur * fanout_[i];
+    if (rc_.sample_type == kKHop1 || rc_.sample_type == kWeightedKHop || rc_.sample_type == kWeightedKHopPrefix)
+      ws_bytes = std::max(ws_bytes, fgnn_k_sample_replace_workspace_bytes((uint32_t)in_max_[i], (uint32_t)fanout_[i]));
+    if (rc_.sample_type == kRandomWalk)
+      ws_bytes = std::max(ws_bytes, fgnn_k_sample_random_walk_workspace_bytes((uint32_t)in_max_[i], (uint32_t)fanout_[i]));
+  }
+  ws_ = Tensor::Device(kU8, {ws_bytes}, dev_, stream_, "sample_ws");
+  for (size_t i = 0; i < L_; ++i) {
+    dst_.push_back(Tensor::Device(kI32, {edge_max_[i] + 1}, dev_, stream_, "scratch_dst"));
+    col_.push_back(Tensor::Device(kI32, {edge_max_[i] + 1}, dev_, stream_, "scratch_col"));
+    row_.push_back(Tensor::Device(kI32, {edge_max_[i] + 1}, dev_, stream_, "scratch_row"));
+    pos_.push_back(Tensor::Device(kI32, {edge_max_[i] + 1}, dev_, stream_, "scratch_pos"));
+    data_.push_back(rc_.sample_type == kRandomWalk
+                        ? Tensor::Device(kI32, {edge_max_[i] + 1}, dev_, stream_, "scratch_data") : nullptr);
+  }
+  if (rc_.sample_type == kWeightedKHop || rc_.sample_type == kWeightedKHopHashDedup)
+    FCHECK(prob_ && alias_) << "weighted sampling needs prob_table.bin and alias_table.bin";
+  if (rc_.sample_type == kWeightedKHopPrefix) FCHECK(prefix_) << "needs prob_prefix_table.bin";
+  CUDA_CALL(cudaStreamSynchronize(stream_));
+}
+
+Sampler::~Sampler() {
+  if (stream_) {
+    cudaStreamSynchronize(stream_);
+    // tensors free themselves on stream_; destroy it last
+  }
+}
+
+void Sampler::Reshuffle(uint64_t epoch) {
+  FGNN_CALL(fgnn_k_shuffle((const IdType *)train_dev_->data, num_train_, rc_.seed, epoch,
+                           (IdType *)perm_dev_->data, shuffle_ws_->data, shuffle_ws_->nbytes,
+                           (fgnn_stream_t)stream_));
+  shuffled_epoch_ = epoch;
+}
+
+TaskPtr Sampler::Next() {
+  if (cur_step_ >= local_steps_) {
+    cur_step_ = 0;
+    ++cur_epoch_;
+  }
+  if (cur_epoch_ >= num_epoch_) return nullptr;
+  CUDA_CALL(cudaSetDevice(dev_));
+  if (shuffled_epoch_ != cur_epoch_) Reshuffle(cur_epoch_);
+  const size_t gstep = step_begin_ + cur_step_;
+  const size_t off = gstep * batch_;
+  const size_t n = std::min(batch_, num_train_ - off);
+  auto task = std::make_shared<Task>();
+  task->key = cur_epoch_ * num_step_ + gstep;  // global key (dist_loops.cc:41-43)
+  // Copy1D slice of the permuted train set (cuda_shuffler.cc:128-154)
+  task->output_nodes = Tensor::Device(kI32, {n}, dev_, stream_, "output_nodes");
+  CUDA_CALL(cudaMemcpyAsync(task->output_nodes->data, (const IdType *)perm_dev_->data + off, n * sizeof(IdType),
+                            cudaMemcpyDeviceToDevice, stream_));
+  ++cur_step_;
+  return task;
+}
+
+void Sampler::Sample(const TaskPtr &task) {
+  CUDA_CALL(cudaSetDevice(dev_));
+  fgnn_stream_t st = (fgnn_stream_t)stream_;
+  const uint32_t n_seed = (uint32_t)task->output_nodes->NumItems();
+  uint32_t *counts = (uint32_t *)counts_dev_->data;  // [L][3] = num_dst, num_edge, num_src ; [3L] = unused
+  uint32_t *num_items = d_num_items();
+  const IdType *indptr = d_indptr(), *indices = d_indices();
+
+  FGNN_CALL(fgnn_k_ht_reset(table_->data, ht_cap_, num_items, st));                      // cuda_loops.cc:63
+  FGNN_CALL(fgnn_k_ht_fill_unique(table_->data, ht_cap_, (const IdType *)task->output_nodes->data, n_seed, nullptr,
+                                  n2o(), num_items, st));                                 // :67-69
+  for (int i = (int)L_ - 1; i >= 0; --i) {                                               // :87
+    uint32_t *n_in = counts + 3 * i, *n_edge = counts + 3 * i + 1, *n_src = counts + 3 * i + 2;
+    CUDA_CALL(cudaMemcpyAsync(n_in, num_items, 4, cudaMemcpyDeviceToDevice, stream_));
+    fgnn_rng rng{rc_.seed, task->key, (uint32_t)i};
+    IdType *dst = (IdType *)dst_[i]->data, *col = (IdType *)col_[i]->data, *row = (IdType *)row_[i]->data;
+    const uint32_t nmax = (uint32_t)in_max_[i], f = (uint32_t)fanout_[i];
+    switch (rc_.sample_type) {                                                           // :118-161
+      case kKHop0:
+        FGNN_CALL(fgnn_k_sample_khop(0, indptr, indices, n2o(), nmax, n_in, f, rng, nullptr, dst, col, n_edge,
+                                     chain_->data, st));
+        break;
+      case kKHop2:
+        FGNN_CALL(fgnn_k_sample_khop(2, indptr, indices, n2o(), nmax, n_in, f, rng, nullptr, dst, col, n_edge,
+                                     chain_->data, st));
+        break;
+      case kKHop1:
+      case kWeightedKHop:
+      case kWeightedKHopPrefix:
+        FGNN_CALL(fgnn_k_sample_replace((int)rc_.sample_type, indptr, indices,
+                                        prob_ ? (const float *)prob_->data : nullptr,
+                                        alias_ ? (const IdType *)alias_->data : nullptr,
+                                        prefix_ ? (const float *)prefix_->data : nullptr, n2o(), nmax, n_in, f, rng,
+                                        nullptr, dst, col, n_edge, ws_->data, ws_->nbytes, chain_->data, st));
+        break;
+      case kWeightedKHopHashDedup:
+        FGNN_CALL(fgnn_k_sample_weighted_hash_dedup(indptr, indices, (const float *)prob_->data,
+                                                    (const IdType *)alias_->data, n2o(), nmax, n_in, f, rng, nullptr,
+                                                    dst, col, n_edge, chain_->data, st));
+        break;
+      case kRandomWalk:
+        FCHECK_EQ(f, rc_.num_neighbor);
+        FGNN_CALL(fgnn_k_sample_random_walk(indptr, indices, n2o(), nmax, n_in, (uint32_t)rc_.random_walk_length,
+                                            rc_.random_walk_restart_prob, (uint32_t)rc_.num_random_walk, f, rng,
+                                            nullptr, dst, col, (IdType *)data_[i]->data, n_edge, nullptr, nullptr,
+                                            ws_->data, ws_->nbytes, chain_->data, st));
+        break;
+      default:
+        FCHECK(false) << "unknown sample type";
+    }
+    // populate the hash table with the sampled neighbours, then remap (:176-205)
+    FGNN_CALL(fgnn_k_ht_fill_duplicates(table_->data, ht_cap_, dst, (uint32_t)edge_max_[i], n_edge,
+                                        (uint32_t *)pos_[i]->data, n2o(), num_items, chain_->data, st));
+    FGNN_CALL(fgnn_k_ht_map(table_->data, ht_cap_, nullptr, (const uint32_t *)pos_[i]->data, (uint32_t)edge_max_[i],
+                            n_edge, row, st));
+    CUDA_CALL(cudaMemcpyAsync(n_src, num_items, 4, cudaMemcpyDeviceToDevice, stream_));
+  }
+  // the ONE host round trip of the batch: all counts at once
+  CUDA_CALL(cudaMemcpyAsync(counts_host_->data, counts, L_ * 3 * 4, cudaMemcpyDeviceToHost, stream_));
+  CUDA_CALL(cudaStreamSynchronize(stream_));
+  const uint32_t *h = (const uint32_t *)counts_host_->data;
+
+  // materialise exact-size tensors (TrainGraph: row = neighbour local id, col = seed local id, :210-229)
+  task->graphs.resize(L_);
+  size_t total_edges = 0;
+  for (size_t i = 0; i < L_; ++i) {
+    TrainGraph &g = task->graphs[i];
+    g.num_dst = h[3 * i];
+    g.num_edge = h[3 * i + 1];
+    g.num_src = h[3 * i + 2];
+    total_edges += g.num_edge;
+    g.row = Tensor::Device(kI32, {g.num_edge}, dev_, stream_, "train_graph.row");
+    g.col = Tensor::Device(kI32, {g.num_edge}, dev_, stream_, "train_graph.col");
+    CUDA_CALL(cudaMemcpyAsync(g.row->data, row_[i]->data, g.num_edge * 4, cudaMemcpyDeviceToDevice, stream_));
+    CUDA_CALL(cudaMemcpyAsync(g.col->data, col_[i]->data, g.num_edge * 4, cudaMemcpyDeviceToDevice, stream_));
+    if (data_[i]) {
+      g.data = Tensor::Device(kI32, {g.num_edge}, dev_, stream_, "train_graph.data");
+      CUDA_CALL(cudaMemcpyAsync(g.data->data, data_[i]->data, g.num_edge * 4, cudaMemcpyDeviceToDevice, stream_));
+    }
+  }
+  const size_t n_input = h[2];  // num_src of layer 0 == number of unique nodes
+  task->input_nodes = Tensor::Device(kI32, {n_input}, dev_, stream_, "input_nodes");
+  CUDA_CALL(cudaMemcpyAsync(task->input_nodes->data, n2o(), n_input * 4, cudaMemcpyDeviceToDevice, stream_));
+  if (!task->ready) CUDA_CALL(cudaEventCreateWithFlags(&task->ready, cudaEventDisableTiming));
+  CUDA_CALL(cudaEventRecord(task->ready, stream_));
+  Profiler::Get().LogStep(task->key, kLogL1NumNode, (double)n_input);
+  Profiler::Get().LogStep(task->key, kLogL1NumSample, (double)total_edges);
+}
+
+void Sampler::CountFrequency(uint32_t *d_freq) {
+  FGNN_CALL(fgnn_k_freq_count(d_freq, n2o(), (uint32_t)max_nodes_, d_num_items(), (fgnn_stream_t)stream_));
+}
+
+// =============================================================================================
+// Extractor: DoGraphCopy + DoCacheFeatureCopy + label extract on the trainer GPU
+// (cuda_loops.cc:599-606, dist_loops.cc:713-929, dist_cache_manager_*.{cc,cu})
+// =============================================================================================
+class Extractor {
+ public:
+  Extractor(const Dataset *ds, Context ctx, const IdType *ranking_host_or_null, const IdType *ranking_dev_or_null,
+            int ranking_dev, int shard_id, int num_shards, SharedRing *ring);
+  ~Extractor();
+  void Extract(const TaskPtr &task);   // task tensors must already live on this device
+  TaskPtr MoveToTrainer(const TaskPtr &task, int src_dev);
+  cudaStream_t stream() const { return stream_; }
+  int device() const { return dev_; }
+
+ private:
+  const Dataset *ds_;
+  int dev_;
+  cudaStream_t stream_ = nullptr;
+  RunConfig &rc_;
+  size_t row_bytes_, num_cached_ = 0;
+  uint64_t feat_mask_ = ~0ull;
+  const void *feat_src_ = nullptr;     // pinned / registered host feature table (UVA)
+  bool feat_registered_ = false;
+  TensorPtr feat_pinned_, label_dev_, cache_table_, shard_ptrs_, stats_, stats_host_;
+  unsigned long long last_stats_[2] = {0, 0};
+  void *shard_ = nullptr;              // this GPU's cache rows (cudaMalloc: IPC exportable)
+  std::vector<void *> peer_shards_;
+  int num_shards_ = 1, shard_id_ = 0;
+};
+
+Extractor::Extractor(const Dataset *ds, Context ctx, const IdType *ranking_host, const IdType *ranking_dev,
+                     int ranking_dev_id, int shard_id, int num_shards, SharedRing *ring)
+    : ds_(ds), dev_(ctx.device_id), rc_(RunConfig::Get()), num_shards_(num_shards), shard_id_(shard_id) {
+  FCHECK(ctx.device_type == kGPU) << "the trainer must be a GPU";
+  CUDA_CALL(cudaSetDevice(dev_));
+  CUDA_CALL(cudaStreamCreateWithFlags(&stream_, cudaStreamNonBlocking));
+  const size_t V = ds->num_node, D = ds->feat_dim;
+  row_bytes_ = D * DataTypeBytes(ds->feat->dtype);
+
+  // ---- host feature table readable from the GPU (miss path: UVA loads over the host link) ----
+  if (rc_.option_empty_feat != 0) feat_mask_ = (1ull << rc_.option_empty_feat) - 1;  // cuda_extraction.cu:131
+  if (ds->feat->ctx.device_type == kMMAP) {
+    cudaError_t e = cudaHostRegister(ds->feat->data, ds->feat->nbytes,
+                                     cudaHostRegisterMapped | cudaHostRegisterPortable | cudaHostRegisterReadOnly);
+    if (e == cudaSuccess) {
+      feat_registered_ = true;
+      feat_src_ = ds->feat->data;
+    } else {
+      cudaGetLastError();
+      FLOG(Warning) << "cudaHostRegister(feat.bin) failed (" << cudaGetErrorString(e)
+                    << "); staging the feature table into pinned memory";
+      feat_pinned_ = Tensor::Pinned(ds->feat->dtype, ds->feat->shape, "feat_pinned");
+      memcpy(feat_pinned_->data, ds->feat->data, ds->feat->nbytes);
+      feat_src_ = feat_pinned_->data;
+    }
+  } else {
+    feat_src_ = ds->feat->data;  // already pinned (EmptyNoScale path, engine.cc:139-155)
+  }
+
+  // ---- labels live in HBM; the reference gathers them on the CPU (dist_loops.cc:886-929) ----
+  label_dev_ = Tensor::Device(kI64, {V}, dev_, stream_, "label");
+  CUDA_CALL(cudaMemcpyAsync(label_dev_->data, ds->label->data, V * 8, cudaMemcpyHostToDevice, stream_));
+
+  stats_ = Tensor::Device(kI64, {2}, dev_, stream_, "gather_stats");
+  CUDA_CALL(cudaMemsetAsync(stats_->data, 0, 16, stream_));
+  stats_host_ = Tensor::Pinned(kI64, {2}, "gather_stats_host");
+
+  // ---- cache: node -> slot table + the rows of this shard -------------------------------------
+  const bool full_gpu = (rc_.run_arch == kArch1);  // arch1: every feature row is HBM resident
+  const double pct = full_gpu ? 1.0 : rc_.cache_percentage;
+  num_cached_ = (size_t)((double)V * pct);         // dist_cache_manager_host.cc:66
+  if (num_cached_ > V) num_cached_ = V;
+  cache_table_ = Tensor::Device(kI32, {V}, dev_, stream_, "cache_table");
+  TensorPtr rank_dev;
+  const IdType *rank = nullptr;
+  if (full_gpu) {
+    // identity ranking: slot == node id (no PreSC needed)
+    rank_dev = Tensor::Device(kI32, {V}, dev_, stream_, "rank_identity");
+    std::vector<IdType> ident(V);
+    for (size_t i = 0; i < V; ++i) ident[i] = (IdType)i;
+    CUDA_CALL(cudaMemcpyAsync(rank_dev->data, ident.data(), V * 4, cudaMemcpyHostToDevice, stream_));
+    CUDA_CALL(cudaStreamSynchronize(stream_));
+    rank = (const IdType *)rank_dev->data;
+  } else if (num_cached_ > 0) {
+    rank_dev = Tensor::Device(kI32, {V}, dev_, stream_, "ranking_nodes");
+    if (ranking_dev && ranking_dev_id == dev_) {
+      CUDA_CALL(cudaMemcpyAsync(rank_dev->data, ranking_dev, V * 4, cudaMemcpyDeviceToDevice, stream_));
+    } else if (ranking_dev) {
+      CUDA_CALL(cudaMemcpyPeerAsync(rank_dev->data, dev_, ranking_dev, ranking_dev_id, V * 4, stream_));
+    } else {
+      FCHECK(ranking_host) << "cache enabled but no ranking available";
+      CUDA_CALL(cudaMemcpyAsync(rank_dev->data, ranking_host, V * 4, cudaMemcpyHostToDevice, stream_));
+    }
+    rank = (const IdType *)rank_dev->data;
+  }
+  FGNN_CALL(fgnn_k_cache_table_build((uint32_t *)cache_table_->data, V, rank, num_cached_, (fgnn_stream_t)stream_));
+
+  // rows of this shard: slots shard_id, shard_id+T, ...  (owner = slot % T, local row = slot / T)
+  const size_t local_rows = num_cached_ > (size_t)shard_id ? (num_cached_ - shard_id + num_shards - 1) / num_shards : 0;
+  FGNN_CALL(fgnn_k_shard_alloc(&shard_, std::max<size_t>(local_rows, 1) * row_bytes_));
+  if (local_rows) {
+    if (num_shards == 1) {
+      FGNN_CALL(fgnn_k_row_copy(shard_, nullptr, feat_src_, rank, feat_mask_, (uint32_t)local_rows, nullptr, row_bytes_,
+                                (fgnn_stream_t)stream_));
+    } else {
+      // strided slice of the ranking: gather ids first
+      auto ids = Tensor::Device(kI32, {local_rows}, dev_, stream_, "shard_ids");
+      CUDA_CALL(cudaMemcpy2DAsync(ids->data, 4, rank + shard_id, (size_t)num_shards * 4, 4, local_rows,
+                                  cudaMemcpyDeviceToDevice, stream_));
+      FGNN_CALL(fgnn_k_row_copy(shard_, nullptr, feat_src_, (const IdType *)ids->data, feat_mask_, (uint32_t)local_rows,
+                                nullptr, row_bytes_, (fgnn_stream_t)stream_));
+      CUDA_CALL(cudaStreamSynchronize(stream_));
+    }
+  }
+  CUDA_CALL(cudaStreamSynchronize(stream_));
+
+  // ---- map the peers' shards (CUDA IPC across trainer processes, loads go over NVLink) ----
+  peer_shards_.assign(num_shards, nullptr);
+  peer_shards_[shard_id] = shard_;
+  if (num_shards > 1) {
+    FCHECK(ring) << "partitioned cache needs the shared segment";
+    FCHECK_LE(num_shards, 16);
+    FGNN_CALL(fgnn_k_ipc_export(shard_, ring->ipc_handle[shard_id]));
+    ring->shard_rows[shard_id] = local_rows;
+    pthread_barrier_wait(&ring->trainer_barrier);
+    for (int t = 0; t < num_shards; ++t)
+      if (t != shard_id) FGNN_CALL(fgnn_k_ipc_open(ring->ipc_handle[t], &peer_shards_[t]));
+    pthread_barrier_wait(&ring->trainer_barrier);
+  }
+  shard_ptrs_ = Tensor::Device(kI64, {(size_t)num_shards}, dev_, stream_, "shard_ptrs");
+  CUDA_CALL(cudaMemcpyAsync(shard_ptrs_->data, peer_shards_.data(), num_shards * sizeof(void *), cudaMemcpyHostToDevice,
+                            stream_));
+  CUDA_CALL(cudaStreamSynchronize(stream_));
+  FLOG(Info) << "GPU cache: " << num_cached_ << " / " << V << " nodes, shard " << shard_id << "/" << num_shards
+             << " holds " << local_rows << " rows (" << (local_rows * row_bytes_ >> 20) << " MiB)";
+}
+
+Extractor::~Extractor() {
+  cudaSetDevice(dev_);
+  if (stream_) cudaStreamSynchronize(stream_);
+  for (int t = 0; t < (int)peer_shards_.size(); ++t)
+    if (t != shard_id_ && peer_shards_[t]) fgnn_k_ipc_close(peer_shards_[t]);
+  if (shard_) fgnn_k_shard_free(shard_);
+  if (feat_registered_) cudaHostUnregister(const_cast<void *>(feat_src_));
+  cudaGetLastError();
+}
+
+TaskPtr Extractor::MoveToTrainer(const TaskPtr &task, int src_dev) {  // DoGraphCopy, cuda_loops.cc:599-606
+  if (src_dev == dev_) return task;
+  CUDA_CALL(cudaSetDevice(dev_));
+  if (task->ready) CUDA_CALL(cudaStreamWaitEvent(stream_, task->ready, 0));
+  auto move = [&](TensorPtr &t) {
+    if (!t) return;
+    auto d = Tensor::Device(t->dtype, t->shape, dev_, stream_, t->name);
+    CUDA_CALL(cudaMemcpyPeerAsync(d->data, dev_, t->data, src_dev, t->nbytes, stream_));
+    t = d;
+  };
+  auto out = std::make_shared<Task>();
+  out->key = task->key;
+  out->graphs = task->graphs;
+  out->input_nodes = task->input_nodes;
+  out->output_nodes = task->output_nodes;
+  for (auto &g : out->graphs) { move(g.row); move(g.col); move(g.data); }
+  move(out->input_nodes);
+  move(out->output_nodes);
+  CUDA_CALL(cudaStreamSynchronize(stream_));  // sources may be released after this
+  return out;
+}
+
+void Extractor::Extract(const TaskPtr &task) {
+  CUDA_CALL(cudaSetDevice(dev_));
+  if (task->ready) CUDA_CALL(cudaStreamWaitEvent(stream_, task->ready, 0));
+  const size_t n_in = task->input_nodes->NumItems(), n_out = task->output_nodes->NumItems();
+  const size_t D = ds_->feat_dim;
+  task->input_feat = Tensor::Device(ds_->feat->dtype, {n_in, D}, dev_, stream_, "input_feat");
+  task->output_label = Tensor::Device(kI64, {n_out}, dev_, stream_, "output_label");
+  unsigned long long *after = (unsigned long long *)stats_host_->data;
+  // one fused kernel instead of GetMissCacheIndex + ExtractMissData + H2D + 2 combine kernels
+  FGNN_CALL(fgnn_k_gather_cached(task->input_feat->data, (const IdType *)task->input_nodes->data, (uint32_t)n_in,
+                                 nullptr, (const uint32_t *)cache_table_->data, (const void *const *)shard_ptrs_->data,
+                                 (uint32_t)num_shards_, feat_src_, feat_mask_, row_bytes_,
+                                 (unsigned long long *)stats_->data, (fgnn_stream_t)stream_));
+  // labels: GPUExtract with D = 1, int64 (cuda_extraction.cu:74-117)
+  FGNN_CALL(fgnn_k_row_copy(task->output_label->data, nullptr, label_dev_->data, (const IdType *)task->output_nodes->data,
+                            ~0ull, (uint32_t)n_out, nullptr, 8, (fgnn_stream_t)stream_));
+  CUDA_CALL(cudaMemcpyAsync(after, stats_->data, 16, cudaMemcpyDeviceToHost, stream_));
+  CUDA_CALL(cudaStreamSynchronize(stream_));
+  task->num_cache = after[0] - last_stats_[0];
+  task->num_miss = after[1] - last_stats_[1];
+  last_stats_[0] = after[0];
+  last_stats_[1] = after[1];
+  FCHECK_EQ(task->num_miss + task->num_cache, n_in);  // cuda_loops.cc:999 invariant
+  auto &p = Profiler::Get();
+  p.LogStep(task->key, kLogL1FeatureBytes, (double)(n_in * row_bytes_));
+  p.LogStep(task->key, kLogL1LabelBytes, (double)(n_out * 8));
+  p.LogStep(task->key, kLogL1MissBytes, (double)(task->num_miss * row_bytes_));
+  p.LogEpochAdd(task->key, kLogEpochFeatureBytes, (double)(n_in * row_bytes_));
+  p.LogEpochAdd(task->key, kLogEpochMissBytes, (double)(task->num_miss * row_bytes_));
+}
+
+// =============================================================================================
+// Engine
+// =============================================================================================
+Engine *Engine::Get() {
+  static Engine *e = new Engine();  // leaked on purpose: Python may hold tensors past static destruction
+  return e;
+}
+Engine::Engine() {}
+Engine::~Engine() {}
+
+static bool FileExists(const std::string &p) {
+  struct stat st;
+  return stat(p.c_str(), &st) == 0;
+}
+
+void Engine::LoadDataset() {  // engine.cc:73-264
+  RunConfig &rc = RunConfig::Get();
+  std::string path = rc.dataset_path;
+  if (path.empty() || path.back() != '/') path.push_back('/');
+  std::unordered_map<std::string, size_t> meta;
+  std::ifstream mf(path + "meta.txt");
+  FCHECK(mf.good()) << "cannot open " << path << "meta.txt";
+  std::string line;
+  while (std::getline(mf, line)) {
+    std::istringstream iss(line);
+    std::vector<std::string> kv{std::istream_iterator<std::string>{iss}, std::istream_iterator<std::string>{}};
+    if (kv.size() < 2) break;
+    meta[kv[0]] = std::stoull(kv[1]);
+  }
+  for (const char *k : {"NUM_NODE", "NUM_EDGE", "FEAT_DIM", "NUM_CLASS", "NUM_TRAIN_SET", "NUM_TEST_SET", "NUM_VALID_SET"})
+    FCHECK(meta.count(k) > 0) << "meta.txt lacks " << k;
+  auto ds = std::make_unique<Dataset>();
+  ds->num_node = meta["NUM_NODE"];
+  ds->num_edge = meta["NUM_EDGE"];
+  ds->num_class = meta["NUM_CLASS"];
+  ds->feat_dim = meta["FEAT_DIM"];
+  ds->indptr = Tensor::FromMmap(path + "indptr.bin", kI32, {ds->num_node + 1}, "dataset.indptr");
+  ds->indices = Tensor::FromMmap(path + "indices.bin", kI32, {ds->num_edge}, "dataset.indices");
+  if (FileExists(path + "feat.bin") && rc.option_empty_feat == 0) {
+    ds->feat = Tensor::FromMmap(path + "feat.bin", kF32, {ds->num_node, ds->feat_dim}, "dataset.feat");
+  } else {
+    // engine.cc:144-155: no feature file (or SAMGRAPH_EMPTY_FEAT=k): an uninitialised table, 2^k rows
+    const size_t rows = rc.option_empty_feat ? ((size_t)1 << rc.option_empty_feat) : ds->num_node;
+    // defer the pinned allocation to the process that owns a GPU (no CUDA before fork)
+    ds->feat = std::make_shared<Tensor>();
+    ds->feat->dtype = kF32;
+    ds->feat->shape = {rows, ds->feat_dim};
+    ds->feat->ctx = Context(kCPU, 0);
+    ds->feat->nbytes = rows * ds->feat_dim * 4;
+    ds->feat->name = "dataset.feat(empty)";
+  }
+  if (FileExists(path + "label.bin")) {
+    ds->label = Tensor::FromMmap(path + "label.bin", kI64, {ds->num_node}, "dataset.label");
+  } else {
+    ds->label = std::make_shared<Tensor>();
+    ds->label->dtype = kI64;
+    ds->label->shape = {ds->num_node};
+    ds->label->nbytes = ds->num_node * 8;
+    ds->label->ctx = Context(kCPU, 0);
+  }
+  ds->train_set = Tensor::FromMmap(path + "train_set.bin", kI32, {meta["NUM_TRAIN_SET"]}, "dataset.train_set");
+  ds->test_set = Tensor::FromMmap(path + "test_set.bin", kI32, {meta["NUM_TEST_SET"]}, "dataset.test_set");
+  ds->valid_set = Tensor::FromMmap(path + "valid_set.bin", kI32, {meta["NUM_VALID_SET"]}, "dataset.valid_set");
+  if (rc.sample_type == kWeightedKHop || rc.sample_type == kWeightedKHopHashDedup) {
+    ds->prob_table = Tensor::FromMmap(path + "prob_table.bin", kF32, {ds->num_edge}, "dataset.prob_table");
+    ds->alias_table = Tensor::FromMmap(path + "alias_table.bin", kI32, {ds->num_edge}, "dataset.alias_table");
+  } else if (rc.sample_type == kWeightedKHopPrefix) {
+    ds->prob_prefix_table = Tensor::FromMmap(path + "prob_prefix_table.bin", kF32, {ds->num_edge}, "dataset.prefix");
+  }
+  if (rc.UseGPUCache()) {  // engine.cc:216-256
+    const char *f = nullptr;
+    switch (rc.cache_policy) {
+      case kCacheByDegree: f = "cache_by_degree.bin"; break;
+      case kCacheByHeuristic: f = "cache_by_heuristic.bin"; break;
+      case kCacheByDegreeHop: f = "cache_by_degree_hop.bin"; break;
+      case kCacheByFakeOptimal: f = "cache_by_fake_optimal.bin"; break;
+      case kCacheByRandom: f = "cache_by_random.bin"; break;
+      case kCacheByPreSample: break;
+      default: FCHECK(false) << "cache policy " << rc.cache_policy << " is outside the hot-path scope";
+    }
+    if (f) ds->ranking_nodes = Tensor::FromMmap(path + f, kI32, {ds->num_node}, "dataset.ranking_nodes");
+  }
+  dataset_ = std::move(ds);
+}
+
+// materialise feature / label buffers that have no backing file (needs CUDA -> post-fork only)
+static void EnsureHostTables(Dataset *ds) {
+  if (!ds->feat->data) {
+    auto t = Tensor::Pinned(kF32, ds->feat->shape, "dataset.feat(empty)");
+    memset(t->data, 0, t->nbytes);
+    ds->feat = t;
+  }
+  if (!ds->label->data) {
+    auto t = Tensor::Pinned(kI64, ds->label->shape, "dataset.label(empty)");
+    memset(t->data, 0, t->nbytes);
+    ds->label = t;
+  }
+}
+
+void Engine::CreateSharedState() {  // dist_engine.cc:115-153 + memory_queue.cc:33-41
+  RunConfig &rc = RunConfig::Get();
+  const size_t L = fanout_.size();
+  size_t slot = sizeof(SlotHeader) + 256;
+  size_t cur = batch_size_;
+  for (int i = (int)L - 1; i >= 0; --i) {
+    slot += cur * fanout_[i] * 4 * 3 + 256 * 3;
+    cur += cur * fanout_[i];
+  }
+  slot += (cur + batch_size_) * 4 + 512;
+  slot = (slot + 4095) & ~(size_t)4095;
+  const uint32_t nslots = (uint32_t)std::max<size_t>(2, std::min<size_t>(rc.max_copying_jobs + 1, 16));
+  const size_t hdr = (sizeof(SharedRing) + 4095) & ~(size_t)4095;
+  const size_t rank_bytes = (dataset_->num_node * 4 + 4095) & ~(size_t)4095;
+  shared_bytes_ = hdr + rank_bytes + slot * nslots;
+  shared_base_ = mmap(nullptr, shared_bytes_, PROT_READ | PROT_WRITE, MAP_SHARED | MAP_ANONYMOUS, -1, 0);
+  FCHECK(shared_base_ != MAP_FAILED) << "mmap of the shared queue failed";
+  ring_ = new (shared_base_) SharedRing();
+  pthread_mutexattr_t ma;
+  pthread_mutexattr_init(&ma);
+  pthread_mutexattr_setpshared(&ma, PTHREAD_PROCESS_SHARED);
+  pthread_mutex_init(&ring_->mu, &ma);
+  sem_init(&ring_->free_slots, 1, nslots);
+  sem_init(&ring_->used_slots, 1, 0);
+  pthread_barrierattr_t ba;
+  pthread_barrierattr_init(&ba);
+  pthread_barrierattr_setpshared(&ba, PTHREAD_PROCESS_SHARED);
+  pthread_barrier_init(&ring_->sampler_barrier, &ba, (unsigned)rc.num_sample_worker);
+  pthread_barrier_init(&ring_->trainer_barrier, &ba, (unsigned)rc.num_train_worker);
+  ring_->head = ring_->tail = 0;
+  ring_->num_slots = nslots;
+  ring_->slot_bytes = slot;
+  ring_->ranking_off = hdr;
+  ring_->slots_off = hdr + rank_bytes;
+  ring_->presample_done = 0;
+  for (uint32_t i = 0; i < nslots; ++i) reinterpret_cast<SlotHeader *>(ring_->slot(i))->ready = 0;
+}
+
+void Engine::Init() {
+  if (initialized_) return;
+  RunConfig &rc = RunConfig::Get();
+  FCHECK(rc.is_configured);
+  Timer t_init;
+  FCHECK(rc.run_arch != kArch0) << "arch0 (CPU sampling) is not provided: this runtime has no CPU fallback";
+  FCHECK(rc.run_arch == kArch1 || rc.run_arch == kArch2 || rc.run_arch == kArch3 || rc.run_arch == kArch5)
+      << "arch" << rc.run_arch << " is outside the hot-path scope (supported: arch1, arch2, arch3, arch5)";
+  batch_size_ = rc.batch_size;
+  fanout_ = rc.fanout;
+  num_epoch_ = rc.num_epoch;
+  Timer t_load;
+  LoadDataset();
+  const double load_time = t_load.Passed();
+  const size_t n_train = dataset_->train_set->NumItems();
+  num_step_ = (n_train + batch_size_ - 1) / batch_size_;
+  num_local_step_ = num_step_;
+  Profiler::Get().Reset(num_epoch_, num_step_);
+  Profiler::Get().LogInit(kLogInitL2LoadDataset, load_time);
+  Profiler::Get().LogInit(kLogInitL3LoadDatasetMMap, load_time);
+  dist_ = (rc.run_arch == kArch5);
+  if (dist_) {
+    // arch5: NO CUDA call before fork (dist_engine.cc:611-632); only shared state is created here
+    Timer tq;
+    CreateSharedState();
+    Profiler::Get().LogInit(kLogInitL2DistQueue, tq.Passed());
+    Profiler::Get().LogInit(kLogInitL1Common, t_init.Passed());
+    return;
+  }
+  // ---- single process: sampler + extractor in this process (cuda_engine.cc:64-196) ----
+  sampler_ctx_ = rc.sampler_ctx;
+  trainer_ctx_ = rc.trainer_ctx;
+  role_ = kRoleBoth;
+  EnsureHostTables(dataset_.get());
+  Timer t_state;
+  sampler_.reset(new Sampler(dataset_.get(), sampler_ctx_, 0, 1, num_epoch_));
+  sample_q_.reset(new TaskPool(rc.max_sampling_jobs));
+  graph_pool_.reset(new TaskPool(rc.max_copying_jobs));
+  Profiler::Get().LogInit(kLogInitL2InternalState, t_state.Passed());
+  TensorPtr rank_dev;
+  if (rc.UseGPUCache() && rc.cache_policy == kCacheByPreSample) {
+    Timer tp;
+    DoPreSample();
+    Profiler::Get().LogInit(kLogInitL2Presample, tp.Passed());
+  }
+  Timer tc;
+  const IdType *rank_host = dataset_->ranking_nodes ? (const IdType *)dataset_->ranking_nodes->data : nullptr;
+  extractor_.reset(new Extractor(dataset_.get(), trainer_ctx_, rank_host, nullptr, 0, 0, 1, nullptr));
+  Profiler::Get().LogInit(kLogInitL2BuildCache, tc.Passed());
+  Profiler::Get().LogInit(kLogInitL1Common, t_init.Passed());
+  initialized_ = true;
+}
+
+// PreSampler::DoPreSample + GetRankNode (cuda/pre_sampler.cc:57-142): presample_epoch epochs of the
+// real sampler, hotness counted in HBM, ranking by one descending radix sort.
+void Engine::DoPreSample() {
+  RunConfig &rc = RunConfig::Get();
+  const size_t V = dataset_->num_node;
+  Sampler *s = sampler_.get();
+  CUDA_CALL(cudaSetDevice(s->device()));
+  auto freq = Tensor::Device(kI32, {V}, s->device(), s->stream(), "presc_freq");
+  CUDA_CALL(cudaMemsetAsync(freq->data, 0, V * 4, s->stream()));
+  Timer ts;
+  // a temporary sampler view limited to presample_epoch epochs: reuse Next() by bounding the loop
+  const size_t total = (size_t)std::max(1, rc.presample_epoch) * s->NumLocalStep();
+  for (size_t i = 0; i < total; ++i) {
+    TaskPtr task = s->Next();
+    if (!task) break;
+    s->Sample(task);
+    s->CountFrequency((uint32_t *)freq->data);
+  }
+  Profiler::Get().LogInit(kLogInitL3PresampleSample, ts.Passed());
+  Timer tr;
+  auto rank = Tensor::Device(kI32, {V}, s->device(), s->stream(), "presc_rank");
+  auto ws = Tensor::Device(kU8, {fgnn_k_presc_rank_workspace_bytes(V)}, s->device(), s->stream(), "presc_ws");
+  FGNN_CALL(fgnn_k_presc_rank((const uint32_t *)freq->data, V, (uint32_t *)rank->data, ws->data, ws->nbytes,
+                              (fgnn_stream_t)s->stream()));
+  IdType *dst_host;
+  TensorPtr host_rank;
+  if (ring_) {
+    dst_host = ring_->ranking();  // published to the trainers through shared memory (dist_engine.cc:119-123)
+  } else {
+    host_rank = Tensor::Pinned(kI32, {V}, "ranking_nodes");
+    dst_host = (IdType *)host_rank->data;
+  }
+  CUDA_CALL(cudaMemcpyAsync(dst_host, rank->data, V * 4, cudaMemcpyDeviceToHost, s->stream()));
+  CUDA_CALL(cudaStreamSynchronize(s->stream()));
+  if (host_rank) dataset_->ranking_nodes = host_rank;
+  Profiler::Get().LogInit(kLogInitL3PresampleSort, tr.Passed());
+  // pre_sampler.cc:101-103: rewind the shuffler and drop the step/epoch logs written while pre-sampling
+  s->ResetShuffler();
+  Profiler::Get().Reset(num_epoch_, num_step_);
+}
+
+void Engine::SampleInit(int worker_id, Context ctx) {  // dist_engine.cc:231-364
+  FCHECK(dist_ && !initialized_) << "sample_init is only valid in arch5, once per process";
+  RunConfig &rc = RunConfig::Get();
+  Timer t0;
+  role_ = kRoleSampler;
+  worker_id_ = worker_id;
+  sampler_ctx_ = ctx;
+  trainer_ctx_ = ctx;
+  CUDA_CALL(cudaSetDevice(ctx.device_id));
+  Timer tp;
+  CUDA_CALL(cudaHostRegister(shared_base_, shared_bytes_, cudaHostRegisterPortable));  // memory_queue.cc:47-49
+  Profiler::Get().LogInit(kLogInitL3DistQueuePin, tp.Passed());
+  sampler_.reset(new Sampler(dataset_.get(), ctx, worker_id, (int)rc.num_sample_worker, num_epoch_));
+  num_local_step_ = sampler_->NumLocalStep();
+  if (rc.UseGPUCache() && rc.cache_policy == kCacheByPreSample) {
+    Timer tps;
+    if (worker_id == 0) {  // dist_engine.cc:323-337: sampler 0 pre-samples over the WHOLE train set
+      std::unique_ptr<Sampler> full(new Sampler(dataset_.get(), ctx, 0, 1, (size_t)std::max(1, rc.presample_epoch)));
+      std::swap(full, sampler_);
+      DoPreSample();
+      std::swap(full, sampler_);
+      ring_->presample_done = 1;
+    }
+    pthread_barrier_wait(&ring_->sampler_barrier);
+    Profiler::Get().LogInit(kLogInitL2Presample, tps.Passed());
+  } else if (dataset_->ranking_nodes && worker_id == 0) {
+    memcpy(ring_->ranking(), dataset_->ranking_nodes->data, dataset_->num_node * 4);
+  }
+  Profiler::Get().Reset(num_epoch_, num_step_);
+  Profiler::Get().LogInit(kLogInitL1Sampler, t0.Passed());
+  initialized_ = true;
+}
+
+void Engine::TrainInit(int worker_id, Context ctx) {  // dist_engine.cc:366-465
+  FCHECK(dist_ && !initialized_) << "train_init is only valid in arch5, once per process";
+  RunConfig &rc = RunConfig::Get();
+  Timer t0;
+  role_ = kRoleTrainer;
+  worker_id_ = worker_id;
+  trainer_ctx_ = ctx;
+  sampler_ctx_ = ctx;
+  CUDA_CALL(cudaSetDevice(ctx.device_id));
+  CUDA_CALL(cudaHostRegister(shared_base_, shared_bytes_, cudaHostRegisterPortable));
+  EnsureHostTables(dataset_.get());
+  graph_pool_.reset(new TaskPool(rc.max_copying_jobs));
+  const int T = (int)rc.num_train_worker;
+  const bool partition = rc.partition_cache && T > 1 && rc.UseGPUCache();
+  Timer tc;
+  extractor_.reset(new Extractor(dataset_.get(), ctx, rc.UseGPUCache() ? ring_->ranking() : nullptr, nullptr, 0,
+                                 partition ? worker_id : 0, partition ? T : 1, ring_));
+  Profiler::Get().LogInit(kLogInitL2BuildCache, tc.Passed());
+  // steps this trainer consumes: step % T == worker_id (train_graphsage.py:298)
+  num_local_step_ = num_step_ / T + ((size_t)worker_id < num_step_ % T ? 1 : 0);
+  Profiler::Get().LogInit(kLogInitL1Trainer, t0.Passed());
+  initialized_ = true;
+}
+
+// ---- arch5 transport: Task <-> record in a pinned shared slot (task_queue.cc:154-347) ----
+void Engine::SendTask(const TaskPtr &t) {
+  Timer ts;
+  sem_wait(&ring_->free_slots);
+  pthread_mutex_lock(&ring_->mu);
+  const uint64_t idx = ring_->tail++;
+  pthread_mutex_unlock(&ring_->mu);
+  char *slot = ring_->slot(idx);
+  SlotHeader *h = reinterpret_cast<SlotHeader *>(slot);
+  cudaStream_t st = sampler_->stream();
+  const size_t L = t->graphs.size();
+  FCHECK_LE(L, (size_t)8);
+  h->num_layer = (uint32_t)L;
+  h->have_data = (L && t->graphs[0].data) ? 1 : 0;
+  h->key = t->key;
+  h->input_size = t->input_nodes->NumItems();
+  h->output_size = t->output_nodes->NumItems();
+  char *p = slot + ((sizeof(SlotHeader) + 255) & ~(size_t)255);
+  auto put = [&](const TensorPtr &x) {
+    if (!x) return;
+    FCHECK_LE((size_t)(p - slot) + x->nbytes, (size_t)ring_->slot_bytes) << "task exceeds the queue slot";
+    CUDA_CALL(cudaMemcpyAsync(p, x->data, x->nbytes, cudaMemcpyDeviceToHost, st));
+    p += (x->nbytes + 255) & ~(size_t)255;
+  };
+  put(t->input_nodes);
+  put(t->output_nodes);
+  for (size_t i = 0; i < L; ++i) {
+    h->num_src[i] = t->graphs[i].num_src;
+    h->num_dst[i] = t->graphs[i].num_dst;
+    h->num_edge[i] = t->graphs[i].num_edge;
+    put(t->graphs[i].row);
+    put(t->graphs[i].col);
+    put(t->graphs[i].data);
+  }
+  CUDA_CALL(cudaStreamSynchronize(st));
+  h->ready.store(1, std::memory_order_release);
+  sem_post(&ring_->used_slots);
+  Profiler::Get().LogStep(t->key, kLogL1SendTime, ts.Passed());
+  Profiler::Get().LogEpochAdd(t->key, kLogEpochSampleSendTime, ts.Passed());
+}
+
+TaskPtr Engine::RecvTask() {
+  Timer tr;
+  while (sem_trywait(&ring_->used_slots) != 0) {
+    if (stop_) return nullptr;
+    std::this_thread::sleep_for(std::chrono::microseconds(1));
+  }
+  pthread_mutex_lock(&ring_->mu);
+  const uint64_t idx = ring_->head++;
+  pthread_mutex_unlock(&ring_->mu);
+  char *slot = ring_->slot(idx);
+  SlotHeader *h = reinterpret_cast<SlotHeader *>(slot);
+  while (h->ready.load(std::memory_order_acquire) == 0) std::this_thread::sleep_for(std::chrono::microseconds(1));
+  const int dev = extractor_->device();
+  cudaStream_t st = extractor_->stream();
+  CUDA_CALL(cudaSetDevice(dev));
+  auto task = std::make_shared<Task>();
+  task->key = h->key;
+  const char *p = slot + ((sizeof(SlotHeader) + 255) & ~(size_t)255);
+  auto get = [&](size_t n, const char *name) {
+    auto t = Tensor::Device(kI32, {n}, dev, st, name);
+    CUDA_CALL(cudaMemcpyAsync(t->data, p, n * 4, cudaMemcpyHostToDevice, st));
+    p += (n * 4 + 255) & ~(size_t)255;
+    return t;
+  };
+  task->input_nodes = get(h->input_size, "input_nodes");
+  task->output_nodes = get(h->output_size, "output_nodes");
+  task->graphs.resize(h->num_layer);
+  for (uint32_t i = 0; i < h->num_layer; ++i) {
+    TrainGraph &g = task->graphs[i];
+    g.num_src = h->num_src[i];
+    g.num_dst = h->num_dst[i];
+    g.num_edge = h->num_edge[i];
+    g.row = get(g.num_edge, "train_graph.row");
+    g.col = get(g.num_edge, "train_graph.col");
+    if (h->have_data) g.data = get(g.num_edge, "train_graph.data");
+  }
+  CUDA_CALL(cudaStreamSynchronize(st));
+  h->ready.store(0, std::memory_order_release);
+  sem_post(&ring_->free_slots);
+  Profiler::Get().LogStep(task->key, kLogL1RecvTime, tr.Passed());
+  return task;
+}
+
+void Engine::SamplerLoopOnce() {  // RunSampleSubLoopOnce, cuda_loops_arch3.cc:54-83 / dist_loops_arch5.cc:60-156
+  Timer t0;
+  TaskPtr task = sampler_->Next();
+  if (!task) {
+    std::this_thread::sleep_for(std::chrono::microseconds(1));
+    return;
+  }
+  const double shuffle_time = t0.Passed();
+  Timer t1;
+  sampler_->Sample(task);
+  const double sample_time = t1.Passed();
+  auto &p = Profiler::Get();
+  p.LogStep(task->key, kLogL1SampleTime, shuffle_time + sample_time);
+  p.LogStep(task->key, kLogL2ShuffleTime, shuffle_time);
+  p.LogStep(task->key, kLogL2CoreSampleTime, sample_time);
+  p.LogEpochAdd(task->key, kLogEpochSampleTime, shuffle_time + sample_time);
+  if (dist_) {
+    SendTask(task);
+    p.LogEpochAdd(task->key, kLogEpochSampleTotalTime, t0.Passed());
+  } else {
+    sample_q_->Submit(task);
+  }
+}
+
+bool Engine::ExtractLoopOnce() {  // RunCacheDataCopySubLoopOnce, cuda_loops_arch3.cc:133-172 / arch5:204-256
+  TaskPtr task = dist_ ? RecvTask() : sample_q_->TryGet();
+  if (!task) return false;
+  Timer t0;
+  if (!dist_) task = extractor_->MoveToTrainer(task, sampler_->device());
+  const double graph_copy = t0.Passed();
+  Timer t1;
+  extractor_->Extract(task);
+  const double feat = t1.Passed();
+  auto &p = Profiler::Get();
+  const double recv = dist_ ? p.GetLogStepValue(task->key, kLogL1RecvTime) : 0.0;
+  p.LogStep(task->key, kLogL1CopyTime, recv + graph_copy + feat);
+  p.LogStep(task->key, kLogL2GraphCopyTime, graph_copy);
+  p.LogStep(task->key, kLogL2CacheCopyTime, feat);
+  p.LogEpochAdd(task->key, kLogEpochCopyTime, recv + graph_copy + feat);
+  graph_pool_->Submit(task);
+  return true;
+}
+
+void Engine::RunSampleOnce() {  // Engine::RunSampleOnce: RunArch3LoopsOnce / RunArch5LoopsOnce
+  FCHECK(initialized_);
+  if (role_ == kRoleBoth) {
+    SamplerLoopOnce();
+    ExtractLoopOnce();
+  } else if (role_ == kRoleSampler) {
+    SamplerLoopOnce();
+  } else if (role_ == kRoleTrainer) {
+    while (!ExtractLoopOnce() && !stop_) {}
+  }
+}
+
+void Engine::Start() {  // GPUEngine::Start, cuda_engine.cc:198-226: SampleSubLoop + DataCopySubLoop threads
+  FCHECK(initialized_ && role_ == kRoleBoth) << "start() is for the single-process archs; arch5 uses extract_start";
+  threads_.emplace_back([this] {
+    while (!stop_) {
+      if (sample_q_->Full()) { std::this_thread::sleep_for(std::chrono::microseconds(1)); continue; }
+      SamplerLoopOnce();
+    }
+  });
+  threads_.emplace_back([this] {
+    while (!stop_) {
+      if (graph_pool_->Full() || !ExtractLoopOnce()) std::this_thread::sleep_for(std::chrono::microseconds(1));
+    }
+  });
+}
+
+void Engine::StartExtract(int count) {  // DistEngine::StartExtract, dist_engine.cc:474-483
+  FCHECK(initialized_ && role_ == kRoleTrainer);
+  threads_.emplace_back([this, count] {
+    int left = count;
+    while (left > 0 && !stop_) {
+      if (graph_pool_->Full()) { std::this_thread::sleep_for(std::chrono::microseconds(1)); continue; }
+      if (ExtractLoopOnce()) --left;
+    }
+  });
+}
+
+TaskPtr Engine::NextBatch() {  // samgraph_get_next_batch, operation.cc:209-221
+  FCHECK(initialized_ && graph_pool_);
+  current_.reset();
+  current_ = graph_pool_->Get(&stop_);
+  FCHECK(current_) << "get_next_batch after shutdown";
+  return current_;
+}
+
+void Engine::Shutdown() {
+  if (stop_.exchange(true)) return;
+  for (auto &t : threads_)
+    if (t.joinable()) t.join();
+  threads_.clear();
+  current_.reset();
+  if (sampler_) { cudaSetDevice(sampler_->device()); cudaStreamSynchronize(sampler_->stream()); }
+  if (extractor_) { cudaSetDevice(extractor_->device()); cudaStreamSynchronize(extractor_->stream()); }
+}
+
+}  // namespace rt
+}  // namespace fgnn

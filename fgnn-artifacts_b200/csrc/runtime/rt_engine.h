@@ -1,0 +1,108 @@
+// Engine: the sampler / extractor / trainer-facing runtime behind the samgraph_*
+// C-ABI (reference: engine.h, cuda/cuda_engine.*, cuda/cuda_loops*.cc,
+// dist/dist_engine.*, dist/dist_loops*.cc, graph_pool.*, task_queue.*,
+// memory_queue.*).  One class covers the single-process archs (arch1/2/3: sampler
+// and extractor threads in this process) and the factored multi-process arch5
+// (sampler processes and trainer processes forked after data_init, connected by a
+// pinned shared-memory queue).
+#pragma once
+#include <pthread.h>
+#include <semaphore.h>
+
+#include <condition_variable>
+#include <deque>
+#include <mutex>
+#include <thread>
+
+#include "rt_common.h"
+#include "rt_profiler.h"
+
+namespace fgnn {
+namespace rt {
+
+// Bounded in-process queue (TaskQueue / GraphPool, task_queue.h, graph_pool.cc:31-57).
+class TaskPool {
+ public:
+  explicit TaskPool(size_t max_size) : max_(max_size ? max_size : 1) {}
+  bool Full();
+  void Submit(TaskPtr t);
+  TaskPtr Get(std::atomic<bool> *stop);   // blocks (1 us polls, like graph_pool.cc:31-49)
+  TaskPtr TryGet();
+ private:
+  std::mutex mu_;
+  std::deque<TaskPtr> q_;
+  size_t max_;
+};
+
+// Process-shared state of arch5, placed in MAP_SHARED memory before fork()
+// (dist_engine.cc:115-153, memory_queue.h:46-113).
+struct SharedRing;
+
+class Sampler;    // sampler-GPU state + DoGPUSample
+class Extractor;  // trainer-GPU state + DoCacheFeatureCopy / label extract
+
+class Engine {
+ public:
+  static Engine *Get();
+  ~Engine();
+
+  // ---- lifecycle (operation.cc:171-186, 335-360) ----
+  void Init();                                  // samgraph_init / samgraph_data_init
+  void SampleInit(int worker_id, Context ctx);  // samgraph_sample_init (arch5)
+  void TrainInit(int worker_id, Context ctx);   // samgraph_train_init (arch5)
+  void Start();                                 // samgraph_start: background sampler+extractor threads
+  void StartExtract(int count);                 // samgraph_extract_start (arch5 trainer)
+  void RunSampleOnce();                         // samgraph_sample_once
+  void Shutdown();
+
+  // ---- queries ----
+  size_t NumEpoch() const { return num_epoch_; }
+  size_t NumStep() const { return num_step_; }
+  size_t NumLocalStep() const { return num_local_step_; }
+  uint64_t BatchKey(uint64_t epoch, uint64_t step) const { return epoch * num_step_ + step; }
+  const Dataset *GetDataset() const { return dataset_.get(); }
+  Context SamplerCtx() const { return sampler_ctx_; }
+  Context TrainerCtx() const { return trainer_ctx_; }
+  bool Initialized() const { return initialized_; }
+  bool IsShutdown() const { return stop_; }
+
+  TaskPtr NextBatch();                          // samgraph_get_next_batch
+  TaskPtr CurrentBatch() { return current_; }
+  void ForwardBarrier() { ++outer_counter_; }
+
+ private:
+  Engine();
+  void LoadDataset();
+  void SamplerLoopOnce();      // shuffle + sample (+ send in arch5)
+  bool ExtractLoopOnce();      // (recv +) extract + submit
+  TaskPtr RecvTask();
+  void SendTask(const TaskPtr &t);
+  void DoPreSample();
+  void CreateSharedState();
+
+  bool initialized_ = false;
+  std::atomic<bool> stop_{false};
+  bool dist_ = false;  // arch5
+  enum Role { kRoleBoth, kRoleSampler, kRoleTrainer, kRoleNone } role_ = kRoleNone;
+  int worker_id_ = 0;
+
+  std::unique_ptr<Dataset> dataset_;
+  Context sampler_ctx_, trainer_ctx_;
+  size_t num_epoch_ = 0, num_step_ = 0, num_local_step_ = 0, batch_size_ = 0;
+  std::vector<size_t> fanout_;
+
+  std::unique_ptr<Sampler> sampler_;
+  std::unique_ptr<Extractor> extractor_;
+  std::unique_ptr<TaskPool> sample_q_;   // sampler -> extractor (in-process)
+  std::unique_ptr<TaskPool> graph_pool_; // extractor -> python
+  TaskPtr current_;
+  std::vector<std::thread> threads_;
+  std::atomic<uint64_t> outer_counter_{0};
+
+  SharedRing *ring_ = nullptr;  // arch5
+  void *shared_base_ = nullptr;
+  size_t shared_bytes_ = 0;
+};
+
+}  // namespace rt
+}  // namespace fgnn

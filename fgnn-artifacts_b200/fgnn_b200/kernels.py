@@ -49,6 +49,13 @@ _SIGS = {
     "fgnn_k_gather_cached": [_vp, _vp, _u32, _vp, _vp, _vp, _u32, _vp, _u64, _sz, _vp, _vp],
     "fgnn_k_freq_count": [_vp, _vp, _u32, _vp, _vp],
     "fgnn_k_presc_rank": [_vp, _sz, _vp, _vp, _sz, _vp],
+    "fgnn_k_shuffle": [_vp, _sz, _u64, _u64, _vp, _vp, _sz, _vp],
+    "fgnn_k_shard_alloc": [C.POINTER(_vp), _sz],
+    "fgnn_k_shard_free": [_vp],
+    "fgnn_k_ipc_export": [_vp, _vp],
+    "fgnn_k_ipc_open": [_vp, C.POINTER(_vp)],
+    "fgnn_k_ipc_close": [_vp],
+    "fgnn_k_enable_peer": [C.c_int],
 }
 _SIZE_FNS = {
     "fgnn_k_ht_capacity": [_sz],
@@ -56,6 +63,7 @@ _SIZE_FNS = {
     "fgnn_k_sample_replace_workspace_bytes": [_u32, _u32],
     "fgnn_k_sample_random_walk_workspace_bytes": [_u32, _u32],
     "fgnn_k_presc_rank_workspace_bytes": [_sz],
+    "fgnn_k_shuffle_workspace_bytes": [_sz],
 }
 
 _lib = None
@@ -226,3 +234,43 @@ def presc_rank_workspace_bytes(num_nodes):
 def presc_rank(freq, num_nodes, rank, workspace):
     _check(load().fgnn_k_presc_rank(_ptr(freq), num_nodes, _ptr(rank), _ptr(workspace),
                                     workspace.numel() * workspace.element_size(), _stream()), "presc_rank")
+
+
+def shuffle_workspace_bytes(n):
+    return int(load().fgnn_k_shuffle_workspace_bytes(n))
+
+
+def shuffle(train_set, n, seed, epoch, out, workspace):
+    _check(load().fgnn_k_shuffle(_ptr(train_set), n, seed & 0xFFFFFFFFFFFFFFFF, epoch, _ptr(out), _ptr(workspace),
+                                 workspace.numel() * workspace.element_size(), _stream()), "shuffle")
+
+
+def shard_alloc(nbytes):
+    p = _vp()
+    _check(load().fgnn_k_shard_alloc(C.byref(p), nbytes), "shard_alloc")
+    return p.value
+
+
+def shard_free(ptr):
+    _check(load().fgnn_k_shard_free(ptr), "shard_free")
+
+
+def ipc_export(ptr):
+    buf = C.create_string_buffer(64)
+    _check(load().fgnn_k_ipc_export(ptr, buf), "ipc_export")
+    return buf.raw
+
+
+def ipc_open(handle_bytes):
+    p = _vp()
+    buf = C.create_string_buffer(handle_bytes, 64)
+    _check(load().fgnn_k_ipc_open(buf, C.byref(p)), "ipc_open")
+    return p.value
+
+
+def ipc_close(ptr):
+    _check(load().fgnn_k_ipc_close(ptr), "ipc_close")
+
+
+def enable_peer(peer_device):
+    _check(load().fgnn_k_enable_peer(peer_device), "enable_peer")

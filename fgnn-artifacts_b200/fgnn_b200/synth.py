@@ -165,3 +165,36 @@ def u32_tensor(np_u32, device="cuda"):
 
 def to_np_u32(t):
     return t.detach().cpu().numpy().view(np.uint32)
+
+
+def write_dataset(path, ds, with_weights=False, oracle=None):
+    """Write `ds` (dict from make_dataset_numpy) in the reference's on-disk format
+    (datagen/README.md, engine.cc:73-264, constant.cc:23-50): meta.txt + *.bin."""
+    import os
+
+    os.makedirs(path, exist_ok=True)
+    V, E = ds["num_node"], ds["num_edge"]
+    n_test = n_valid = min(1000, V // 10)
+    rng = np.random.default_rng(5)
+    test = rng.permutation(V)[:n_test].astype(np.uint32)
+    valid = rng.permutation(V)[:n_valid].astype(np.uint32)
+    with open(os.path.join(path, "meta.txt"), "w") as f:
+        f.write("NUM_NODE %d\nNUM_EDGE %d\nFEAT_DIM %d\nNUM_CLASS %d\nNUM_TRAIN_SET %d\nNUM_VALID_SET %d\nNUM_TEST_SET %d\n"
+                % (V, E, ds["feat_dim"], ds["num_class"], len(ds["train_set"]), n_valid, n_test))
+    ds["indptr"].astype(np.uint32).tofile(os.path.join(path, "indptr.bin"))
+    ds["indices"].astype(np.uint32).tofile(os.path.join(path, "indices.bin"))
+    if "feat" in ds:
+        ds["feat"].astype(np.float32).tofile(os.path.join(path, "feat.bin"))
+    ds["label"].astype(np.uint64).tofile(os.path.join(path, "label.bin"))
+    ds["train_set"].astype(np.uint32).tofile(os.path.join(path, "train_set.bin"))
+    test.tofile(os.path.join(path, "test_set.bin"))
+    valid.tofile(os.path.join(path, "valid_set.bin"))
+    if with_weights:
+        assert oracle is not None, "weight tables are built by the oracle's restatement of the reference tools"
+        prob, alias = oracle.build_alias_table(ds["indptr"], ds["indices"], ds["edge_weight"])
+        prefix = oracle.build_prefix_table(ds["indptr"], ds["edge_weight"])
+        prob.tofile(os.path.join(path, "prob_table.bin"))
+        alias.tofile(os.path.join(path, "alias_table.bin"))
+        prefix.tofile(os.path.join(path, "prob_prefix_table.bin"))
+        ds["prob_table"], ds["alias_table"], ds["prob_prefix_table"] = prob, alias, prefix
+    return path

@@ -51,6 +51,19 @@ const char *fgnn_k_error_string(int code);
 /* number of kernel launches issued through this library since load */
 uint64_t fgnn_k_launch_count(void);
 
+/* ---- epoch shuffle --------------------------------------------------------- */
+/* GPUShuffler::ReShuffle / DistShuffler::ReShuffle (cuda_shuffler.cc:75-126,
+ * dist_shuffler.cc:98-151): a fresh permutation of the train set per epoch, a pure
+ * function of (seed, epoch) like the reference's dist shuffler (seed = epoch,
+ * dist_shuffler.cc:114).  out[rank of key_i] = train_set[i] with
+ * key_i = Philox(seed, batch_key=epoch, tag=FGNN_SHUFFLE_TAG, item=i, draw 0),
+ * stable ascending sort. */
+#define FGNN_SHUFFLE_TAG 0xFFFF0001u
+size_t fgnn_k_shuffle_workspace_bytes(size_t n);
+int fgnn_k_shuffle(const uint32_t *train_set, size_t n, uint64_t seed,
+                   uint64_t epoch, uint32_t *out, void *workspace,
+                   size_t workspace_bytes, fgnn_stream_t stream);
+
 /* ---- uniform k-hop sampling --------------------------------------------- */
 /* variant 0: GPUSampleKHop0 (cuda_sampling_khop0.cu:178-253, reservoir)
  * variant 2: GPUSampleKHop2 (cuda_sampling_khop2.cu:177-252, Fisher-Yates,
@@ -189,6 +202,21 @@ int fgnn_k_gather_cached(void *out, const uint32_t *nodes, uint32_t n_max,
                          const void *miss_src, uint64_t miss_mask,
                          size_t row_bytes, unsigned long long *d_stats,
                          fgnn_stream_t stream);
+
+/* ---- partitioned cache plumbing ------------------------------------------------ */
+/* The reference replicates the feature cache in every trainer process
+ * (dist_engine.cc:418-424).  Here each trainer GPU owns the slots with
+ * slot % T == t; the other trainers map that shard (same process: peer access,
+ * other processes: CUDA IPC) and fgnn_k_gather_cached reads it over NVLink.
+ * shard_alloc returns plain cudaMalloc memory (exportable); the 64-byte handle is
+ * a cudaIpcMemHandle_t. */
+#define FGNN_IPC_HANDLE_BYTES 64
+int fgnn_k_shard_alloc(void **ptr, size_t bytes);
+int fgnn_k_shard_free(void *ptr);
+int fgnn_k_ipc_export(void *ptr, void *handle64);
+int fgnn_k_ipc_open(const void *handle64, void **ptr);
+int fgnn_k_ipc_close(void *ptr);
+int fgnn_k_enable_peer(int peer_device);
 
 /* ---- PreSC ---------------------------------------------------------------------- */
 /* freq[nodes[i]] += 1  (cuda/pre_sampler.cc:84-88) */

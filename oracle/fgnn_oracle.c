@@ -86,6 +86,28 @@ size_t fgo_table_size(size_t num, size_t scale) {
 }
 
 /* ======================================================================== */
+/* epoch shuffle                                                              */
+/* ======================================================================== */
+typedef struct { uint32_t key; uint32_t idx; } key_idx;
+static int cmp_key_idx(const void *a, const void *b) {
+  const key_idx *x = a, *y = b;
+  if (x->key != y->key) return x->key < y->key ? -1 : 1;
+  if (x->idx != y->idx) return x->idx < y->idx ? -1 : 1;
+  return 0;
+}
+void fgo_shuffle(const uint32_t *train_set, size_t n, uint64_t seed,
+                 uint64_t epoch, uint32_t *out) {
+  key_idx *k = malloc(sizeof(key_idx) * (n + 1));
+  for (size_t i = 0; i < n; ++i) {
+    k[i].key = fgo_rand_u32(seed, epoch, FGO_SHUFFLE_TAG, (uint32_t)i, 0);
+    k[i].idx = (uint32_t)i;
+  }
+  qsort(k, n, sizeof(key_idx), cmp_key_idx);
+  for (size_t i = 0; i < n; ++i) out[i] = train_set[k[i].idx];
+  free(k);
+}
+
+/* ======================================================================== */
 /* samplers                                                                   */
 /* ======================================================================== */
 /* compaction of a padded [num_input x fanout] COO whose valid entries form a

@@ -43,6 +43,12 @@ size_t fgo_predict_num_nodes(size_t batch, const size_t *fanout,
                              size_t num_fanout); /* common.cc:330-339 */
 size_t fgo_table_size(size_t num, size_t scale); /* cuda_hashtable.cu:125-128 */
 
+/* ---- epoch shuffle (replaces cuda_shuffler.cc:75-126 / dist_shuffler.cc:98-151):
+ * stable ascending sort of train_set by key_i = rand(seed, epoch, FGO_SHUFFLE_TAG, i, 0) */
+#define FGO_SHUFFLE_TAG 0xFFFF0001u
+void fgo_shuffle(const uint32_t *train_set, size_t n, uint64_t seed,
+                 uint64_t epoch, uint32_t *out);
+
 /* ---- samplers: all write compact COO (out_src = seed id, out_dst = nbr id)
  * and return the number of edges.  out_* must hold num_input*fanout. -------- */
 /* cuda_sampling_khop0.cu:42-89 + :128-173 (reservoir, Algorithm R) */

@@ -101,6 +101,7 @@ class Oracle:
         L.fgo_build_alias_table.argtypes = [u32p, u32p, C.c_size_t, f32p, f32p, u32p]
         L.fgo_build_prefix_table.argtypes = [u32p, C.c_size_t, f32p, f32p]
         L.fgo_set_threads.argtypes = [C.c_int]
+        L.fgo_shuffle.argtypes = [u32p, C.c_size_t, C.c_uint64, C.c_uint64, u32p]
 
     # ---- rng ----
     def rand_u32(self, seed, batch_key, tag, item, draw):
@@ -116,6 +117,12 @@ class Oracle:
     def predict_num_nodes(self, batch, fanout):
         f = (C.c_size_t * len(fanout))(*fanout)
         return int(self.lib.fgo_predict_num_nodes(batch, f, len(fanout)))
+
+    def shuffle(self, train_set, seed, epoch):
+        train_set = _u32(train_set)
+        out = np.empty(len(train_set), np.uint32)
+        self.lib.fgo_shuffle(_p(train_set), len(train_set), seed, epoch, _p(out))
+        return out
 
     def table_size(self, num, scale=2):
         return int(self.lib.fgo_table_size(num, scale))

@@ -447,3 +447,18 @@ def test_full_batch_pipeline_matches_oracle_driver(K, oracle, gm):
         assert m == e["num_edge"] and int(n_in.item()) == e["num_dst"] and int(n_src.item()) == e["num_src"]
         assert np.array_equal(host(row, m), e["row"]) and np.array_equal(host(col, m), e["col"])
     assert np.array_equal(ht.unique(), exp["input_nodes"])
+
+
+@pytest.mark.parametrize("n", [0, 1, 1000, 300001])
+def test_epoch_shuffle_matches_oracle(K, oracle, n):
+    train = np.random.default_rng(n).permutation(1 << 20)[:n].astype(np.uint32)
+    out = torch.empty(max(1, n), dtype=torch.int32, device="cuda")
+    ws = torch.empty(K.shuffle_workspace_bytes(n), dtype=torch.uint8, device="cuda")
+    for epoch in (0, 3):
+        K.shuffle(dev(train), n, SEED, epoch, out, ws)
+        torch.cuda.synchronize()
+        got = host(out, n)
+        assert np.array_equal(got, oracle.shuffle(train, SEED, epoch))
+        assert np.array_equal(np.sort(got), np.sort(train))          # a permutation
+    if n > 1000:
+        assert not np.array_equal(oracle.shuffle(train, SEED, 0), oracle.shuffle(train, SEED, 3))

@@ -1,0 +1,134 @@
+"""GPU tests of the host runtime through the reference-facing API (samgraph.torch / samgraph_* C-ABI):
+every batch the engine hands to Python is recomputed with the CPU oracle from the same seed."""
+import json
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+torch = pytest.importorskip("torch")
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+SEED = 777
+
+
+def base_config(path, sample_type="khop2", arch="arch3", cache=0.3, fanout=(5, 10), batch=512, epochs=2):
+    import samgraph.common as sc
+    cfg = {"dataset_path": path, "_arch": sc.builtin_archs[arch]["arch"], "arch": arch,
+           "_sample_type": sc.sample_types[sample_type], "sample_type": sample_type, "batch_size": batch,
+           "num_epoch": epochs, "_cache_policy": sc.cache_policies["pre_sample"], "cache_policy": "pre_sample",
+           "cache_percentage": cache, "max_sampling_jobs": 4, "max_copying_jobs": 2, "omp_thread_num": 4,
+           "presample_epoch": 1, "seed": SEED}
+    if sample_type == "random_walk":
+        cfg.update(random_walk_length=3, random_walk_restart_prob=0.5, num_random_walk=4, num_neighbor=5, num_layer=3)
+    else:
+        cfg.update(fanout=list(fanout), num_fanout=len(fanout), num_layer=len(fanout))
+    if arch != "arch5":
+        cfg.update(sampler_ctx="cuda:0", trainer_ctx="cuda:0")
+    return cfg
+
+
+@pytest.fixture(scope="module")
+def dataset(tmp_path_factory, oracle):
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    from fgnn_b200.synth import make_dataset_numpy, write_dataset
+    ds = make_dataset_numpy((20000, 300000, 48, 7, 2000), seed=99)
+    path = str(tmp_path_factory.mktemp("ds"))
+    write_dataset(path, ds, with_weights=True, oracle=oracle)
+    ds["path"] = path
+    return ds
+
+
+def run_driver(tmp_path, scenario):
+    sc_path = os.path.join(str(tmp_path), "scenario.json")
+    out = os.path.join(str(tmp_path), "out.npz")
+    json.dump(scenario, open(sc_path, "w"))
+    env = dict(os.environ, SAMGRAPH_LOG_LEVEL="warn")
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "runtime_driver.py"), sc_path, out],
+                       capture_output=True, text=True, timeout=600, env=env)
+    assert r.returncode == 0, "driver failed:\n%s\n%s" % (r.stdout[-3000:], r.stderr[-3000:])
+    return out
+
+
+def check_batches(oracle, ds, cfg, data, num_step, keys=None):
+    from oracle.oracle import sample_batch_oracle
+    stype = cfg["sample_type"]
+    fanouts = cfg["fanout"] if stype != "random_walk" else [cfg["num_neighbor"]] * cfg["num_layer"]
+    rw = {k: cfg[k] for k in ("random_walk_length", "random_walk_restart_prob", "num_random_walk", "num_neighbor")} \
+        if stype == "random_walk" else None
+    B = cfg["batch_size"]
+    perms = {}
+    keys = data["keys"] if keys is None else keys
+    for key in [int(k) for k in keys]:
+        epoch, step = key // num_step, key % num_step
+        if epoch not in perms:
+            perms[epoch] = oracle.shuffle(ds["train_set"], SEED, epoch)
+        seeds = perms[epoch][step * B:(step + 1) * B]
+        exp = sample_batch_oracle(oracle, ds, seeds, fanouts, stype, SEED, key, rw)
+        pre = "b/%d/" % key
+        assert np.array_equal(data[pre + "output_nodes"].view(np.uint32), seeds)
+        assert np.array_equal(data[pre + "input_nodes"].view(np.uint32), exp["input_nodes"])
+        for i in range(len(fanouts)):
+            e = exp["layers"][i]
+            assert np.array_equal(data[pre + "row%d" % i].view(np.uint32), e["row"])
+            assert np.array_equal(data[pre + "col%d" % i].view(np.uint32), e["col"])
+            assert int(data[pre + "nsrc%d" % i]) == e["num_src"] and int(data[pre + "ndst%d" % i]) == e["num_dst"]
+            if rw:
+                assert np.array_equal(data[pre + "data%d" % i].view(np.uint32), e["data"])
+        # extraction: bit-exact rows of the host feature table / labels (CPUExtract semantics)
+        assert np.array_equal(data[pre + "feat"].view(np.uint32), oracle.extract(ds["feat"], exp["input_nodes"]).view(np.uint32))
+        assert np.array_equal(data[pre + "label"], ds["label"][seeds])
+
+
+@pytest.mark.parametrize("sample_type,cache,pipeline", [("khop2", 0.3, False), ("khop2", 0.0, True), ("khop0", 1.0, False),
+                                                        ("khop1", 0.2, False), ("weighted_khop", 0.2, False),
+                                                        ("weighted_khop_prefix", 0.1, False),
+                                                        ("weighted_khop_hash_dedup", 0.1, False),
+                                                        ("random_walk", 0.25, False)])
+def test_single_process_engine_matches_oracle(tmp_path, oracle, dataset, sample_type, cache, pipeline):
+    cfg = base_config(dataset["path"], sample_type=sample_type, cache=cache)
+    out = run_driver(tmp_path, {"mode": "single", "config": cfg, "pipeline": pipeline})
+    data = np.load(out)
+    num_step = int(data["num_step"])
+    assert num_step == (len(dataset["train_set"]) + cfg["batch_size"] - 1) // cfg["batch_size"]
+    assert int(data["feat_dim"]) == dataset["feat_dim"] and int(data["num_class"]) == dataset["num_class"]
+    assert len(data["keys"]) == num_step * cfg["num_epoch"]
+    assert sorted(int(k) for k in data["keys"]) == list(range(num_step * cfg["num_epoch"]))
+    check_batches(oracle, dataset, cfg, data, num_step)
+    if cache == 1.0:
+        assert all(float(data["miss/%d" % int(k)]) == 0.0 for k in data["keys"])
+    if cache == 0.0:
+        k0 = int(data["keys"][0])
+        assert float(data["miss/%d" % k0]) == data["b/%d/feat" % k0].nbytes
+
+
+def test_arch1_all_features_resident(tmp_path, oracle, dataset):
+    cfg = base_config(dataset["path"], arch="arch1", cache=0.0)
+    out = run_driver(tmp_path, {"mode": "single", "config": cfg})
+    data = np.load(out)
+    check_batches(oracle, dataset, cfg, data, int(data["num_step"]))
+    assert all(float(data["miss/%d" % int(k)]) == 0.0 for k in data["keys"])
+
+
+@pytest.mark.parametrize("S,T", [(1, 1), (2, 2)])
+def test_arch5_forked_sampler_and_trainer_processes(tmp_path, oracle, dataset, S, T):
+    """Factored mode on one GPU (the scripts' --single-gpu placement): sampler and trainer processes forked
+    after data_init, tasks through the pinned shared-memory queue, cache partitioned over the T trainers
+    (CUDA IPC peer mappings)."""
+    cfg = base_config(dataset["path"], arch="arch5", cache=0.4)
+    cfg.update(num_sample_worker=S, num_train_worker=T)
+    sc = {"mode": "arch5", "config": cfg, "sample_devices": ["cuda:0"] * S, "train_devices": ["cuda:0"] * T}
+    out = run_driver(tmp_path, sc)
+    meta = np.load(out)
+    assert int(meta["bad"]) == 0
+    num_step = int(meta["num_step"])
+    seen = []
+    for t in range(T):
+        data = np.load(out + ".t%d.npz" % t)
+        check_batches(oracle, dataset, cfg, data, num_step)
+        seen += [int(k) for k in data["keys"]]
+    assert sorted(seen) == list(range(num_step * cfg["num_epoch"]))
