@@ -101,6 +101,25 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
+def step_of(k, rank, world, steps_per_epoch):
+    """Mini-batch index (within an epoch) that rank `rank` processes at its k-th step: consecutive batches are
+    dealt round-robin, so ranks never touch the same batch and no collective is needed on the data path."""
+    return (k * world + rank) % steps_per_epoch
+
+
+def aggregate(ms_total, edges, device):
+    """Whole-job numbers: time = max over ranks, work = sum over ranks."""
+    import torch
+    import torch.distributed as dist
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+        return ms_total, edges
+    t = torch.tensor([ms_total], dtype=torch.float64, device=device)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e = torch.tensor([edges], dtype=torch.int64, device=device)
+    dist.all_reduce(e, op=dist.ReduceOp.SUM)
+    return float(t.item()), int(e.item())
+
+
 def peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -160,7 +179,7 @@ def run_ours(args):
     perm = wl["train"][torch.randperm(wl["T"], generator=g, device=dev)].contiguous()
 
     def seeds_of(step):
-        s = (step * world + rank) % steps_per_epoch
+        s = step_of(step, rank, world, steps_per_epoch)
         lo = s * BATCH
         hi = min(wl["T"], lo + BATCH)
         return perm[lo:hi], hi - lo
@@ -237,15 +256,7 @@ def run_ours(args):
     sample_ms, gather_ms, hits, misses = r["sample_ms"], r["gather_ms"], r["hits"], r["misses"]
     launches, clk, cache_s = r["launches"], r["clk"], r["cache_s"]
 
-    if world > 1:
-        t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms_total = float(t.item())
-        tot = torch.tensor([edges, n_in_total], dtype=torch.int64, device=dev)
-        dist.all_reduce(tot, op=dist.ReduceOp.SUM)
-        edges_all, n_in_all = int(tot[0].item()), int(tot[1].item())
-    else:
-        edges_all, n_in_all = edges, n_in_total
+    ms_total, edges_all = aggregate(ms_total, edges, dev)
 
     # ---- roofline of the dominant kernel: the fused cache-aware feature gather -----------
     peak, peak_kind = peaks()
@@ -289,7 +300,11 @@ def run_ours(args):
 
     # ---- e2e through the host runtime (samgraph_* C-ABI) with host buffers ------------------
     if not args.no_e2e:
-        out["e2e"] = run_e2e(args, wl, hp, seeds_of, world, rank, dev)
+        # release the device-resident leg's buffers first: the engine child builds its own cache
+        hp.cache = hp.feat_out = hp.cache_table = None
+        del hp, rank_nodes
+        torch.cuda.empty_cache()
+        out["e2e"] = run_e2e(args, wl, world, rank, dev)
     # ---- CPU baseline: the reference's own CPU code on this box's cores -----------------------
     if world == 1 and rank == 0 and not args.no_cpu_baseline:
         out["cpu_baseline"] = cpu_baseline(args, wl, steps=None, budget_s=20.0)
@@ -300,49 +315,67 @@ def run_ours(args):
         print(json.dumps(out))
 
 
-def run_e2e(args, wl, hp, seeds_of, world, rank, dev):
-    """Same metric with host buffers: every step copies its seed ids from pinned host memory, runs the
-    hot path, reads the per-layer counts and the batch labels back to the host (blocking)."""
-    import torch
+def write_dataset_shm(args, wl, rank, world):
+    """Persist the generated graph in the reference's on-disk format (meta.txt + *.bin, engine.cc:73-264) on
+    tmpfs so the C++ engine can load it like a real dataset.  feat.bin is omitted: SAMGRAPH_EMPTY_FEAT=k."""
+    import numpy as np
     import torch.distributed as dist
-    Ksteps, W = args.steps, max(3, args.warmup)
-    host_seeds = [seeds_of(W + k)[0].cpu().pin_memory() for k in range(Ksteps)]
-    d_seeds = torch.empty(BATCH, dtype=torch.int32, device=dev)
-    h_counts = torch.zeros((hp.L, 3), dtype=torch.int32).pin_memory()
-    h_label = torch.zeros(BATCH, dtype=torch.int64).pin_memory()
-    hp.stats.zero_()
-    torch.cuda.synchronize()
+    path = "/dev/shm/fgnn_bench_%s" % args.workload
+    if rank == 0:
+        os.makedirs(path, exist_ok=True)
+        T = wl["T"]
+        with open(os.path.join(path, "meta.txt"), "w") as f:
+            f.write("NUM_NODE %d\nNUM_EDGE %d\nFEAT_DIM %d\nNUM_CLASS %d\nNUM_TRAIN_SET %d\nNUM_VALID_SET %d\nNUM_TEST_SET %d\n"
+                    % (wl["V"], wl["E"], wl["D"], wl["C"], T, 16, 16))
+        wl["indptr"].cpu().numpy().tofile(os.path.join(path, "indptr.bin"))
+        wl["indices"].cpu().numpy().tofile(os.path.join(path, "indices.bin"))
+        wl["label"].cpu().numpy().tofile(os.path.join(path, "label.bin"))
+        wl["train"].cpu().numpy().tofile(os.path.join(path, "train_set.bin"))
+        np.arange(16, dtype=np.uint32).tofile(os.path.join(path, "test_set.bin"))
+        np.arange(16, dtype=np.uint32).tofile(os.path.join(path, "valid_set.bin"))
     if world > 1:
         dist.barrier()
-    s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    edges = 0
-    h2d = d2h = 0
-    s.record()
-    for k in range(Ksteps):
-        n = host_seeds[k].numel()
-        d_seeds[:n].copy_(host_seeds[k], non_blocking=True)
-        hp.step(d_seeds, n, 10_000 + k)
-        h_counts.copy_(hp.counts, non_blocking=True)
-        h_label[:n].copy_(hp.label_out[:n], non_blocking=True)
-        torch.cuda.current_stream().synchronize()
-        edges += int(h_counts[:, 1].sum())
-        h2d += n * 4
-        d2h += h_counts.numel() * 4 + n * 8
-    e.record()
-    torch.cuda.synchronize()
-    ms = s.elapsed_time(e)
-    hits, misses = [int(x) for x in hp.stats.tolist()]
-    h2d += misses * hp.row_bytes                      # miss rows are read from pinned host memory (UVA)
+    return path
+
+
+def run_e2e(args, wl, world, rank, dev):
+    """Same metric through the public API: a child process drives the C++ engine (samgraph.torch over the
+    samgraph_* C-ABI) on the dataset loaded from disk; see tools/e2e_runtime.py."""
+    import torch
+    import torch.distributed as dist
+    path = write_dataset_shm(args, wl, rank, world)
+    Ksteps, W = args.steps, max(3, args.warmup)
+    env = dict(os.environ, SAMGRAPH_EMPTY_FEAT=str(args.empty_feat), SAMGRAPH_LOG_LEVEL="error")
+    for k in ("RANK", "WORLD_SIZE", "LOCAL_RANK", "MASTER_ADDR", "MASTER_PORT"):
+        env.pop(k, None)
+    cmd = [sys.executable, os.path.join(ROOT, "tools", "e2e_runtime.py"), path, str(Ksteps), str(W),
+           str(args.cache_pct), dev, str(0x5EED0000 + rank)]
     if world > 1:
-        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        dist.barrier()
+    r = subprocess.run(cmd, capture_output=True, text=True, env=env, timeout=1500)
+    res = None
+    for line in r.stdout.splitlines():
+        if line.startswith("E2E_JSON "):
+            res = json.loads(line[len("E2E_JSON "):])
+    if res is None:
+        raise RuntimeError("e2e runtime leg failed:\n%s\n%s" % (r.stdout[-2000:], r.stderr[-2000:]))
+    if world > 1:
+        # whole-job number: all ranks run concurrently; time = max over ranks, edges = sum
+        t = torch.tensor([res["ms_per_step"]], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms = float(t.item())
-        tot = torch.tensor([edges], dtype=torch.int64, device=dev)
-        dist.all_reduce(tot, op=dist.ReduceOp.SUM)
-        edges = int(tot.item())
-    return {"value": edges / (ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d // Ksteps,
-            "d2h_bytes_per_step": d2h // Ksteps, "ms_per_step": ms / Ksteps,
-            "api": "fgnn_b200.pipeline.HotPath over the fgnn_k_* C-ABI"}
+        e = torch.tensor([res["edges_per_step"]], dtype=torch.float64, device=dev)
+        dist.all_reduce(e, op=dist.ReduceOp.SUM)
+        res["ms_per_step"] = float(t.item())
+        res["value"] = float(e.item()) / (res["ms_per_step"] * 1e-3)
+    if world > 1:
+        dist.barrier()
+    if rank == 0:
+        try:
+            import shutil
+            shutil.rmtree(path)
+        except OSError:
+            pass
+    return res
 
 
 # ---------------------------------------------------------------------------

@@ -12,6 +12,21 @@
 namespace fgnn {
 namespace rt {
 
+}  // namespace rt
+}  // namespace fgnn
+
+// Share of an epoch's steps owned by sampler `worker_id` of `num_worker` (dist_shuffler.cc:60-83):
+// every sampler takes floor(N/S) consecutive steps, the last one also takes the remainder.
+extern "C" void fgnn_rt_step_split(size_t num_step, size_t num_worker, size_t worker_id, size_t *begin,
+                                   size_t *count) {
+  const size_t per = num_step / num_worker;
+  *begin = per * worker_id;
+  *count = (worker_id == num_worker - 1) ? num_step - *begin : per;
+}
+
+namespace fgnn {
+namespace rt {
+
 // =============================================================================================
 // TaskPool
 // =============================================================================================
@@ -136,9 +151,7 @@ Sampler::Sampler(const Dataset *ds, Context ctx, int worker_id, int num_worker, 
   // ---- shuffler split (dist_shuffler.cc:60-83): worker w owns steps [w*floor(N/S), ...) ----
   num_train_ = ds->train_set->NumItems();
   num_step_ = (num_train_ + batch_ - 1) / batch_;
-  const size_t per = num_step_ / num_worker;
-  step_begin_ = per * worker_id;
-  local_steps_ = (worker_id == num_worker - 1) ? num_step_ - step_begin_ : per;
+  fgnn_rt_step_split(num_step_, (size_t)num_worker, (size_t)worker_id, &step_begin_, &local_steps_);
   train_dev_ = upload(ds->train_set, "train_set");
   perm_dev_ = Tensor::Device(kI32, {num_train_}, dev_, stream_, "train_perm");
   shuffle_ws_ = Tensor::Device(kU8, {fgnn_k_shuffle_workspace_bytes(num_train_)}, dev_, stream_, "shuffle_ws");

@@ -17,6 +17,9 @@
 #include "rt_common.h"
 #include "rt_profiler.h"
 
+extern "C" void fgnn_rt_step_split(size_t num_step, size_t num_worker, size_t worker_id, size_t *begin,
+                                   size_t *count);
+
 namespace fgnn {
 namespace rt {
 
