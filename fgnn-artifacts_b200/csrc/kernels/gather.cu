@@ -16,6 +16,9 @@
 // sides (rows are touched once per batch).
 #include "common.cuh"
 
+#include <stdlib.h>
+#include <string.h>
+
 namespace fgnn {
 namespace {
 
@@ -132,6 +135,296 @@ gather_cached_kernel(char *__restrict__ out, const uint32_t *__restrict__ nodes,
   }
 }
 
+
+// ---------------------------------------------------------------------------
+// Warp-group gather (16-byte rows, production path of the LDG family).
+//
+// ncu r1_b on the flat kernel above: every 16-byte chunk pays the dependent
+// chain nodes[row] -> table[node] -> row load, so only a third of the time a
+// thread is in flight carries payload.  Here a warp owns a *group* of G
+// consecutive output rows: lane l < G resolves row l's source pointer
+// (coalesced id load, one table lookup per ROW instead of per chunk), the
+// pointers are broadcast by shuffle and all 32 lanes stream the group's chunks,
+// 8 x 16 B in flight per thread.  The two index loads are software-pipelined two
+// and one groups ahead, so the copy loop never waits on them.
+// ---------------------------------------------------------------------------
+constexpr int kGroupUnroll = 8;
+constexpr uint32_t kGroupChunks = 32 * kGroupUnroll;  // chunks of one pass
+
+struct RowSrc {
+  const void *const *shards;
+  const char *shard0;
+  uint32_t num_shards;
+  const char *miss_src;
+  uint64_t miss_mask;
+  size_t row_bytes;
+  __device__ __forceinline__ const char *resolve(uint32_t node, uint32_t slot) const {
+    if (slot != kEmpty) {
+      if (num_shards == 1) return shard0 + (size_t)slot * row_bytes;
+      const uint32_t owner = slot % num_shards, lrow = slot / num_shards;
+      return (const char *)__ldg((const unsigned long long *)shards + owner) + (size_t)lrow * row_bytes;
+    }
+    return miss_src + ((uint64_t)node & miss_mask) * row_bytes;
+  }
+};
+
+__device__ __forceinline__ const char *shfl_ptr(const char *p, int src) {
+  unsigned long long v = (unsigned long long)p;
+  v = __shfl_sync(0xFFFFFFFFu, v, src);
+  return (const char *)v;
+}
+
+__global__ void __launch_bounds__(kBlock)
+gather_group_kernel(char *__restrict__ out, const uint32_t *__restrict__ nodes, uint32_t n_max,
+                    const uint32_t *__restrict__ d_n, const uint32_t *__restrict__ table,
+                    RowSrc rs, uint32_t cpr, uint32_t G, unsigned long long *d_stats) {
+  rs.shard0 = (const char *)__ldg((const unsigned long long *)rs.shards);
+  const uint32_t n = load_count(n_max, d_n);
+  const uint32_t lane = threadIdx.x & 31;
+  const uint32_t W = gridDim.x * (kBlock / 32);
+  uint32_t g = blockIdx.x * (kBlock / 32) + (threadIdx.x >> 5);
+  const uint32_t groups = (n + G - 1) / G;
+  const uint32_t CH = G * cpr;  // chunks per group; <= kGroupChunks unless G == 1
+  // loop-invariant chunk map of this lane: (row in group) << 24 | byte offset in row
+  uint32_t cmap[kGroupUnroll];
+#pragma unroll
+  for (int k = 0; k < kGroupUnroll; ++k) {
+    const uint32_t c = lane + 32u * k;
+    cmap[k] = kEmpty;
+    if (c < CH && G > 1) {
+      const uint32_t r = c / cpr;
+      cmap[k] = (r << 24) | ((c - r * cpr) * 16u);
+    }
+  }
+  uint32_t hits = 0, misses = 0;
+  auto load_node = [&](uint32_t gg) -> uint32_t {
+    const uint64_t row = (uint64_t)gg * G + lane;
+    return (gg < groups && lane < G && row < n) ? __ldg(nodes + row) : kEmpty;
+  };
+  // pipeline registers: node/slot of the current group, node of the next one
+  uint32_t node_c = load_node(g);
+  uint32_t node_n = load_node(g + W);
+  uint32_t slot_c = node_c != kEmpty ? __ldg(table + node_c) : kEmpty;
+  for (; g < groups; g += W) {
+    const char *sp = nullptr;
+    if (node_c != kEmpty) {
+      sp = rs.resolve(node_c, slot_c);
+      if (slot_c != kEmpty) ++hits; else ++misses;
+    }
+    // stage the next groups' index loads before streaming this one
+    const uint32_t slot_n = node_n != kEmpty ? __ldg(table + node_n) : kEmpty;
+    const uint32_t node_nn = load_node(g + 2 * W);
+    const uint64_t row0 = (uint64_t)g * G;
+    const uint32_t rows_here = (uint32_t)(n - row0 < G ? n - row0 : G);
+    char *obase = out + row0 * rs.row_bytes;
+    if (G > 1) {
+      uint4 v[kGroupUnroll];
+#pragma unroll
+      for (int k = 0; k < kGroupUnroll; ++k) {
+        const uint32_t r = cmap[k] == kEmpty ? 0u : (cmap[k] >> 24);
+        const char *p = shfl_ptr(sp, (int)r);
+        if (cmap[k] != kEmpty && r < rows_here) v[k] = ld_nc_na_v4(p + (cmap[k] & 0xFFFFFFu));
+      }
+#pragma unroll
+      for (int k = 0; k < kGroupUnroll; ++k) {
+        const uint32_t r = cmap[k] >> 24;
+        if (cmap[k] != kEmpty && r < rows_here)
+          st_na_v4(obase + (size_t)r * rs.row_bytes + (cmap[k] & 0xFFFFFFu), v[k]);
+      }
+    } else {  // long rows: one row per group, several passes
+      const char *p = shfl_ptr(sp, 0);
+      for (uint32_t c0 = lane; c0 < cpr; c0 += kGroupChunks) {
+        uint4 v[kGroupUnroll];
+#pragma unroll
+        for (int k = 0; k < kGroupUnroll; ++k)
+          if (c0 + 32u * k < cpr) v[k] = ld_nc_na_v4(p + (size_t)(c0 + 32u * k) * 16u);
+#pragma unroll
+        for (int k = 0; k < kGroupUnroll; ++k)
+          if (c0 + 32u * k < cpr) st_na_v4(obase + (size_t)(c0 + 32u * k) * 16u, v[k]);
+      }
+    }
+    node_c = node_n;
+    slot_c = slot_n;
+    node_n = node_nn;
+  }
+  if (d_stats) {
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) {
+      hits += __shfl_down_sync(0xFFFFFFFFu, hits, d);
+      misses += __shfl_down_sync(0xFFFFFFFFu, misses, d);
+    }
+    if (lane == 0) {
+      if (hits) atomicAdd(d_stats + 0, (unsigned long long)hits);
+      if (misses) atomicAdd(d_stats + 1, (unsigned long long)misses);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------
+// Bulk-copy gather (TMA engine, no tensor map: rows are plain byte ranges).
+//
+// A warp walks super-groups of 32 consecutive output rows (lane l resolves row
+// l: one coalesced id load + one table lookup per ROW, software-pipelined one
+// and two super-groups ahead).  A super-group is cut into sub-groups of G rows;
+// each sub-group goes through one stage of the warp's shared-memory ring:
+//   - lanes of the sub-group issue `cp.async.bulk` global->shared for their
+//     (hit) row, completion counted on the stage's mbarrier;
+//   - miss rows (pinned host memory over the host link) are copied by the whole
+//     warp with 16-byte loads into the same stage;
+//   - the G output rows are consecutive, so the stage leaves the SM as ONE bulk
+//     store of G*row_bytes.
+// Payload never touches the register file; S-2 sub-groups of loads and two
+// stores are in flight per warp.
+// ---------------------------------------------------------------------------
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) {
+  return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra DONE_%=;\n"
+      "bra WAIT_%=;\n"
+      "DONE_%=:\n"
+      "}\n" ::"r"(bar), "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst_smem, const void *src, uint32_t bytes,
+                                         uint32_t bar) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst_smem),
+      "l"(src), "r"(bytes), "r"(bar)
+      : "memory");
+}
+__device__ __forceinline__ void bulk_s2g(void *dst, uint32_t src_smem, uint32_t bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst),
+               "r"(src_smem), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void bulk_wait_read() {
+  asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() {
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+
+template <int S, int NW>
+__global__ void __launch_bounds__(NW * 32)
+gather_bulk_kernel(char *__restrict__ out, const uint32_t *__restrict__ nodes, uint32_t n_max,
+                   const uint32_t *__restrict__ d_n, const uint32_t *__restrict__ table,
+                   RowSrc rs, uint32_t G, uint32_t stage_bytes, int miss_by_ldg,
+                   unsigned long long *d_stats) {
+  rs.shard0 = (const char *)__ldg((const unsigned long long *)rs.shards);
+  constexpr int A = S - 2;  // sub-groups of loads in flight ahead of the store
+  extern __shared__ __align__(128) unsigned char s_raw[];
+  __shared__ __align__(8) unsigned long long s_bar[NW][S];
+  const uint32_t n = load_count(n_max, d_n);
+  const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  // balanced contiguous partition: warp w owns sub-groups [w*T/W, (w+1)*T/W) of G rows each
+  const uint64_t W = (uint64_t)gridDim.x * NW, w = (uint64_t)blockIdx.x * NW + warp;
+  const uint64_t T = ((uint64_t)n + G - 1) / G;
+  const uint64_t jb = w * T / W, je = (w + 1) * T / W;
+  const uint32_t total = (uint32_t)(je - jb);
+  const uint64_t r0 = jb * G;                                   // first row of this warp
+  const uint64_t r_end = je * G < n ? je * G : n;               // one past its last row
+  const uint32_t spg = 32 / G;                                  // sub-groups per 32-row super-group
+  const uint32_t row_bytes = (uint32_t)rs.row_bytes;
+  unsigned char *stage0 = s_raw + (size_t)warp * S * stage_bytes;
+  if (lane == 0) {
+#pragma unroll
+    for (int s = 0; s < S; ++s) mbar_init(smem_u32(&s_bar[warp][s]), 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncwarp();
+  uint32_t hits = 0, misses = 0;
+  auto load_node = [&](uint32_t m) -> uint32_t {  // super-group m of this warp: rows r0+32m+lane
+    const uint64_t row = r0 + (uint64_t)m * 32 + lane;
+    return row < r_end ? __ldg(nodes + row) : kEmpty;
+  };
+
+  // index pipeline: (node,slot) of the super-group being issued, the next one, and the node after
+  uint32_t node_i = load_node(0), node_n = load_node(1);
+  uint32_t slot_i = node_i != kEmpty ? __ldg(table + node_i) : kEmpty;
+  uint32_t slot_n = node_n != kEmpty ? __ldg(table + node_n) : kEmpty;
+  uint32_t node_nn = load_node(2);
+  const char *sp = node_i != kEmpty ? rs.resolve(node_i, slot_i) : nullptr;
+  if (node_i != kEmpty) { if (slot_i != kEmpty) ++hits; else ++misses; }
+
+  // issue the loads of this warp's sub-group number j (all lanes call)
+  auto issue = [&](uint32_t j) {
+    const uint32_t sub = j % spg;
+    if (j != 0 && sub == 0) {  // entering the next super-group: rotate the index pipeline
+      node_i = node_n; slot_i = slot_n;
+      node_n = node_nn;
+      slot_n = node_n != kEmpty ? __ldg(table + node_n) : kEmpty;
+      node_nn = load_node(j / spg + 2);
+      sp = node_i != kEmpty ? rs.resolve(node_i, slot_i) : nullptr;
+      if (node_i != kEmpty) { if (slot_i != kEmpty) ++hits; else ++misses; }
+    }
+    const uint32_t s = j % S;
+    const uint32_t bar = smem_u32(&s_bar[warp][s]);
+    unsigned char *st = stage0 + (size_t)s * stage_bytes;
+    const bool mine = (lane / G) == sub && node_i != kEmpty;
+    const bool by_bulk = mine && (slot_i != kEmpty || !miss_by_ldg);
+    const uint32_t nbulk = __popc(__ballot_sync(0xFFFFFFFFu, by_bulk));
+    if (lane == 0) mbar_expect_tx(bar, nbulk * row_bytes);
+    __syncwarp();
+    if (by_bulk) bulk_g2s(smem_u32(st + (size_t)(lane - sub * G) * row_bytes), sp, row_bytes, bar);
+    uint32_t ldg_rows = __ballot_sync(0xFFFFFFFFu, mine && !by_bulk);
+    while (ldg_rows) {  // host-resident rows: warp-wide 16-byte loads into the stage
+      const int r = __ffs(ldg_rows) - 1;
+      ldg_rows &= ldg_rows - 1;
+      const char *p = shfl_ptr(sp, r);
+      for (uint32_t c = lane * 16u; c < row_bytes; c += 32u * 16u)
+        *reinterpret_cast<uint4 *>(st + (size_t)(r - sub * G) * row_bytes + c) = ld_nc_na_v4(p + c);
+    }
+  };
+
+  for (uint32_t j = 0; j < (uint32_t)A && j < total; ++j) issue(j);
+  for (uint32_t j = 0; j < total; ++j) {
+    if (j + A < total) {
+      // stage (j+A)%S was last stored at iteration j-2: allow one younger store to still read
+      if (lane == 0) bulk_wait_read<1>();
+      __syncwarp();
+      issue(j + A);
+    }
+    const uint32_t s = j % S;
+    mbar_wait(smem_u32(&s_bar[warp][s]), (j / S) & 1u);
+    const uint64_t row0 = r0 + (uint64_t)j * G;
+    const uint32_t rows_here = (uint32_t)(r_end - row0 < G ? r_end - row0 : G);
+    fence_proxy_async();  // generic-proxy stage writes (miss rows) -> async proxy
+    __syncwarp();
+    if (lane == 0) {
+      bulk_s2g(out + row0 * row_bytes, smem_u32(stage0 + (size_t)s * stage_bytes), rows_here * row_bytes);
+      bulk_commit();
+    }
+  }
+  if (lane == 0) bulk_wait_read<0>();
+  if (d_stats) {
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) {
+      hits += __shfl_down_sync(0xFFFFFFFFu, hits, d);
+      misses += __shfl_down_sync(0xFFFFFFFFu, misses, d);
+    }
+    if (lane == 0) {
+      if (hits) atomicAdd(d_stats + 0, (unsigned long long)hits);
+      if (misses) atomicAdd(d_stats + 1, (unsigned long long)misses);
+    }
+  }
+}
+
 inline int vec_width(size_t row_bytes, const void *a, const void *b, const void *c = nullptr) {
   const uintptr_t bits = (uintptr_t)row_bytes | (uintptr_t)a | (uintptr_t)b | (uintptr_t)c;
   if ((bits & 15) == 0) return 16;
@@ -175,6 +468,80 @@ extern "C" int fgnn_k_row_copy(void *dst, const uint32_t *dst_index, const void 
   return check_last();
 }
 
+namespace fgnn {
+namespace {
+// A/B switches for profiling (read once): FGNN_GATHER_IMPL = flat | group | bulk
+struct GatherTuning {
+  int impl;         // 0 flat, 1 group, 2 bulk
+  int stages;       // bulk: ring depth per warp
+  int warps;        // bulk: warps per CTA
+  uint32_t stage_cap;  // bulk: max bytes per stage
+  int miss_ldg;     // bulk: host-resident rows by warp loads (1) or by the bulk engine (0)
+  uint32_t group_rows; // group: rows per warp group (0 = auto)
+  int ctas_per_sm;  // 0 = occupancy
+};
+inline int env_int(const char *name, int dflt) {
+  const char *v = getenv(name);
+  return v && *v ? atoi(v) : dflt;
+}
+GatherTuning read_tuning() {
+  GatherTuning g;
+  const char *v = getenv("FGNN_GATHER_IMPL");
+  g.impl = 2;
+  if (v && !strcmp(v, "flat")) g.impl = 0;
+  if (v && !strcmp(v, "group")) g.impl = 1;
+  if (v && !strcmp(v, "bulk")) g.impl = 2;
+  g.stages = env_int("FGNN_BULK_STAGES", 8);
+  g.warps = env_int("FGNN_BULK_WARPS", 8);
+  g.stage_cap = (uint32_t)env_int("FGNN_BULK_STAGE_BYTES", 2048);
+  g.miss_ldg = env_int("FGNN_BULK_MISS_LDG", 0);
+  g.group_rows = (uint32_t)env_int("FGNN_GROUP_ROWS", 0);
+  g.ctas_per_sm = env_int("FGNN_GATHER_CTAS_PER_SM", 0);
+  return g;
+}
+const GatherTuning &tuning() {
+  static GatherTuning t = read_tuning();
+  if (env_int("FGNN_TUNING_DYNAMIC", 0) != 0) t = read_tuning();  // sweeps/tests: re-read per call
+  return t;
+}
+
+template <int S, int NW>
+int launch_bulk(char *out, const uint32_t *nodes, uint32_t n_max, const uint32_t *d_n,
+                const uint32_t *table, const RowSrc &rs, uint32_t G, uint32_t stage_bytes,
+                unsigned long long *d_stats, cudaStream_t st) {
+  auto kern = gather_bulk_kernel<S, NW>;
+  const size_t smem = (size_t)NW * S * stage_bytes;
+  static size_t configured = 0;
+  if (smem > configured) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+    configured = smem;
+  }
+  int occ = tuning().ctas_per_sm ? tuning().ctas_per_sm : occupancy(kern, NW * 32, smem);
+  // at least kMinSub sub-groups per warp so the ring fills
+  const uint64_t subs = ((uint64_t)n_max + G - 1) / G;
+  const int grid = persistent_grid(subs, NW * 4, occ, false);
+  kern<<<grid, NW * 32, smem, st>>>(out, nodes, n_max, d_n, table, rs, G, stage_bytes,
+                                    tuning().miss_ldg, d_stats);
+  return 0;
+}
+
+template <int NW>
+int launch_bulk_s(int stages, char *out, const uint32_t *nodes, uint32_t n_max, const uint32_t *d_n,
+                  const uint32_t *table, const RowSrc &rs, uint32_t G, uint32_t stage_bytes,
+                  unsigned long long *d_stats, cudaStream_t st) {
+  switch (stages) {
+    case 3: return launch_bulk<3, NW>(out, nodes, n_max, d_n, table, rs, G, stage_bytes, d_stats, st);
+    case 4: return launch_bulk<4, NW>(out, nodes, n_max, d_n, table, rs, G, stage_bytes, d_stats, st);
+    case 6: return launch_bulk<6, NW>(out, nodes, n_max, d_n, table, rs, G, stage_bytes, d_stats, st);
+    case 12: return launch_bulk<12, NW>(out, nodes, n_max, d_n, table, rs, G, stage_bytes, d_stats, st);
+    case 16: return launch_bulk<16, NW>(out, nodes, n_max, d_n, table, rs, G, stage_bytes, d_stats, st);
+    default: return launch_bulk<8, NW>(out, nodes, n_max, d_n, table, rs, G, stage_bytes, d_stats, st);
+  }
+}
+}  // namespace
+}  // namespace fgnn
+
 extern "C" int fgnn_k_gather_cached(void *out, const uint32_t *nodes, uint32_t n_max,
                                     const uint32_t *d_n, const uint32_t *table,
                                     const void *const *shards, uint32_t num_shards,
@@ -186,6 +553,51 @@ extern "C" int fgnn_k_gather_cached(void *out, const uint32_t *nodes, uint32_t n
   // shard bases are cudaMalloc'ed (256-B aligned); only out/miss_src/row_bytes decide
   const int w = vec_width(row_bytes, out, miss_src);
   const uint32_t cpr = (uint32_t)(row_bytes / w);
+  const GatherTuning &tn = tuning();
+  if (w == 16 && tn.impl != 0) {
+    RowSrc rs;
+    rs.shards = shards;
+    rs.shard0 = nullptr;  // fetched from shards[0] by the kernel
+    rs.num_shards = num_shards;
+    rs.miss_src = (const char *)miss_src;
+    rs.miss_mask = miss_mask;
+    rs.row_bytes = row_bytes;
+    if (tn.impl == 2) {
+      // stage = the most rows (power of two, <= 32) that fit the stage cap; the ring depth
+      // shrinks for long rows so that warps * stages * stage_bytes stays within shared memory
+      uint32_t G = 32;
+      while (G > 1 && (size_t)G * row_bytes > tn.stage_cap) G >>= 1;
+      const uint32_t stage_bytes = (uint32_t)(G * row_bytes);
+      const int warps = (tn.warps == 4 || tn.warps == 16) ? tn.warps : 8;
+      int stages = tn.stages;
+      const size_t kSmemBudget = 200 * 1024;
+      while (stages > 3 && (size_t)warps * stages * stage_bytes > kSmemBudget)
+        stages = stages > 12 ? 12 : stages > 8 ? 8 : stages > 6 ? 6 : stages > 4 ? 4 : 3;
+      if ((size_t)warps * stages * stage_bytes <= kSmemBudget) {
+        int rc;
+        if (warps == 4)
+          rc = launch_bulk_s<4>(stages, (char *)out, nodes, n_max, d_n, table, rs, G, stage_bytes, d_stats, st);
+        else if (warps == 16)
+          rc = launch_bulk_s<16>(stages, (char *)out, nodes, n_max, d_n, table, rs, G, stage_bytes, d_stats, st);
+        else
+          rc = launch_bulk_s<8>(stages, (char *)out, nodes, n_max, d_n, table, rs, G, stage_bytes, d_stats, st);
+        if (rc) return rc;
+        note_launch();
+        return check_last();
+      }
+      // rows too long for a shared-memory ring: warp-group kernel below
+    }
+    uint32_t G = tn.group_rows ? tn.group_rows : kGroupChunks / cpr;
+    if (G > 32) G = 32;
+    if (G < 1 || G * cpr > kGroupChunks) G = 1;
+    static const int occ_g = occupancy(gather_group_kernel, kBlock, 0);
+    const int occ = tn.ctas_per_sm ? tn.ctas_per_sm : occ_g;
+    const uint64_t groups = ((uint64_t)n_max + G - 1) / G;
+    const int grid = persistent_grid(groups, kBlock / 32, occ, false);
+    gather_group_kernel<<<grid, kBlock, 0, st>>>((char *)out, nodes, n_max, d_n, table, rs, cpr, G, d_stats);
+    note_launch();
+    return check_last();
+  }
 #define FGNN_GC(V)                                                                               \
   do {                                                                                           \
     static const int occ = occupancy(gather_cached_kernel<V>, kBlock, 0);                        \

@@ -306,6 +306,55 @@ def test_gather_cached_matches_reference_pipeline(K, oracle, num_shards, dim, pc
     assert stats.tolist() == [len(cs), len(ms)]
 
 
+@pytest.mark.parametrize("impl", ["bulk", "group", "flat"])
+@pytest.mark.parametrize("row_bytes,n,n_max,pct,shards", [
+    (512, 0, 64, 0.5, 1), (512, 1, 1, 0.5, 1), (512, 3, 3, 1.0, 1), (512, 33, 40, 0.0, 1),
+    (512, 70001, 70001, 0.9, 1), (512, 70001, 90000, 1.0, 3), (400, 12345, 12345, 0.7, 2),
+    (16, 5000, 5000, 0.5, 1), (48, 5000, 6000, 0.5, 1), (1024, 9999, 9999, 0.8, 1), (2048, 3001, 3001, 0.6, 2),
+    (4096, 2000, 2000, 0.5, 1), (6400, 777, 777, 0.5, 1), (12288, 301, 301, 0.5, 1), (36, 2000, 2000, 0.5, 1)])
+def test_gather_cached_impls_edge_cases(K, oracle, impl, row_bytes, n, n_max, pct, shards):
+    """Every implementation of fgnn_k_gather_cached (TMA bulk ring, warp-group, flat) over ragged counts
+    (device count < n_max, n not a multiple of the row group), rows from 16 B to 12 KB (ring-depth
+    fallbacks), non-16-byte rows (flat path), striped shards and host-resident misses: bit-exact."""
+    import os
+    rng = np.random.default_rng(row_bytes * 7 + n)
+    V = 30000
+    src = rng.integers(0, 256, size=(V, row_bytes), dtype=np.uint8)
+    rank = rng.permutation(V).astype(np.uint32)
+    nc = oracle.num_cached(V, pct)
+    table_ref = oracle.cache_table_build(rank, V, nc)
+    nodes = rng.integers(0, V, size=n_max).astype(np.uint32)
+    exp = src[nodes[:n]]
+    cache = src[rank[:nc]]
+    bufs = []
+    for t in range(shards):
+        rows = cache[t::shards]
+        bufs.append(torch.from_numpy(np.ascontiguousarray(rows)).cuda() if len(rows) else
+                    torch.zeros((1, row_bytes), dtype=torch.uint8, device="cuda"))
+    ptrs = torch.tensor([b.data_ptr() for b in bufs], dtype=torch.int64, device="cuda")
+    host_src = torch.from_numpy(src).pin_memory()
+    out = torch.full((n_max + 1, row_bytes), 0xA5, dtype=torch.uint8, device="cuda")
+    stats = torch.zeros(2, dtype=torch.int64, device="cuda")
+    d_n = torch.tensor([n], dtype=torch.int32, device="cuda")
+    old = {k: os.environ.get(k) for k in ("FGNN_TUNING_DYNAMIC", "FGNN_GATHER_IMPL")}
+    os.environ["FGNN_TUNING_DYNAMIC"] = "1"
+    os.environ["FGNN_GATHER_IMPL"] = impl
+    try:
+        K.gather_cached(out, dev(nodes), n_max, d_n, dev(table_ref), ptrs, shards, host_src, row_bytes, stats)
+        torch.cuda.synchronize()
+    finally:
+        for k, v in old.items():
+            if v is None:
+                os.environ.pop(k, None)
+            else:
+                os.environ[k] = v
+    got = out.cpu().numpy()
+    assert np.array_equal(got[:n], exp)
+    assert (got[n:] == 0xA5).all(), "rows beyond the device count must not be written"
+    hit = int((table_ref[nodes[:n]] != 0xFFFFFFFF).sum())
+    assert stats.tolist() == [hit, n - hit]
+
+
 # ---------------------------------------------------------------------------
 def test_presc_count_and_rank(K, oracle):
     rng = np.random.default_rng(3)
