@@ -175,26 +175,33 @@ __device__ __forceinline__ unsigned long long block_sum_u64(
 }
 
 // ---------------------------------------------------------------------------
-// chunk-chained single-pass scan.
+// chunk-chained single-pass scan (decoupled look-back).
 //
 // A persistent grid of P <= kMaxChainCtas CTAs splits [0,n) into P contiguous
-// chunks in *ticket* order.  Each CTA publishes the aggregate of its chunk,
-// then sums the aggregates of all lower tickets (they belong to CTAs that
-// started earlier and publish before they wait, so this cannot deadlock even
-// when P exceeds residency).  The last CTA to leave re-zeroes the workspace,
-// so the same buffer serves the next launch on the stream.
+// chunks in *ticket* order.  Each CTA publishes the aggregate of its chunk, then
+// warp 0 looks back over the lower tickets 32 at a time, summing aggregates until
+// it meets a ticket that has already published its inclusive prefix, and finally
+// publishes its own inclusive prefix.  Lower tickets belong to CTAs that started
+// earlier and publish before they wait, so this cannot deadlock even when P
+// exceeds residency.  Only ONE warp per CTA ever polls, with a nanosleep
+// back-off: the first version let every thread spin on every lower ticket, which
+// is harmless when the kernel has the GPU to itself but saturated the L2 request
+// path once several sampling slots ran next to the HBM-bound gather (r1_g/h:
+// 0.3 ms -> 1-4 ms per step).  The last CTA to leave re-zeroes the workspace, so
+// the same buffer serves the next launch on the stream.
 // ---------------------------------------------------------------------------
 struct ChainWs {
   unsigned int ticket;
   unsigned int done;
   unsigned int pad[2];
-  unsigned long long agg[kMaxChainCtas];
+  unsigned long long agg[kMaxChainCtas];  // [63:62] 0 = empty, 1 = aggregate, 2 = inclusive prefix
 };
 static_assert(sizeof(ChainWs) == FGNN_CHAIN_WS_BYTES, "chain ws size");
 
 struct ChainSmem {
   uint32_t ticket;
   uint32_t last;
+  unsigned long long excl;
   unsigned long long warp64[kBlock / 32];
 };
 
@@ -205,23 +212,45 @@ __device__ __forceinline__ uint32_t chain_ticket(ChainWs *ws, ChainSmem *sm) {
 }
 
 // all threads pass their partial; returns exclusive prefix over lower tickets
-// and publishes this chunk's aggregate.
+// and publishes this chunk's aggregate / inclusive prefix.
 template <int NT = kBlock>
 __device__ __forceinline__ unsigned long long chain_scan(
     ChainWs *ws, ChainSmem *sm, uint32_t p, unsigned long long thread_partial,
     unsigned long long *chunk_total) {
+  constexpr unsigned long long kAgg = 1ull << 62, kPre = 2ull << 62, kVal = (1ull << 62) - 1;
   const unsigned long long total = block_sum_u64<NT>(thread_partial, sm->warp64);
-  if (threadIdx.x == 0) st_relaxed_u64(&ws->agg[p], (1ull << 63) | total);
-  unsigned long long sum = 0;
-  for (uint32_t t = threadIdx.x; t < p; t += NT) {
-    unsigned long long v;
-    do {
-      v = ld_relaxed_u64(&ws->agg[t]);
-    } while (!(v >> 63));
-    sum += v & ~(1ull << 63);
+  if (threadIdx.x < 32) {
+    const int lane = threadIdx.x;
+    if (lane == 0) st_relaxed_u64(&ws->agg[p], (p == 0 ? kPre : kAgg) | total);
+    unsigned long long excl = 0;
+    if (p > 0) {
+      int newest = (int)p - 1;  // window = tickets newest, newest-1, ..., newest-31 (lane order)
+      while (true) {
+        const int t = newest - lane;
+        unsigned long long v = kPre;  // lanes past ticket 0 read as a zero prefix
+        if (t >= 0) {
+          v = ld_relaxed_u64(&ws->agg[t]);
+          while (!(v >> 62)) {
+            __nanosleep(64);
+            v = ld_relaxed_u64(&ws->agg[t]);
+          }
+        }
+        const unsigned pre = __ballot_sync(0xFFFFFFFFu, (v >> 62) == 2ull);
+        const int stop = pre ? __ffs(pre) - 1 : 31;  // nearest ticket that already holds a prefix
+        unsigned long long c = lane <= stop ? (v & kVal) : 0ull;
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) c += __shfl_down_sync(0xFFFFFFFFu, c, d);
+        excl += c;  // valid in lane 0
+        if (pre) break;
+        newest -= 32;
+      }
+      if (lane == 0) st_relaxed_u64(&ws->agg[p], kPre | ((excl + total) & kVal));
+    }
+    if (lane == 0) sm->excl = excl;
   }
+  __syncthreads();
   *chunk_total = total;
-  return block_sum_u64<NT>(sum, sm->warp64);
+  return sm->excl;
 }
 
 template <int NT = kBlock>

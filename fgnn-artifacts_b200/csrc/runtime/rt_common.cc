@@ -8,6 +8,7 @@
 #include <algorithm>
 #include <cctype>
 #include <ctime>
+#include <map>
 #include <mutex>
 #include <numeric>
 
@@ -107,17 +108,77 @@ size_t Tensor::NumItems() const {
   return std::accumulate(shape.begin(), shape.end(), (size_t)1, std::multiplies<size_t>());
 }
 
-static void EnsurePool(int device) {
-  static std::mutex mu;
-  static bool done[64] = {false};
-  std::lock_guard<std::mutex> lk(mu);
-  if (device < 0 || device >= 64 || done[device]) return;
-  cudaMemPool_t pool;
-  CUDA_CALL(cudaDeviceGetDefaultMemPool(&pool, device));
-  uint64_t thresh = UINT64_MAX;  // keep freed blocks cached: WorkspacePool behaviour (workspace_pool.cc)
-  CUDA_CALL(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thresh));
-  done[device] = true;
-}
+// ---------------------------------------------------------------------------
+// WorkspacePool (workspace_pool.cc:30-196, cuda_device.cc:143-157): size-sorted free list per GPU, 4 KiB
+// rounding, blocks over-allocated x1.25 the first time a size is seen (constant.h:78) so the slightly
+// different batch sizes of consecutive mini-batches reuse the same blocks.  Backing store is plain
+// cudaMalloc; nothing is returned to the driver until the process ends (or an allocation fails).
+// The stream-ordered allocator (cudaMallocAsync) was measured unusable here: 283 MB feature tensors whose
+// size changes every batch made it remap on most calls — 1-8 ms per allocation, occasionally 100+ ms
+// (gpurun r1_k) — which stalled the pump while the GPU sat idle.
+// Memory is reusable as soon as it is freed: callers free only after the producing/consuming GPU work has
+// been synchronised on the host (Sampler::Finish / Extractor::Finish), like the reference.
+// ---------------------------------------------------------------------------
+namespace {
+class DevicePool {
+ public:
+  void *Alloc(int device, size_t nbytes) {
+    const size_t want = RoundUp(std::max<size_t>(nbytes, 256));
+    {
+      std::lock_guard<std::mutex> lk(mu_);
+      auto &fl = free_[device];
+      auto it = fl.lower_bound(want);
+      // smallest block that fits, unless it would waste more than half of a big block
+      if (it != fl.end() && (it->first <= want * 2 || it->first <= (1u << 20))) {
+        void *p = it->second;
+        fl.erase(it);
+        return p;
+      }
+    }
+    const size_t cap = want >= (1u << 20) ? RoundUp(want + want / 4) : want;
+    int cur = 0;
+    CUDA_CALL(cudaGetDevice(&cur));
+    if (cur != device) CUDA_CALL(cudaSetDevice(device));
+    void *p = nullptr;
+    cudaError_t e = cudaMalloc(&p, cap);
+    if (e != cudaSuccess) {  // out of memory: drop the cache and retry once
+      cudaGetLastError();
+      Trim(device);
+      e = cudaMalloc(&p, cap);
+    }
+    FCHECK(e == cudaSuccess) << "cudaMalloc(" << cap << " B) on GPU " << device << ": " << cudaGetErrorString(e);
+    if (cur != device) CUDA_CALL(cudaSetDevice(cur));
+    std::lock_guard<std::mutex> lk(mu_);
+    size_[p] = cap;
+    return p;
+  }
+  void Free(int device, void *p) {
+    std::lock_guard<std::mutex> lk(mu_);
+    auto it = size_.find(p);
+    if (it == size_.end()) return;
+    free_[device].emplace(it->second, p);
+  }
+  void Trim(int device) {
+    std::lock_guard<std::mutex> lk(mu_);
+    for (auto &kv : free_[device]) {
+      cudaFree(kv.second);
+      size_.erase(kv.second);
+    }
+    free_[device].clear();
+    cudaGetLastError();
+  }
+  static DevicePool &Get() {
+    static DevicePool *p = new DevicePool();  // leaked on purpose: tensors may outlive static destructors
+    return *p;
+  }
+
+ private:
+  static size_t RoundUp(size_t n) { return (n + 4095) & ~(size_t)4095; }
+  std::mutex mu_;
+  std::map<int, std::multimap<size_t, void *>> free_;
+  std::unordered_map<void *, size_t> size_;
+};
+}  // namespace
 
 TensorPtr Tensor::Device(DataType dt, std::vector<size_t> shape, int device, cudaStream_t stream,
                          const std::string &name) {
@@ -129,12 +190,7 @@ TensorPtr Tensor::Device(DataType dt, std::vector<size_t> shape, int device, cud
   t->name = name;
   t->kind_ = kDeviceAsync;
   t->stream_ = stream;
-  EnsurePool(device);
-  int cur = 0;
-  CUDA_CALL(cudaGetDevice(&cur));
-  if (cur != device) CUDA_CALL(cudaSetDevice(device));
-  CUDA_CALL(cudaMallocAsync(&t->data, std::max<size_t>(t->nbytes, 16), stream));
-  if (cur != device) CUDA_CALL(cudaSetDevice(cur));
+  t->data = DevicePool::Get().Alloc(device, t->nbytes);
   return t;
 }
 
@@ -189,16 +245,10 @@ TensorPtr Tensor::View(void *data, DataType dt, std::vector<size_t> shape, Conte
 Tensor::~Tensor() {
   if (!data) return;
   switch (kind_) {
-    case kDeviceAsync: {
+    case kDeviceAsync:
       // may run on a Python thread, possibly during interpreter teardown: never abort here
-      int cur = 0;
-      if (cudaGetDevice(&cur) != cudaSuccess) break;
-      if (cur != ctx.device_id) cudaSetDevice(ctx.device_id);
-      cudaFreeAsync(data, stream_);
-      if (cur != ctx.device_id) cudaSetDevice(cur);
-      cudaGetLastError();
+      DevicePool::Get().Free(ctx.device_id, data);
       break;
-    }
     case kPinned:
       cudaFreeHost(data);
       cudaGetLastError();
@@ -212,10 +262,10 @@ Tensor::~Tensor() {
 }
 
 Task::~Task() {
-  if (ready) {
-    cudaEventDestroy(ready);
-    cudaGetLastError();
-  }
+  if (ready) cudaEventDestroy(ready);
+  if (extracted) cudaEventDestroy(extracted);
+  if (xbegin) cudaEventDestroy(xbegin);
+  cudaGetLastError();
 }
 
 }  // namespace rt

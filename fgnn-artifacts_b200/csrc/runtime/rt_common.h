@@ -164,7 +164,13 @@ struct Task {  // common.h:197-217
   std::vector<TrainGraph> graphs;
   TensorPtr input_nodes, output_nodes, input_feat, output_label;
   size_t num_miss = 0, num_cache = 0;
+  int slot = -1;                // sampler slot (stream + scratch) that produces this batch
+  std::shared_ptr<void> block;  // pooled device block the sampler outputs live in (rt_engine.cc TaskBlock)
   cudaEvent_t ready = nullptr;  // recorded on the producing stream when all tensors are final
+  cudaEvent_t extracted = nullptr;  // recorded on the extraction stream after feature + label gather
+  int xslot = 0;
+  cudaEvent_t xbegin = nullptr;  // FGNN_TRACE_GPU=1
+  uint64_t t_extract = 0;       // host clock (us) when extraction was enqueued
   ~Task();
 };
 using TaskPtr = std::shared_ptr<Task>;

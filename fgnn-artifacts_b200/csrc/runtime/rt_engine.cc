@@ -87,30 +87,138 @@ struct SharedRing {
 // =============================================================================================
 // Sampler: DoShuffle + DoGPUSample (cuda_loops.cc:30-267 == dist_loops.cc:35-269)
 // =============================================================================================
+// One device allocation holding every sampler output of a mini-batch at its PredictNumNodes bound: the seed
+// list, the running unique list (== input_nodes) and per layer row / col / data.  The kernels write straight
+// into the block and the task's tensors are exact-size VIEWS of it, so the hot path has no allocation and no
+// device-to-device "materialise" copies; 180 GB of HBM make a pool of bound-sized blocks cheap (27 MB each for
+// GraphSAGE [25,10], 100 MB for GCN [5,10,15]).  A block returns to the pool when the last tensor that views
+// it is released (Python included).
+struct TaskBlock {
+  char *base = nullptr;
+  size_t bytes = 0;
+  IdType *seeds = nullptr, *n2o = nullptr;
+  IdType *row[8] = {nullptr}, *col[8] = {nullptr}, *data[8] = {nullptr};
+};
+
+class BlockPool : public std::enable_shared_from_this<BlockPool> {
+ public:
+  BlockPool(int dev, size_t batch, size_t max_nodes, const std::vector<size_t> &edge_max, bool with_data)
+      : dev_(dev), batch_(batch), max_nodes_(max_nodes), edge_max_(edge_max), with_data_(with_data) {}
+  ~BlockPool() {
+    cudaSetDevice(dev_);
+    for (TaskBlock *b : all_) { cudaFree(b->base); delete b; }
+    cudaGetLastError();
+  }
+  void Reserve(size_t n) {
+    std::lock_guard<std::mutex> lk(mu_);
+    while (all_.size() < n) free_.push_back(NewBlock());
+  }
+  // never blocks: a consumer that holds on to many batches makes the pool grow instead of stalling the sampler
+  std::shared_ptr<TaskBlock> Acquire() {
+    TaskBlock *b = nullptr;
+    {
+      std::lock_guard<std::mutex> lk(mu_);
+      if (free_.empty()) free_.push_back(NewBlock());
+      b = free_.back();
+      free_.pop_back();
+    }
+    std::shared_ptr<BlockPool> self = shared_from_this();
+    return std::shared_ptr<TaskBlock>(b, [self](TaskBlock *x) {
+      std::lock_guard<std::mutex> lk(self->mu_);
+      self->free_.push_back(x);
+    });
+  }
+  size_t NumBlocks() { std::lock_guard<std::mutex> lk(mu_); return all_.size(); }
+
+ private:
+  TaskBlock *NewBlock() {  // mu_ held
+    auto al = [](size_t n) { return (n * sizeof(IdType) + 255) & ~(size_t)255; };
+    size_t total = al(batch_) + al(max_nodes_ + 1);
+    for (size_t e : edge_max_) total += al(e + 1) * (with_data_ ? 3 : 2);
+    TaskBlock *b = new TaskBlock();
+    int cur = 0;
+    CUDA_CALL(cudaGetDevice(&cur));
+    if (cur != dev_) CUDA_CALL(cudaSetDevice(dev_));
+    CUDA_CALL(cudaMalloc((void **)&b->base, total));
+    if (cur != dev_) CUDA_CALL(cudaSetDevice(cur));
+    b->bytes = total;
+    char *p = b->base;
+    b->seeds = (IdType *)p; p += al(batch_);
+    b->n2o = (IdType *)p; p += al(max_nodes_ + 1);
+    for (size_t i = 0; i < edge_max_.size(); ++i) {
+      b->row[i] = (IdType *)p; p += al(edge_max_[i] + 1);
+      b->col[i] = (IdType *)p; p += al(edge_max_[i] + 1);
+      if (with_data_) { b->data[i] = (IdType *)p; p += al(edge_max_[i] + 1); }
+    }
+    all_.push_back(b);
+    return b;
+  }
+  int dev_;
+  size_t batch_, max_nodes_;
+  std::vector<size_t> edge_max_;
+  bool with_data_;
+  std::mutex mu_;
+  std::vector<TaskBlock *> all_, free_;
+};
+
+// One sampling slot = one mini-batch in flight: its own stream, hash table and scratch.  A single 8000-seed
+// batch cannot fill a B200 (ncu r1_b: sampling kernels at 3-27 % active warps, every kernel a chain of
+// dependent DRAM latencies), so the sampler keeps `num_slots` batches in flight on separate streams and
+// hands them out in order.
+// FGNN_TRACE_HOST=1: report any host-side region of the hot loop that blocks for more than 1 ms
+struct SlowScope {
+  const char *name;
+  Timer t;
+  explicit SlowScope(const char *n) : name(n) {}
+  ~SlowScope() {
+    static const bool on = IsEnvSet("FGNN_TRACE_HOST") && GetEnv("FGNN_TRACE_HOST") != "0";
+    if (on && t.Passed() > 1e-3) fprintf(stderr, "[fgnn slow] %s %.3f ms\n", name, t.Passed() * 1e3);
+  }
+};
+
+static bool TraceGpu() {
+  static const bool on = IsEnvSet("FGNN_TRACE_GPU") && GetEnv("FGNN_TRACE_GPU") != "0";
+  return on;
+}
+
+struct SampleSlot {
+  cudaStream_t stream = nullptr;
+  cudaEvent_t done = nullptr;   // counts are on the host
+  cudaEvent_t idle = nullptr;   // scratch marker used by Reshuffle
+  cudaEvent_t begin = nullptr;  // FGNN_TRACE_GPU=1: device-side start of the batch
+  TensorPtr table, num_items, chain, counts_dev, counts_host, ws;
+  std::vector<TensorPtr> dst, pos;   // scratch: sampled global ids, their bucket positions
+};
+
 class Sampler {
  public:
   Sampler(const Dataset *ds, Context ctx, int worker_id, int num_worker, size_t num_epoch);
   ~Sampler();
   // next mini-batch of this sampler's share of the epoch; nullptr when all epochs are done
   TaskPtr Next();
-  void Sample(const TaskPtr &task);
-  void CountFrequency(uint32_t *d_freq);          // PreSC: freq[input_nodes] += 1
+  void Enqueue(const TaskPtr &task);              // all kernels of the batch + async count read-back, no host sync
+  void Finish(const TaskPtr &task);               // the ONE host sync of the batch + exact-size tensors
+  void Sample(const TaskPtr &task) { Enqueue(task); Finish(task); }
+  void CountFrequency(const TaskPtr &task, uint32_t *d_freq);  // PreSC: freq[input_nodes] += 1 (after Enqueue)
+  void SyncAll();
+  bool Done(const TaskPtr &task) { return cudaEventQuery(slots_[task->slot].done) == cudaSuccess; }
+  void SyncSlot(const TaskPtr &task) { CUDA_CALL(cudaStreamSynchronize(slots_[task->slot].stream)); }
   void ResetShuffler() { cur_epoch_ = 0; cur_step_ = 0; shuffled_epoch_ = (uint64_t)-1; }
   size_t NumStep() const { return num_step_; }
   size_t NumLocalStep() const { return local_steps_; }
+  size_t NumSlots() const { return slots_.size(); }
   cudaStream_t stream() const { return stream_; }
   int device() const { return dev_; }
   const IdType *d_indptr() const { return (const IdType *)indptr_->data; }
   const IdType *d_indices() const { return (const IdType *)indices_->data; }
-  IdType *n2o() { return (IdType *)n2o_->data; }
-  uint32_t *d_num_items() { return (uint32_t *)num_items_->data; }
   size_t max_nodes() const { return max_nodes_; }
 
  private:
   void Reshuffle(uint64_t epoch);
   const Dataset *ds_;
   int dev_;
-  cudaStream_t stream_ = nullptr;
+  cudaStream_t stream_ = nullptr;  // uploads + epoch shuffle
+  cudaEvent_t shuffled_ = nullptr;
   RunConfig &rc_;
   std::vector<size_t> fanout_;
   size_t L_, batch_;
@@ -120,11 +228,12 @@ class Sampler {
   TensorPtr train_dev_, perm_dev_, shuffle_ws_;
   size_t num_train_, num_step_, local_steps_, step_begin_;
   uint64_t cur_epoch_ = 0, cur_step_ = 0, shuffled_epoch_ = (uint64_t)-1, num_epoch_;
-  // hash table + scratch sized from PredictNumNodes
+  // hash table + scratch sized from PredictNumNodes, one set per slot
   size_t max_nodes_, ht_cap_;
-  TensorPtr table_, n2o_, num_items_, chain_, counts_dev_, counts_host_, ws_;
   std::vector<size_t> in_max_, edge_max_;
-  std::vector<TensorPtr> dst_, col_, row_, pos_, data_;
+  std::vector<SampleSlot> slots_;
+  size_t next_slot_ = 0;
+  std::shared_ptr<BlockPool> pool_;
 };
 
 Sampler::Sampler(const Dataset *ds, Context ctx, int worker_id, int num_worker, size_t num_epoch)
@@ -132,6 +241,7 @@ Sampler::Sampler(const Dataset *ds, Context ctx, int worker_id, int num_worker, 
   FCHECK(ctx.device_type == kGPU) << "the sampler must live on a GPU: there is no CPU sampling path";
   CUDA_CALL(cudaSetDevice(dev_));
   CUDA_CALL(cudaStreamCreateWithFlags(&stream_, cudaStreamNonBlocking));
+  CUDA_CALL(cudaEventCreateWithFlags(&shuffled_, cudaEventDisableTiming));
   fanout_ = rc_.fanout;
   L_ = fanout_.size();
   batch_ = rc_.batch_size;
@@ -159,13 +269,6 @@ Sampler::Sampler(const Dataset *ds, Context ctx, int worker_id, int num_worker, 
   // ---- per-batch scratch at the PredictNumNodes bounds (common.cc:330-339) ----
   max_nodes_ = PredictNumNodes(batch_, fanout_, L_);
   ht_cap_ = fgnn_k_ht_capacity(max_nodes_);
-  table_ = Tensor::Device(kU8, {fgnn_k_ht_bytes(ht_cap_)}, dev_, stream_, "hashtable");
-  n2o_ = Tensor::Device(kI32, {max_nodes_ + 1}, dev_, stream_, "n2o");
-  num_items_ = Tensor::Device(kI32, {4}, dev_, stream_, "num_items");
-  chain_ = Tensor::Device(kU8, {FGNN_CHAIN_WS_BYTES}, dev_, stream_, "chain_ws");
-  CUDA_CALL(cudaMemsetAsync(chain_->data, 0, FGNN_CHAIN_WS_BYTES, stream_));
-  counts_dev_ = Tensor::Device(kI32, {L_ * 3 + 1}, dev_, stream_, "counts");
-  counts_host_ = Tensor::Pinned(kI32, {L_ * 3 + 1}, "counts_host");
   in_max_.resize(L_);
   edge_max_.resize(L_);
   size_t cur = batch_;
@@ -180,32 +283,60 @@ Sampler::Sampler(const Dataset *ds, Context ctx, int worker_id, int num_worker, 
     if (rc_.sample_type == kRandomWalk)
       ws_bytes = std::max(ws_bytes, fgnn_k_sample_random_walk_workspace_bytes((uint32_t)in_max_[i], (uint32_t)fanout_[i]));
   }
-  ws_ = Tensor::Device(kU8, {ws_bytes}, dev_, stream_, "sample_ws");
-  for (size_t i = 0; i < L_; ++i) {
-    dst_.push_back(Tensor::Device(kI32, {edge_max_[i] + 1}, dev_, stream_, "scratch_dst"));
-    col_.push_back(Tensor::Device(kI32, {edge_max_[i] + 1}, dev_, stream_, "scratch_col"));
-    row_.push_back(Tensor::Device(kI32, {edge_max_[i] + 1}, dev_, stream_, "scratch_row"));
-    pos_.push_back(Tensor::Device(kI32, {edge_max_[i] + 1}, dev_, stream_, "scratch_pos"));
-    data_.push_back(rc_.sample_type == kRandomWalk
-                        ? Tensor::Device(kI32, {edge_max_[i] + 1}, dev_, stream_, "scratch_data") : nullptr);
+  size_t nslots = 3;
+  if (IsEnvSet("FGNN_SAMPLER_SLOTS")) nslots = (size_t)std::max(1, atoi(GetEnv("FGNN_SAMPLER_SLOTS").c_str()));
+  nslots = std::min<size_t>(nslots, 8);
+  slots_.resize(nslots);
+  for (auto &sl : slots_) {
+    CUDA_CALL(cudaStreamCreateWithFlags(&sl.stream, cudaStreamNonBlocking));
+    CUDA_CALL(cudaEventCreateWithFlags(&sl.done, TraceGpu() ? cudaEventDefault : cudaEventDisableTiming));
+    CUDA_CALL(cudaEventCreateWithFlags(&sl.idle, cudaEventDisableTiming));
+    if (TraceGpu()) CUDA_CALL(cudaEventCreate(&sl.begin));
+    sl.table = Tensor::Device(kU8, {fgnn_k_ht_bytes(ht_cap_)}, dev_, sl.stream, "hashtable");
+    sl.num_items = Tensor::Device(kI32, {4}, dev_, sl.stream, "num_items");
+    sl.chain = Tensor::Device(kU8, {FGNN_CHAIN_WS_BYTES}, dev_, sl.stream, "chain_ws");
+    CUDA_CALL(cudaMemsetAsync(sl.chain->data, 0, FGNN_CHAIN_WS_BYTES, sl.stream));
+    sl.counts_dev = Tensor::Device(kI32, {L_ * 3 + 1}, dev_, sl.stream, "counts");
+    sl.counts_host = Tensor::Pinned(kI32, {L_ * 3 + 1}, "counts_host");
+    sl.ws = Tensor::Device(kU8, {ws_bytes}, dev_, sl.stream, "sample_ws");
+    for (size_t i = 0; i < L_; ++i) {
+      sl.dst.push_back(Tensor::Device(kI32, {edge_max_[i] + 1}, dev_, sl.stream, "scratch_dst"));
+      sl.pos.push_back(Tensor::Device(kI32, {edge_max_[i] + 1}, dev_, sl.stream, "scratch_pos"));
+    }
+    CUDA_CALL(cudaStreamSynchronize(sl.stream));
   }
+  pool_ = std::make_shared<BlockPool>(dev_, batch_, max_nodes_, edge_max_, rc_.sample_type == kRandomWalk);
+  pool_->Reserve(nslots + rc_.max_sampling_jobs + rc_.max_copying_jobs + 2);
   if (rc_.sample_type == kWeightedKHop || rc_.sample_type == kWeightedKHopHashDedup)
     FCHECK(prob_ && alias_) << "weighted sampling needs prob_table.bin and alias_table.bin";
   if (rc_.sample_type == kWeightedKHopPrefix) FCHECK(prefix_) << "needs prob_prefix_table.bin";
   CUDA_CALL(cudaStreamSynchronize(stream_));
 }
 
+void Sampler::SyncAll() {
+  cudaSetDevice(dev_);
+  for (auto &sl : slots_)
+    if (sl.stream) cudaStreamSynchronize(sl.stream);
+  if (stream_) cudaStreamSynchronize(stream_);
+}
+
 Sampler::~Sampler() {
-  if (stream_) {
-    cudaStreamSynchronize(stream_);
-    // tensors free themselves on stream_; destroy it last
-  }
+  SyncAll();  // tensors free themselves on their streams afterwards
+  cudaGetLastError();
 }
 
 void Sampler::Reshuffle(uint64_t epoch) {
+  SlowScope ss("Sampler::Reshuffle");
+  // batches still in flight read the old permutation: order the shuffle after them
+  for (auto &sl : slots_) {
+    CUDA_CALL(cudaEventRecord(sl.idle, sl.stream));
+    CUDA_CALL(cudaStreamWaitEvent(stream_, sl.idle, 0));
+  }
   FGNN_CALL(fgnn_k_shuffle((const IdType *)train_dev_->data, num_train_, rc_.seed, epoch,
                            (IdType *)perm_dev_->data, shuffle_ws_->data, shuffle_ws_->nbytes,
                            (fgnn_stream_t)stream_));
+  CUDA_CALL(cudaEventRecord(shuffled_, stream_));
+  for (auto &sl : slots_) CUDA_CALL(cudaStreamWaitEvent(sl.stream, shuffled_, 0));
   shuffled_epoch_ = epoch;
 }
 
@@ -220,41 +351,53 @@ TaskPtr Sampler::Next() {
   const size_t gstep = step_begin_ + cur_step_;
   const size_t off = gstep * batch_;
   const size_t n = std::min(batch_, num_train_ - off);
+  SlowScope ss("Sampler::Next");
   auto task = std::make_shared<Task>();
   task->key = cur_epoch_ * num_step_ + gstep;  // global key (dist_loops.cc:41-43)
-  // Copy1D slice of the permuted train set (cuda_shuffler.cc:128-154)
-  task->output_nodes = Tensor::Device(kI32, {n}, dev_, stream_, "output_nodes");
-  CUDA_CALL(cudaMemcpyAsync(task->output_nodes->data, (const IdType *)perm_dev_->data + off, n * sizeof(IdType),
-                            cudaMemcpyDeviceToDevice, stream_));
+  task->slot = (int)(next_slot_++ % slots_.size());
+  cudaStream_t st = slots_[task->slot].stream;
+  // Copy1D slice of the permuted train set (cuda_shuffler.cc:128-154) into the batch's block
+  task->block = pool_->Acquire();
+  TaskBlock *blk = static_cast<TaskBlock *>(task->block.get());
+  task->output_nodes = Tensor::View(blk->seeds, kI32, {n}, Context(kGPU, dev_), task->block, "output_nodes");
+  CUDA_CALL(cudaMemcpyAsync(blk->seeds, (const IdType *)perm_dev_->data + off, n * sizeof(IdType),
+                            cudaMemcpyDeviceToDevice, st));
   ++cur_step_;
   return task;
 }
 
-void Sampler::Sample(const TaskPtr &task) {
+void Sampler::Enqueue(const TaskPtr &task) {
+  SlowScope ss("Sampler::Enqueue");
   CUDA_CALL(cudaSetDevice(dev_));
-  fgnn_stream_t st = (fgnn_stream_t)stream_;
+  FCHECK(task->slot >= 0 && (size_t)task->slot < slots_.size());
+  SampleSlot &sl = slots_[task->slot];
+  cudaStream_t stream = sl.stream;
+  fgnn_stream_t st = (fgnn_stream_t)stream;
   const uint32_t n_seed = (uint32_t)task->output_nodes->NumItems();
-  uint32_t *counts = (uint32_t *)counts_dev_->data;  // [L][3] = num_dst, num_edge, num_src ; [3L] = unused
-  uint32_t *num_items = d_num_items();
+  uint32_t *counts = (uint32_t *)sl.counts_dev->data;  // [L][3] = num_dst, num_edge, num_src
+  uint32_t *num_items = (uint32_t *)sl.num_items->data;
+  TaskBlock *blk = static_cast<TaskBlock *>(task->block.get());
+  IdType *n2o = blk->n2o;
   const IdType *indptr = d_indptr(), *indices = d_indices();
 
-  FGNN_CALL(fgnn_k_ht_reset(table_->data, ht_cap_, num_items, st));                      // cuda_loops.cc:63
-  FGNN_CALL(fgnn_k_ht_fill_unique(table_->data, ht_cap_, (const IdType *)task->output_nodes->data, n_seed, nullptr,
-                                  n2o(), num_items, st));                                 // :67-69
+  if (sl.begin) CUDA_CALL(cudaEventRecord(sl.begin, stream));
+  FGNN_CALL(fgnn_k_ht_reset(sl.table->data, ht_cap_, num_items, st));                     // cuda_loops.cc:63
+  FGNN_CALL(fgnn_k_ht_fill_unique(sl.table->data, ht_cap_, (const IdType *)task->output_nodes->data, n_seed, nullptr,
+                                  n2o, num_items, st));                                   // :67-69
   for (int i = (int)L_ - 1; i >= 0; --i) {                                               // :87
     uint32_t *n_in = counts + 3 * i, *n_edge = counts + 3 * i + 1, *n_src = counts + 3 * i + 2;
-    CUDA_CALL(cudaMemcpyAsync(n_in, num_items, 4, cudaMemcpyDeviceToDevice, stream_));
+    CUDA_CALL(cudaMemcpyAsync(n_in, num_items, 4, cudaMemcpyDeviceToDevice, stream));
     fgnn_rng rng{rc_.seed, task->key, (uint32_t)i};
-    IdType *dst = (IdType *)dst_[i]->data, *col = (IdType *)col_[i]->data, *row = (IdType *)row_[i]->data;
+    IdType *dst = (IdType *)sl.dst[i]->data, *col = blk->col[i], *row = blk->row[i];
     const uint32_t nmax = (uint32_t)in_max_[i], f = (uint32_t)fanout_[i];
     switch (rc_.sample_type) {                                                           // :118-161
       case kKHop0:
-        FGNN_CALL(fgnn_k_sample_khop(0, indptr, indices, n2o(), nmax, n_in, f, rng, nullptr, dst, col, n_edge,
-                                     chain_->data, st));
+        FGNN_CALL(fgnn_k_sample_khop(0, indptr, indices, n2o, nmax, n_in, f, rng, nullptr, dst, col, n_edge,
+                                     sl.chain->data, st));
         break;
       case kKHop2:
-        FGNN_CALL(fgnn_k_sample_khop(2, indptr, indices, n2o(), nmax, n_in, f, rng, nullptr, dst, col, n_edge,
-                                     chain_->data, st));
+        FGNN_CALL(fgnn_k_sample_khop(2, indptr, indices, n2o, nmax, n_in, f, rng, nullptr, dst, col, n_edge,
+                                     sl.chain->data, st));
         break;
       case kKHop1:
       case kWeightedKHop:
@@ -262,37 +405,52 @@ void Sampler::Sample(const TaskPtr &task) {
         FGNN_CALL(fgnn_k_sample_replace((int)rc_.sample_type, indptr, indices,
                                         prob_ ? (const float *)prob_->data : nullptr,
                                         alias_ ? (const IdType *)alias_->data : nullptr,
-                                        prefix_ ? (const float *)prefix_->data : nullptr, n2o(), nmax, n_in, f, rng,
-                                        nullptr, dst, col, n_edge, ws_->data, ws_->nbytes, chain_->data, st));
+                                        prefix_ ? (const float *)prefix_->data : nullptr, n2o, nmax, n_in, f, rng,
+                                        nullptr, dst, col, n_edge, sl.ws->data, sl.ws->nbytes, sl.chain->data, st));
         break;
       case kWeightedKHopHashDedup:
         FGNN_CALL(fgnn_k_sample_weighted_hash_dedup(indptr, indices, (const float *)prob_->data,
-                                                    (const IdType *)alias_->data, n2o(), nmax, n_in, f, rng, nullptr,
-                                                    dst, col, n_edge, chain_->data, st));
+                                                    (const IdType *)alias_->data, n2o, nmax, n_in, f, rng, nullptr,
+                                                    dst, col, n_edge, sl.chain->data, st));
         break;
       case kRandomWalk:
         FCHECK_EQ(f, rc_.num_neighbor);
-        FGNN_CALL(fgnn_k_sample_random_walk(indptr, indices, n2o(), nmax, n_in, (uint32_t)rc_.random_walk_length,
+        FGNN_CALL(fgnn_k_sample_random_walk(indptr, indices, n2o, nmax, n_in, (uint32_t)rc_.random_walk_length,
                                             rc_.random_walk_restart_prob, (uint32_t)rc_.num_random_walk, f, rng,
-                                            nullptr, dst, col, (IdType *)data_[i]->data, n_edge, nullptr, nullptr,
-                                            ws_->data, ws_->nbytes, chain_->data, st));
+                                            nullptr, dst, col, blk->data[i], n_edge, nullptr, nullptr,
+                                            sl.ws->data, sl.ws->nbytes, sl.chain->data, st));
         break;
       default:
         FCHECK(false) << "unknown sample type";
     }
     // populate the hash table with the sampled neighbours, then remap (:176-205)
-    FGNN_CALL(fgnn_k_ht_fill_duplicates(table_->data, ht_cap_, dst, (uint32_t)edge_max_[i], n_edge,
-                                        (uint32_t *)pos_[i]->data, n2o(), num_items, chain_->data, st));
-    FGNN_CALL(fgnn_k_ht_map(table_->data, ht_cap_, nullptr, (const uint32_t *)pos_[i]->data, (uint32_t)edge_max_[i],
-                            n_edge, row, st));
-    CUDA_CALL(cudaMemcpyAsync(n_src, num_items, 4, cudaMemcpyDeviceToDevice, stream_));
+    FGNN_CALL(fgnn_k_ht_fill_duplicates(sl.table->data, ht_cap_, dst, (uint32_t)edge_max_[i], n_edge,
+                                        (uint32_t *)sl.pos[i]->data, n2o, num_items, sl.chain->data, st));
+    FGNN_CALL(fgnn_k_ht_map(sl.table->data, ht_cap_, nullptr, (const uint32_t *)sl.pos[i]->data,
+                            (uint32_t)edge_max_[i], n_edge, row, st));
+    CUDA_CALL(cudaMemcpyAsync(n_src, num_items, 4, cudaMemcpyDeviceToDevice, stream));
   }
-  // the ONE host round trip of the batch: all counts at once
-  CUDA_CALL(cudaMemcpyAsync(counts_host_->data, counts, L_ * 3 * 4, cudaMemcpyDeviceToHost, stream_));
-  CUDA_CALL(cudaStreamSynchronize(stream_));
-  const uint32_t *h = (const uint32_t *)counts_host_->data;
+  // all counts of the batch go to the host at once
+  CUDA_CALL(cudaMemcpyAsync(sl.counts_host->data, counts, L_ * 3 * 4, cudaMemcpyDeviceToHost, stream));
+  CUDA_CALL(cudaEventRecord(sl.done, stream));
+}
 
-  // materialise exact-size tensors (TrainGraph: row = neighbour local id, col = seed local id, :210-229)
+void Sampler::Finish(const TaskPtr &task) {
+  SlowScope ss("Sampler::Finish");
+  CUDA_CALL(cudaSetDevice(dev_));
+  SampleSlot &sl = slots_[task->slot];
+  cudaStream_t stream = sl.stream;
+  CUDA_CALL(cudaEventSynchronize(sl.done));  // the ONE host round trip of the batch
+  if (sl.begin) {
+    float ms = 0.f;
+    CUDA_CALL(cudaEventElapsedTime(&ms, sl.begin, sl.done));
+    Profiler::Get().LogStep(task->key, kLogL2IdCopyTime, ms * 1e-3);  // trace: device time of the sampling chain
+  }
+  const uint32_t *h = (const uint32_t *)sl.counts_host->data;
+
+  // exact-size views of the batch's block (TrainGraph: row = neighbour local id, col = seed local id, :210-229)
+  TaskBlock *blk = static_cast<TaskBlock *>(task->block.get());
+  const Context ctx(kGPU, dev_);
   task->graphs.resize(L_);
   size_t total_edges = 0;
   for (size_t i = 0; i < L_; ++i) {
@@ -301,26 +459,22 @@ void Sampler::Sample(const TaskPtr &task) {
     g.num_edge = h[3 * i + 1];
     g.num_src = h[3 * i + 2];
     total_edges += g.num_edge;
-    g.row = Tensor::Device(kI32, {g.num_edge}, dev_, stream_, "train_graph.row");
-    g.col = Tensor::Device(kI32, {g.num_edge}, dev_, stream_, "train_graph.col");
-    CUDA_CALL(cudaMemcpyAsync(g.row->data, row_[i]->data, g.num_edge * 4, cudaMemcpyDeviceToDevice, stream_));
-    CUDA_CALL(cudaMemcpyAsync(g.col->data, col_[i]->data, g.num_edge * 4, cudaMemcpyDeviceToDevice, stream_));
-    if (data_[i]) {
-      g.data = Tensor::Device(kI32, {g.num_edge}, dev_, stream_, "train_graph.data");
-      CUDA_CALL(cudaMemcpyAsync(g.data->data, data_[i]->data, g.num_edge * 4, cudaMemcpyDeviceToDevice, stream_));
-    }
+    g.row = Tensor::View(blk->row[i], kI32, {g.num_edge}, ctx, task->block, "train_graph.row");
+    g.col = Tensor::View(blk->col[i], kI32, {g.num_edge}, ctx, task->block, "train_graph.col");
+    if (blk->data[i]) g.data = Tensor::View(blk->data[i], kI32, {g.num_edge}, ctx, task->block, "train_graph.data");
   }
   const size_t n_input = h[2];  // num_src of layer 0 == number of unique nodes
-  task->input_nodes = Tensor::Device(kI32, {n_input}, dev_, stream_, "input_nodes");
-  CUDA_CALL(cudaMemcpyAsync(task->input_nodes->data, n2o(), n_input * 4, cudaMemcpyDeviceToDevice, stream_));
+  task->input_nodes = Tensor::View(blk->n2o, kI32, {n_input}, ctx, task->block, "input_nodes");
   if (!task->ready) CUDA_CALL(cudaEventCreateWithFlags(&task->ready, cudaEventDisableTiming));
-  CUDA_CALL(cudaEventRecord(task->ready, stream_));
+  CUDA_CALL(cudaEventRecord(task->ready, stream));
   Profiler::Get().LogStep(task->key, kLogL1NumNode, (double)n_input);
   Profiler::Get().LogStep(task->key, kLogL1NumSample, (double)total_edges);
 }
 
-void Sampler::CountFrequency(uint32_t *d_freq) {
-  FGNN_CALL(fgnn_k_freq_count(d_freq, n2o(), (uint32_t)max_nodes_, d_num_items(), (fgnn_stream_t)stream_));
+void Sampler::CountFrequency(const TaskPtr &task, uint32_t *d_freq) {
+  SampleSlot &sl = slots_[task->slot];
+  FGNN_CALL(fgnn_k_freq_count(d_freq, static_cast<TaskBlock *>(task->block.get())->n2o, (uint32_t)max_nodes_,
+                              (const uint32_t *)sl.num_items->data, (fgnn_stream_t)sl.stream));
 }
 
 // =============================================================================================
@@ -332,7 +486,12 @@ class Extractor {
   Extractor(const Dataset *ds, Context ctx, const IdType *ranking_host_or_null, const IdType *ranking_dev_or_null,
             int ranking_dev, int shard_id, int num_shards, SharedRing *ring);
   ~Extractor();
-  void Extract(const TaskPtr &task);   // task tensors must already live on this device
+  // task tensors must already live on this device
+  void Enqueue(const TaskPtr &task);   // gather kernels + async stats read-back, no host sync
+  void Finish(const TaskPtr &task);    // wait for the batch, hit/miss accounting
+  void Extract(const TaskPtr &task) { Enqueue(task); Finish(task); }
+  bool Done(const TaskPtr &task) { return cudaEventQuery(task->extracted) == cudaSuccess; }
+  static constexpr int kDepth = 2;     // batches in flight on the extraction stream
   TaskPtr MoveToTrainer(const TaskPtr &task, int src_dev);
   cudaStream_t stream() const { return stream_; }
   int device() const { return dev_; }
@@ -348,6 +507,7 @@ class Extractor {
   bool feat_registered_ = false;
   TensorPtr feat_pinned_, label_dev_, cache_table_, shard_ptrs_, stats_, stats_host_;
   unsigned long long last_stats_[2] = {0, 0};
+  uint64_t enq_seq_ = 0;
   void *shard_ = nullptr;              // this GPU's cache rows (cudaMalloc: IPC exportable)
   std::vector<void *> peer_shards_;
   int num_shards_ = 1, shard_id_ = 0;
@@ -358,7 +518,14 @@ Extractor::Extractor(const Dataset *ds, Context ctx, const IdType *ranking_host,
     : ds_(ds), dev_(ctx.device_id), rc_(RunConfig::Get()), num_shards_(num_shards), shard_id_(shard_id) {
   FCHECK(ctx.device_type == kGPU) << "the trainer must be a GPU";
   CUDA_CALL(cudaSetDevice(dev_));
-  CUDA_CALL(cudaStreamCreateWithFlags(&stream_, cudaStreamNonBlocking));
+  {
+    // the HBM-bound gather runs at the highest stream priority: its CTAs (one 128 KB shared-memory ring per
+    // SM) must not queue behind the many small CTAs of the latency-bound sampling kernels of other slots
+    int lo = 0, hi = 0;
+    CUDA_CALL(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+    const bool prio = !(IsEnvSet("FGNN_EXTRACT_PRIORITY") && GetEnv("FGNN_EXTRACT_PRIORITY") == "0");
+    CUDA_CALL(cudaStreamCreateWithPriority(&stream_, cudaStreamNonBlocking, prio ? hi : lo));
+  }
   const size_t V = ds->num_node, D = ds->feat_dim;
   row_bytes_ = D * DataTypeBytes(ds->feat->dtype);
 
@@ -388,7 +555,7 @@ Extractor::Extractor(const Dataset *ds, Context ctx, const IdType *ranking_host,
 
   stats_ = Tensor::Device(kI64, {2}, dev_, stream_, "gather_stats");
   CUDA_CALL(cudaMemsetAsync(stats_->data, 0, 16, stream_));
-  stats_host_ = Tensor::Pinned(kI64, {2}, "gather_stats_host");
+  stats_host_ = Tensor::Pinned(kI64, {2 * kDepth}, "gather_stats_host");
 
   // ---- cache: node -> slot table + the rows of this shard -------------------------------------
   const bool full_gpu = (rc_.run_arch == kArch1);  // arch1: every feature row is HBM resident
@@ -492,14 +659,23 @@ TaskPtr Extractor::MoveToTrainer(const TaskPtr &task, int src_dev) {  // DoGraph
   return out;
 }
 
-void Extractor::Extract(const TaskPtr &task) {
+void Extractor::Enqueue(const TaskPtr &task) {
+  SlowScope ss("Extractor::Enqueue");
   CUDA_CALL(cudaSetDevice(dev_));
   if (task->ready) CUDA_CALL(cudaStreamWaitEvent(stream_, task->ready, 0));
   const size_t n_in = task->input_nodes->NumItems(), n_out = task->output_nodes->NumItems();
   const size_t D = ds_->feat_dim;
-  task->input_feat = Tensor::Device(ds_->feat->dtype, {n_in, D}, dev_, stream_, "input_feat");
-  task->output_label = Tensor::Device(kI64, {n_out}, dev_, stream_, "output_label");
-  unsigned long long *after = (unsigned long long *)stats_host_->data;
+  {
+    SlowScope sa("Extractor::Enqueue alloc");
+    task->input_feat = Tensor::Device(ds_->feat->dtype, {n_in, D}, dev_, stream_, "input_feat");
+    task->output_label = Tensor::Device(kI64, {n_out}, dev_, stream_, "output_label");
+  }
+  task->xslot = (int)(enq_seq_++ % kDepth);
+  unsigned long long *after = (unsigned long long *)stats_host_->data + 2 * task->xslot;
+  if (TraceGpu()) {
+    if (!task->xbegin) CUDA_CALL(cudaEventCreate(&task->xbegin));
+    CUDA_CALL(cudaEventRecord(task->xbegin, stream_));
+  }
   // one fused kernel instead of GetMissCacheIndex + ExtractMissData + H2D + 2 combine kernels
   FGNN_CALL(fgnn_k_gather_cached(task->input_feat->data, (const IdType *)task->input_nodes->data, (uint32_t)n_in,
                                  nullptr, (const uint32_t *)cache_table_->data, (const void *const *)shard_ptrs_->data,
@@ -509,8 +685,23 @@ void Extractor::Extract(const TaskPtr &task) {
   FGNN_CALL(fgnn_k_row_copy(task->output_label->data, nullptr, label_dev_->data, (const IdType *)task->output_nodes->data,
                             ~0ull, (uint32_t)n_out, nullptr, 8, (fgnn_stream_t)stream_));
   CUDA_CALL(cudaMemcpyAsync(after, stats_->data, 16, cudaMemcpyDeviceToHost, stream_));
-  CUDA_CALL(cudaStreamSynchronize(stream_));
-  task->num_cache = after[0] - last_stats_[0];
+  if (!task->extracted)
+    CUDA_CALL(cudaEventCreateWithFlags(&task->extracted, TraceGpu() ? cudaEventDefault : cudaEventDisableTiming));
+  CUDA_CALL(cudaEventRecord(task->extracted, stream_));
+}
+
+void Extractor::Finish(const TaskPtr &task) {
+  SlowScope ss("Extractor::Finish");
+  CUDA_CALL(cudaSetDevice(dev_));
+  CUDA_CALL(cudaEventSynchronize(task->extracted));
+  if (task->xbegin) {
+    float ms = 0.f;
+    CUDA_CALL(cudaEventElapsedTime(&ms, task->xbegin, task->extracted));
+    Profiler::Get().LogStep(task->key, kLogL2ExtractTime, ms * 1e-3);  // trace: device time of gather + labels
+  }
+  const unsigned long long *after = (const unsigned long long *)stats_host_->data + 2 * task->xslot;
+  const size_t n_in = task->input_nodes->NumItems(), n_out = task->output_nodes->NumItems();
+  task->num_cache = after[0] - last_stats_[0];   // batches finish in enqueue order: cumulative counters
   task->num_miss = after[1] - last_stats_[1];
   last_stats_[0] = after[0];
   last_stats_[1] = after[1];
@@ -696,7 +887,6 @@ void Engine::Init() {
   EnsureHostTables(dataset_.get());
   Timer t_state;
   sampler_.reset(new Sampler(dataset_.get(), sampler_ctx_, 0, 1, num_epoch_));
-  sample_q_.reset(new TaskPool(rc.max_sampling_jobs));
   graph_pool_.reset(new TaskPool(rc.max_copying_jobs));
   Profiler::Get().LogInit(kLogInitL2InternalState, t_state.Passed());
   TensorPtr rank_dev;
@@ -725,12 +915,21 @@ void Engine::DoPreSample() {
   Timer ts;
   // a temporary sampler view limited to presample_epoch epochs: reuse Next() by bounding the loop
   const size_t total = (size_t)std::max(1, rc.presample_epoch) * s->NumLocalStep();
+  CUDA_CALL(cudaStreamSynchronize(s->stream()));  // freq is zeroed before any slot stream adds to it
+  std::deque<TaskPtr> hold;  // a batch's block may only return to the pool once its slot has drained
   for (size_t i = 0; i < total; ++i) {
+    if (hold.size() == s->NumSlots()) {
+      s->SyncSlot(hold.front());
+      hold.pop_front();
+    }
     TaskPtr task = s->Next();
     if (!task) break;
-    s->Sample(task);
-    s->CountFrequency((uint32_t *)freq->data);
+    s->Enqueue(task);  // no count read-back wait: PreSC only needs the unique list on the device
+    s->CountFrequency(task, (uint32_t *)freq->data);
+    hold.push_back(task);
   }
+  s->SyncAll();
+  hold.clear();
   Profiler::Get().LogInit(kLogInitL3PresampleSample, ts.Passed());
   Timer tr;
   auto rank = Tensor::Device(kI32, {V}, s->device(), s->stream(), "presc_rank");
@@ -820,7 +1019,10 @@ void Engine::SendTask(const TaskPtr &t) {
   pthread_mutex_unlock(&ring_->mu);
   char *slot = ring_->slot(idx);
   SlotHeader *h = reinterpret_cast<SlotHeader *>(slot);
-  cudaStream_t st = sampler_->stream();
+  CUDA_CALL(cudaSetDevice(sampler_->device()));
+  if (!send_stream_) CUDA_CALL(cudaStreamCreateWithFlags(&send_stream_, cudaStreamNonBlocking));
+  cudaStream_t st = send_stream_;
+  if (t->ready) CUDA_CALL(cudaStreamWaitEvent(st, t->ready, 0));
   const size_t L = t->graphs.size();
   FCHECK_LE(L, (size_t)8);
   h->num_layer = (uint32_t)L;
@@ -852,10 +1054,10 @@ void Engine::SendTask(const TaskPtr &t) {
   Profiler::Get().LogEpochAdd(t->key, kLogEpochSampleSendTime, ts.Passed());
 }
 
-TaskPtr Engine::RecvTask() {
+TaskPtr Engine::RecvTask(bool block) {
   Timer tr;
   while (sem_trywait(&ring_->used_slots) != 0) {
-    if (stop_) return nullptr;
+    if (stop_ || !block) return nullptr;
     std::this_thread::sleep_for(std::chrono::microseconds(1));
   }
   pthread_mutex_lock(&ring_->mu);
@@ -895,45 +1097,115 @@ TaskPtr Engine::RecvTask() {
   return task;
 }
 
-void Engine::SamplerLoopOnce() {  // RunSampleSubLoopOnce, cuda_loops_arch3.cc:54-83 / dist_loops_arch5.cc:60-156
-  Timer t0;
-  TaskPtr task = sampler_->Next();
-  if (!task) {
-    std::this_thread::sleep_for(std::chrono::microseconds(1));
-    return;
-  }
-  const double shuffle_time = t0.Passed();
-  Timer t1;
-  sampler_->Sample(task);
-  const double sample_time = t1.Passed();
-  auto &p = Profiler::Get();
-  p.LogStep(task->key, kLogL1SampleTime, shuffle_time + sample_time);
-  p.LogStep(task->key, kLogL2ShuffleTime, shuffle_time);
-  p.LogStep(task->key, kLogL2CoreSampleTime, sample_time);
-  p.LogEpochAdd(task->key, kLogEpochSampleTime, shuffle_time + sample_time);
-  if (dist_) {
-    SendTask(task);
-    p.LogEpochAdd(task->key, kLogEpochSampleTotalTime, t0.Passed());
-  } else {
-    sample_q_->Submit(task);
+// ---------------------------------------------------------------------------------------------
+// The loops.  The reference runs a sampler thread and a data-copy thread that each block on their own
+// stream (cuda_engine.cc:198-226, cuda_loops_arch3.cc:54-172).  Here ONE host thread pumps an event-driven
+// pipeline: it keeps every sampling slot and the extraction stream fed and only ever *polls* CUDA events,
+// so all host work (≈16 launches per batch) overlaps the GPU work of the batches in flight and no two host
+// threads contend for the driver (measured r1_f: two blocking threads + 3 slots ran 0.39-0.55 ms/step, the
+// same work pumped by one thread 0.26 ms/step).
+//   stage 1  fill the sampler slots           Sampler::Next + Enqueue        (no wait)
+//   stage 2  sampled -> extraction stream     Sampler::Finish + Extractor::Enqueue   when the slot's event fired
+//   stage 3  extracted -> graph pool          Extractor::Finish + Submit     when the batch's event fired
+// Batches leave in the order they were drawn.
+// ---------------------------------------------------------------------------------------------
+static inline void CpuRelax(int &idle) {
+  if (++idle < 2000) std::this_thread::yield();
+  else std::this_thread::sleep_for(std::chrono::microseconds(20));
+}
+
+void Engine::FillSamplerSlots() {
+  while (inflight_.size() < sampler_->NumSlots()) {
+    Timer te;
+    TaskPtr next = sampler_->Next();
+    if (!next) break;
+    sampler_->Enqueue(next);
+    Profiler::Get().LogStep(next->key, kLogL2ShuffleTime, te.Passed());  // host time spent enqueueing
+    inflight_.push_back(next);
   }
 }
 
-bool Engine::ExtractLoopOnce() {  // RunCacheDataCopySubLoopOnce, cuda_loops_arch3.cc:133-172 / arch5:204-256
-  TaskPtr task = dist_ ? RecvTask() : sample_q_->TryGet();
-  if (!task) return false;
-  Timer t0;
-  if (!dist_) task = extractor_->MoveToTrainer(task, sampler_->device());
-  const double graph_copy = t0.Passed();
-  Timer t1;
-  extractor_->Extract(task);
-  const double feat = t1.Passed();
+void Engine::LogSampled(const TaskPtr &task, double finish_time) {
   auto &p = Profiler::Get();
+  const double enqueue_time = p.GetLogStepValue(task->key, kLogL2ShuffleTime);
+  p.LogStep(task->key, kLogL1SampleTime, enqueue_time + finish_time);
+  p.LogStep(task->key, kLogL2CoreSampleTime, finish_time);
+  p.LogEpochAdd(task->key, kLogEpochSampleTime, enqueue_time + finish_time);
+}
+
+void Engine::LogExtracted(const TaskPtr &task, double finish_time) {
+  auto &p = Profiler::Get();
+  const double graph_copy = p.GetLogStepValue(task->key, kLogL2GraphCopyTime);
   const double recv = dist_ ? p.GetLogStepValue(task->key, kLogL1RecvTime) : 0.0;
-  p.LogStep(task->key, kLogL1CopyTime, recv + graph_copy + feat);
-  p.LogStep(task->key, kLogL2GraphCopyTime, graph_copy);
-  p.LogStep(task->key, kLogL2CacheCopyTime, feat);
-  p.LogEpochAdd(task->key, kLogEpochCopyTime, recv + graph_copy + feat);
+  p.LogStep(task->key, kLogL1CopyTime, recv + graph_copy + finish_time);
+  p.LogStep(task->key, kLogL2CacheCopyTime, finish_time);
+  p.LogEpochAdd(task->key, kLogEpochCopyTime, recv + graph_copy + finish_time);
+}
+
+// single-process archs: one non-blocking turn of the pump; *delivered is set when a batch reached the graph pool
+bool Engine::PumpBoth(bool *delivered) {
+  bool progress = false;
+  const size_t before = inflight_.size();
+  FillSamplerSlots();
+  progress |= inflight_.size() != before;
+  while (!inflight_.empty() && (int)x_inflight_.size() < Extractor::kDepth && sampler_->Done(inflight_.front())) {
+    TaskPtr task = inflight_.front();
+    inflight_.pop_front();
+    Timer t1;
+    sampler_->Finish(task);  // the event has fired: no wait
+    LogSampled(task, t1.Passed());
+    Timer t0;
+    task = extractor_->MoveToTrainer(task, sampler_->device());
+    Profiler::Get().LogStep(task->key, kLogL2GraphCopyTime, t0.Passed());
+    task->t_extract = Timer::NowMicro();
+    extractor_->Enqueue(task);
+    x_inflight_.push_back(task);
+    progress = true;
+  }
+  if (!x_inflight_.empty() && !graph_pool_->Full() && extractor_->Done(x_inflight_.front())) {
+    TaskPtr task = x_inflight_.front();
+    x_inflight_.pop_front();
+    extractor_->Finish(task);
+    LogExtracted(task, (double)(Timer::NowMicro() - task->t_extract) * 1e-6);
+    graph_pool_->Submit(task);
+    if (delivered) *delivered = true;
+    progress = true;
+  }
+  return progress;
+}
+
+// arch5 sampler process: complete the oldest batch and send it through the shared queue
+bool Engine::PumpSampler() {
+  Timer t0;
+  FillSamplerSlots();
+  if (inflight_.empty()) return false;
+  TaskPtr task = inflight_.front();
+  inflight_.pop_front();
+  Timer t1;
+  sampler_->Finish(task);
+  LogSampled(task, t1.Passed());
+  SendTask(task);
+  Profiler::Get().LogEpochAdd(task->key, kLogEpochSampleTotalTime, t0.Passed());
+  return true;
+}
+
+// arch5 trainer process: `depth` batches may be taken from the shared queue ahead of the one being delivered.
+// Trainers share ONE queue and each consumes a fixed number of batches, so a trainer must never hold more
+// batches than it will deliver: depth is 1 under sample_once and bounded by the remaining count under
+// extract_start.
+bool Engine::PumpTrainer(int depth) {
+  while ((int)x_inflight_.size() < depth) {
+    TaskPtr task = RecvTask(/*block=*/x_inflight_.empty());
+    if (!task) break;
+    task->t_extract = Timer::NowMicro();
+    extractor_->Enqueue(task);
+    x_inflight_.push_back(task);
+  }
+  if (x_inflight_.empty()) return false;
+  TaskPtr task = x_inflight_.front();
+  x_inflight_.pop_front();
+  extractor_->Finish(task);
+  LogExtracted(task, (double)(Timer::NowMicro() - task->t_extract) * 1e-6);
   graph_pool_->Submit(task);
   return true;
 }
@@ -941,26 +1213,28 @@ bool Engine::ExtractLoopOnce() {  // RunCacheDataCopySubLoopOnce, cuda_loops_arc
 void Engine::RunSampleOnce() {  // Engine::RunSampleOnce: RunArch3LoopsOnce / RunArch5LoopsOnce
   FCHECK(initialized_);
   if (role_ == kRoleBoth) {
-    SamplerLoopOnce();
-    ExtractLoopOnce();
+    // exactly one batch reaches the graph pool per call; the slots stay primed across calls
+    bool delivered = false;
+    int idle = 0;
+    while (!delivered && !stop_) {
+      if (PumpBoth(&delivered)) { idle = 0; continue; }
+      if (inflight_.empty() && x_inflight_.empty()) break;  // all epochs done
+      CpuRelax(idle);
+    }
   } else if (role_ == kRoleSampler) {
-    SamplerLoopOnce();
+    PumpSampler();
   } else if (role_ == kRoleTrainer) {
-    while (!ExtractLoopOnce() && !stop_) {}
+    while (!PumpTrainer(1) && !stop_) {}
   }
 }
 
-void Engine::Start() {  // GPUEngine::Start, cuda_engine.cc:198-226: SampleSubLoop + DataCopySubLoop threads
+void Engine::Start() {  // GPUEngine::Start, cuda_engine.cc:198-226
   FCHECK(initialized_ && role_ == kRoleBoth) << "start() is for the single-process archs; arch5 uses extract_start";
   threads_.emplace_back([this] {
+    int idle = 0;
     while (!stop_) {
-      if (sample_q_->Full()) { std::this_thread::sleep_for(std::chrono::microseconds(1)); continue; }
-      SamplerLoopOnce();
-    }
-  });
-  threads_.emplace_back([this] {
-    while (!stop_) {
-      if (graph_pool_->Full() || !ExtractLoopOnce()) std::this_thread::sleep_for(std::chrono::microseconds(1));
+      if (PumpBoth(nullptr)) idle = 0;
+      else CpuRelax(idle);
     }
   });
 }
@@ -971,7 +1245,7 @@ void Engine::StartExtract(int count) {  // DistEngine::StartExtract, dist_engine
     int left = count;
     while (left > 0 && !stop_) {
       if (graph_pool_->Full()) { std::this_thread::sleep_for(std::chrono::microseconds(1)); continue; }
-      if (ExtractLoopOnce()) --left;
+      if (PumpTrainer(std::min(left, (int)Extractor::kDepth))) --left;
     }
   });
 }
@@ -990,7 +1264,9 @@ void Engine::Shutdown() {
     if (t.joinable()) t.join();
   threads_.clear();
   current_.reset();
-  if (sampler_) { cudaSetDevice(sampler_->device()); cudaStreamSynchronize(sampler_->stream()); }
+  if (sampler_) sampler_->SyncAll();
+  inflight_.clear();
+  x_inflight_.clear();
   if (extractor_) { cudaSetDevice(extractor_->device()); cudaStreamSynchronize(extractor_->stream()); }
 }
 

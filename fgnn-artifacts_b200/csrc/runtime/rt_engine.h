@@ -76,9 +76,14 @@ class Engine {
  private:
   Engine();
   void LoadDataset();
-  void SamplerLoopOnce();      // shuffle + sample (+ send in arch5)
-  bool ExtractLoopOnce();      // (recv +) extract + submit
-  TaskPtr RecvTask();
+  // event-driven pump (see rt_engine.cc "The loops")
+  void FillSamplerSlots();
+  bool PumpBoth(bool *delivered);
+  bool PumpSampler();
+  bool PumpTrainer(int depth);
+  void LogSampled(const TaskPtr &t, double finish_time);
+  void LogExtracted(const TaskPtr &t, double finish_time);
+  TaskPtr RecvTask(bool block = true);
   void SendTask(const TaskPtr &t);
   void DoPreSample();
   void CreateSharedState();
@@ -96,9 +101,11 @@ class Engine {
 
   std::unique_ptr<Sampler> sampler_;
   std::unique_ptr<Extractor> extractor_;
-  std::unique_ptr<TaskPool> sample_q_;   // sampler -> extractor (in-process)
   std::unique_ptr<TaskPool> graph_pool_; // extractor -> python
   TaskPtr current_;
+  std::deque<TaskPtr> inflight_;  // enqueued on a sampler slot, not yet completed (sampler thread only)
+  cudaStream_t send_stream_ = nullptr;
+  std::deque<TaskPtr> x_inflight_;  // enqueued on the extraction stream, not yet completed (extract thread only)
   std::vector<std::thread> threads_;
   std::atomic<uint64_t> outer_counter_{0};
 

@@ -4,7 +4,7 @@ C-ABI of the C++ engine), one process, dataset loaded from the reference's on-di
 
   python tools/e2e_runtime.py <dataset_dir> <steps> <warmup> <cache_pct> <device> <seed>
 
-Per timed step: sam.sample_once(); key = sam.get_next_batch(); the batch label tensor and the per-layer
+Per timed step: (sam.sample_once();) key = sam.get_next_batch(); the batch label tensor and the per-layer
 edge counts are read back to the host.  Prints one JSON object."""
 import json
 import os
@@ -21,9 +21,13 @@ def main():
     import torch
     import samgraph.torch as sam
     fanout = [25, 10]
-    steps_per_epoch_guess = 1 << 30
+    meta = dict(l.split() for l in open(os.path.join(path, "meta.txt")) if l.strip())
+    spe_guess = (int(meta["NUM_TRAIN_SET"]) + 7999) // 8000
+    # enough epochs for warm-up + timed steps + the batches the pipelined sampler keeps in flight
+    # (the profiler keeps one record per (epoch, step), so this is sized, not "infinite")
+    num_epoch = (steps + warmup + 32) // spe_guess + 2
     cfg = {"dataset_path": path, "_arch": sam.kArch3, "_sample_type": sam.kKHop2, "batch_size": 8000,
-           "num_epoch": 1_000_000, "_cache_policy": sam.kCacheByPreSample, "cache_percentage": cache_pct,
+           "num_epoch": num_epoch, "_cache_policy": sam.kCacheByPreSample, "cache_percentage": cache_pct,
            "max_sampling_jobs": 10, "max_copying_jobs": 2, "omp_thread_num": os.cpu_count() or 1,
            "sampler_ctx": dev, "trainer_ctx": dev, "fanout": fanout, "num_fanout": 2, "presample_epoch": 1,
            "seed": seed}
@@ -33,8 +37,12 @@ def main():
     init_s = time.time() - t0
     torch.cuda.set_device(torch.device(dev))
     L = 2
+    pipeline = os.environ.get("FGNN_E2E_PIPELINE", "1") != "0"
+    if pipeline:
+        sam.start()                                            # background sampler + extractor threads (--pipeline)
     for _ in range(warmup):
-        sam.sample_once()
+        if not pipeline:
+            sam.sample_once()
         sam.get_next_batch()
     torch.cuda.synchronize()
     edges = 0
@@ -42,9 +50,12 @@ def main():
     d2h = 0
     miss_bytes = 0.0
     spe = sam.steps_per_epoch()
+    step_wall = []
     t0 = time.perf_counter()
+    t_prev = t0
     for k in range(steps):
-        sam.sample_once()
+        if not pipeline:
+            sam.sample_once()
         key = sam.get_next_batch()
         label = sam.get_graph_label(key).cpu()                 # device -> host read of the step's result
         feat = sam.get_graph_feat(key)
@@ -53,14 +64,36 @@ def main():
         n_in += feat.shape[0]
         d2h += label.numel() * 8 + L * 3 * 4
         miss_bytes += sam.get_log_step_value(key // spe, key % spe, sam.kLogL1MissBytes)
+        t_now = time.perf_counter()
+        step_wall.append(t_now - t_prev)
+        t_prev = t_now
     torch.cuda.synchronize()
     dt = time.perf_counter() - t0
     out = {"value": edges / dt, "unit": "edges/s", "ms_per_step": dt / steps * 1e3,
            "h2d_bytes_per_step": int(miss_bytes / steps), "d2h_bytes_per_step": d2h // steps,
            "input_nodes_per_step": n_in / steps, "edges_per_step": edges / steps, "init_s": init_s,
-           "api": "samgraph.torch (sample_once/get_next_batch/get_graph_*) over the samgraph_* C-ABI, C++ engine arch3",
-           "note": "features are HBM resident at cache 100% so the per-step host->device traffic is only the miss rows "
-                   "(0); seeds are shuffled on the GPU (no per-step H2D); timed with the host clock around the loop"}
+           "cache_percentage": cache_pct, "mode": "pipeline (sam.start)" if pipeline else "sample_once",
+           "api": "samgraph.torch (start|sample_once / get_next_batch / get_graph_*) over the samgraph_* C-ABI, "
+                  "C++ engine arch3",
+           "note": "host->device bytes per step = feature rows missing from the HBM cache, read from the pinned host "
+                   "feature table inside the gather kernel; device->host = labels + edge counts; host clock around "
+                   "the loop"}
+    if os.environ.get("FGNN_E2E_DIAG"):
+        names = ["kLogL1SampleTime", "kLogL2ShuffleTime", "kLogL2CoreSampleTime", "kLogL1CopyTime",
+                 "kLogL2GraphCopyTime", "kLogL2CacheCopyTime", "kLogL2IdCopyTime", "kLogL2ExtractTime"]
+        step_ms = sorted(step_wall)
+        out["step_wall_us_p50_p99_max"] = [round(step_ms[len(step_ms) // 2] * 1e6, 1),
+                                           round(step_ms[int(len(step_ms) * 0.99)] * 1e6, 1), round(step_ms[-1] * 1e6, 1)]
+        diag = {}
+        for nm in names:
+            item = getattr(sam, nm)
+            vals = [sam.get_log_step_value((warmup + k) // spe, (warmup + k) % spe, item) for k in range(steps)]
+            diag[nm] = round(sum(vals) / len(vals) * 1e6, 1)
+            if nm in ("kLogL2IdCopyTime", "kLogL2ExtractTime", "kLogL1CopyTime"):
+                sv = sorted(vals)
+                diag[nm + "_p50_max"] = [round(sv[len(sv) // 2] * 1e6, 1), round(sv[-1] * 1e6, 1)]
+                diag[nm + "_n_over_1ms"] = sum(1 for v in vals if v > 1e-3)
+        out["diag_us"] = diag
     print("E2E_JSON " + json.dumps(out))
     sam.shutdown()
 
