@@ -299,6 +299,26 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
       "}\n" ::"r"(bar), "r"(parity)
       : "memory");
 }
+// L2 policy for data that is touched once per batch (feature rows in, feature tensor out): evict-first, so
+// the 566 MB a gather streams through the 126 MB L2 do not displace the samplers' hash tables and the hot
+// part of the CSR that the batches in flight on the other streams live on.
+__device__ __forceinline__ uint64_t l2_evict_first_policy() {
+  uint64_t pol;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+  return pol;
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst_smem, const void *src, uint32_t bytes,
+                                         uint32_t bar, uint64_t pol) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(dst_smem),
+      "l"(src), "r"(bytes), "r"(bar), "l"(pol)
+      : "memory");
+}
+__device__ __forceinline__ void bulk_s2g(void *dst, uint32_t src_smem, uint32_t bytes, uint64_t pol) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group.L2::cache_hint [%0], [%1], %2, %3;" ::"l"(dst),
+               "r"(src_smem), "r"(bytes), "l"(pol)
+               : "memory");
+}
 __device__ __forceinline__ void bulk_g2s(uint32_t dst_smem, const void *src, uint32_t bytes,
                                          uint32_t bar) {
   asm volatile(
@@ -327,6 +347,9 @@ gather_bulk_kernel(char *__restrict__ out, const uint32_t *__restrict__ nodes, u
                    RowSrc rs, uint32_t G, uint32_t stage_bytes, int miss_by_ldg,
                    unsigned long long *d_stats) {
   rs.shard0 = (const char *)__ldg((const unsigned long long *)rs.shards);
+  const bool hint = (miss_by_ldg & 2) != 0;  // bit 1 of the mode word: stream through L2 with evict-first
+  miss_by_ldg &= 1;
+  const uint64_t pol = l2_evict_first_policy();
   constexpr int A = S - 2;  // sub-groups of loads in flight ahead of the store
   extern __shared__ __align__(128) unsigned char s_raw[];
   __shared__ __align__(8) unsigned long long s_bar[NW][S];
@@ -381,7 +404,10 @@ gather_bulk_kernel(char *__restrict__ out, const uint32_t *__restrict__ nodes, u
     const uint32_t nbulk = __popc(__ballot_sync(0xFFFFFFFFu, by_bulk));
     if (lane == 0) mbar_expect_tx(bar, nbulk * row_bytes);
     __syncwarp();
-    if (by_bulk) bulk_g2s(smem_u32(st + (size_t)(lane - sub * G) * row_bytes), sp, row_bytes, bar);
+    if (by_bulk) {
+      if (hint) bulk_g2s(smem_u32(st + (size_t)(lane - sub * G) * row_bytes), sp, row_bytes, bar, pol);
+      else bulk_g2s(smem_u32(st + (size_t)(lane - sub * G) * row_bytes), sp, row_bytes, bar);
+    }
     uint32_t ldg_rows = __ballot_sync(0xFFFFFFFFu, mine && !by_bulk);
     while (ldg_rows) {  // host-resident rows: warp-wide 16-byte loads into the stage
       const int r = __ffs(ldg_rows) - 1;
@@ -407,7 +433,8 @@ gather_bulk_kernel(char *__restrict__ out, const uint32_t *__restrict__ nodes, u
     fence_proxy_async();  // generic-proxy stage writes (miss rows) -> async proxy
     __syncwarp();
     if (lane == 0) {
-      bulk_s2g(out + row0 * row_bytes, smem_u32(stage0 + (size_t)s * stage_bytes), rows_here * row_bytes);
+      if (hint) bulk_s2g(out + row0 * row_bytes, smem_u32(stage0 + (size_t)s * stage_bytes), rows_here * row_bytes, pol);
+      else bulk_s2g(out + row0 * row_bytes, smem_u32(stage0 + (size_t)s * stage_bytes), rows_here * row_bytes);
       bulk_commit();
     }
   }
@@ -477,6 +504,7 @@ struct GatherTuning {
   int warps;        // bulk: warps per CTA
   uint32_t stage_cap;  // bulk: max bytes per stage
   int miss_ldg;     // bulk: host-resident rows by warp loads (1) or by the bulk engine (0)
+  int l2_hint;      // bulk: evict-first L2 policy on the streamed rows
   uint32_t group_rows; // group: rows per warp group (0 = auto)
   int ctas_per_sm;  // 0 = occupancy
 };
@@ -495,6 +523,7 @@ GatherTuning read_tuning() {
   g.warps = env_int("FGNN_BULK_WARPS", 8);
   g.stage_cap = (uint32_t)env_int("FGNN_BULK_STAGE_BYTES", 2048);
   g.miss_ldg = env_int("FGNN_BULK_MISS_LDG", 0);
+  g.l2_hint = env_int("FGNN_GATHER_L2HINT", 1);
   g.group_rows = (uint32_t)env_int("FGNN_GROUP_ROWS", 0);
   g.ctas_per_sm = env_int("FGNN_GATHER_CTAS_PER_SM", 0);
   return g;
@@ -522,7 +551,7 @@ int launch_bulk(char *out, const uint32_t *nodes, uint32_t n_max, const uint32_t
   const uint64_t subs = ((uint64_t)n_max + G - 1) / G;
   const int grid = persistent_grid(subs, NW * 4, occ, false);
   kern<<<grid, NW * 32, smem, st>>>(out, nodes, n_max, d_n, table, rs, G, stage_bytes,
-                                    tuning().miss_ldg, d_stats);
+                                    (tuning().miss_ldg ? 1 : 0) | (tuning().l2_hint ? 2 : 0), d_stats);
   return 0;
 }
 

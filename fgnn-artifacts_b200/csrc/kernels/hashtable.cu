@@ -11,21 +11,10 @@
 // (< 2^31) compare smaller, so the same atomicMin leaves ids from earlier fills
 // untouched.  Fill remembers each item's bucket position so that remapping the
 // edge list afterwards is a direct 4-byte read instead of a second probe.
-#include "common.cuh"
+#include "hashtable.cuh"
 
 namespace fgnn {
 namespace {
-
-struct __align__(8) Bucket {
-  uint32_t key;
-  uint32_t local;
-};
-
-constexpr uint32_t kPending = 0x80000000u;
-
-__device__ __forceinline__ uint32_t hash_id(uint32_t id, uint32_t mask) {
-  return ((id * 0x9E3779B1u) >> 7) & mask;
-}
 
 // returns bucket position holding `id` (inserting it if absent)
 __device__ __forceinline__ uint32_t insert_key(Bucket *table, uint32_t mask, uint32_t id) {
@@ -61,25 +50,6 @@ __global__ void ht_bump_kernel(uint32_t *d_num_items, uint32_t n_max, const uint
   *d_num_items += load_count(n_max, d_n);
 }
 
-__device__ __forceinline__ uint2 load_bucket(const Bucket *b) {
-  return *reinterpret_cast<const uint2 *>(b);
-}
-
-// finish the probe sequence of `id` starting from a first-probe snapshot `b` of
-// bucket `pos`; returns the bucket position, *local_seen = last observed local
-__device__ __forceinline__ uint32_t resolve_insert(Bucket *table, uint32_t mask, uint32_t id,
-                                                   uint32_t pos, uint2 b, uint32_t *local_seen) {
-  while (true) {
-    if (b.x == id) { *local_seen = b.y; return pos; }
-    if (b.x == kEmpty) {
-      const uint32_t old = atomicCAS(&table[pos].key, kEmpty, id);
-      if (old == kEmpty || old == id) { *local_seen = kEmpty; return pos; }
-    }
-    pos = (pos + 1) & mask;
-    b = load_bucket(table + pos);
-  }
-}
-
 constexpr int kInsIlp = 4;
 
 // ncu r1_a: 48 us for 0.85 M items with one dependent probe per thread and an
@@ -107,10 +77,7 @@ ht_insert_kernel(Bucket *table, uint32_t mask, const uint32_t *__restrict__ inpu
     for (int u = 0; u < kInsIlp; ++u) {
       const uint32_t i = i0 + u * stride;
       if (i < n) {
-        uint32_t seen;
-        const uint32_t bp = resolve_insert(table, mask, id[u], pos[u], b[u], &seen);
-        if (seen > (kPending | i)) atomicMin(&table[bp].local, kPending | i);
-        pos_out[i] = bp;
+        pos_out[i] = insert_item(table, mask, id[u], i, pos[u], b[u]);
       }
     }
   }
@@ -121,32 +88,56 @@ struct CompactSmem {
   ChainSmem chain;
 };
 
+// wait until the owner of bucket `bp` has received its local id (only lower
+// tickets or this CTA's earlier tiles can own it, see ht_compact_kernel)
+__device__ __forceinline__ uint32_t wait_local(const Bucket *table, uint32_t bp) {
+  uint32_t w = ld_relaxed_u32(&table[bp].local);
+  while (w & kPending) {
+    __nanosleep(32);
+    w = ld_relaxed_u32(&table[bp].local);
+  }
+  return w;
+}
+
+// Assign local ids to the ids that are new in this fill (first occurrence order)
+// and — when out_local != nullptr — remap EVERY item of the fill to its local id
+// in the same launch (the reference runs FillWithDuplicates, then GPUMapEdges as
+// a second probe pass, cuda_hashtable.cu:725-807 + cuda_mapping.cu:68-81).
+//
+// Remap without a grid-wide barrier: the owner of an id is its smallest input
+// index, so it always lives in this CTA's chunk at an earlier position or in a
+// chunk with a LOWER ticket.  Lower tickets never wait on higher ones (they only
+// look back), so spinning on the bucket's local word until the pending bit
+// clears cannot deadlock; the CTA assigns all of its own owners first and only
+// then waits, so it never delays the tickets that wait on it.
 __global__ void __launch_bounds__(kBlock)
 ht_compact_kernel(Bucket *table, const uint32_t *__restrict__ input, uint32_t n_max,
                   const uint32_t *__restrict__ d_n, const uint32_t *__restrict__ pos,
-                  uint32_t *__restrict__ n2o, uint32_t *d_num_items, ChainWs *ws) {
+                  uint32_t *__restrict__ n2o, uint32_t *d_num_items,
+                  uint32_t *__restrict__ out_local, uint32_t *count_copy, uint32_t *count_copy2,
+                  ChainWs *ws) {
   __shared__ CompactSmem sm;
   const uint32_t n = load_count(n_max, d_n);
   const uint32_t p = chain_ticket(ws, &sm.chain);
   uint32_t begin, end;
   chunk_range(n, p, gridDim.x, kBlock, &begin, &end);
-  const uint32_t items0 = *d_num_items;  // stable: only the last ticket updates it, at the end
+  const uint32_t items0 = *d_num_items;  // stable: only the last finisher updates it, at the end
 
-  // flags of the first kCache tiles of the chunk stay in registers so the
-  // random bucket read happens once (a chunk is <= 4 tiles up to ~1.2 M items)
+  // bucket + local word of the first kCache tiles of the chunk stay in registers so
+  // the random bucket read happens once (a chunk is <= 4 tiles up to ~1.2 M items)
   constexpr int kCache = 4;
-  uint32_t bpr[kCache], flr[kCache];
+  uint32_t bpr[kCache], wr[kCache];
   unsigned long long partial = 0;
 #pragma unroll
   for (int it = 0; it < kCache; ++it) {
     const uint32_t i = begin + it * kBlock + threadIdx.x;
     bpr[it] = 0;
-    flr[it] = 0;
+    wr[it] = 0;
     if (i < end) {
       bpr[it] = pos[i];
-      flr[it] = (table[bpr[it]].local == (kPending | i)) ? 1u : 0u;
+      wr[it] = table[bpr[it]].local;
+      partial += (wr[it] == (kPending | i)) ? 1u : 0u;
     }
-    partial += flr[it];
   }
   for (uint32_t i = begin + kCache * kBlock + threadIdx.x; i < end; i += kBlock)
     partial += (table[pos[i]].local == (kPending | i)) ? 1u : 0u;
@@ -158,44 +149,52 @@ ht_compact_kernel(Bucket *table, const uint32_t *__restrict__ input, uint32_t n_
     const uint32_t t0 = begin + it * kBlock;
     if (t0 < end) {  // uniform across the CTA
       const uint32_t i = t0 + threadIdx.x;
+      const uint32_t flag = (i < end && wr[it] == (kPending | i)) ? 1u : 0u;
       uint32_t tile_total;
-      const uint32_t excl = block_excl_scan(flr[it], sm.warp, &tile_total);
-      if (flr[it]) {
+      const uint32_t excl = block_excl_scan(flag, sm.warp, &tile_total);
+      if (flag) {
         const uint32_t local = items0 + (uint32_t)base + excl;
         table[bpr[it]].local = local;
         n2o[local] = __ldg(input + i);
+        wr[it] = local;
       }
       base += tile_total;
     }
   }
   for (uint32_t t0 = begin + kCache * kBlock; t0 < end; t0 += kBlock) {
     const uint32_t i = t0 + threadIdx.x;
-    uint32_t flag = 0, bp = 0;
+    uint32_t flag = 0, bp = 0, w = 0;
     if (i < end) {
       bp = pos[i];
-      flag = (table[bp].local == (kPending | i)) ? 1u : 0u;
+      w = table[bp].local;
+      flag = (w == (kPending | i)) ? 1u : 0u;
     }
     uint32_t tile_total;
     const uint32_t excl = block_excl_scan(flag, sm.warp, &tile_total);
     if (flag) {
-      const uint32_t local = items0 + (uint32_t)base + excl;
-      table[bp].local = local;
-      n2o[local] = __ldg(input + i);
+      w = items0 + (uint32_t)base + excl;
+      table[bp].local = w;
+      n2o[w] = __ldg(input + i);
     }
     base += tile_total;
+    if (out_local) {  // long chunks: remap tile by tile (owners of this tile are written above)
+      __syncthreads();
+      if (i < end) out_local[i] = (w & kPending) ? wait_local(table, bp) : w;
+    }
   }
-  // every ticket read items0 before any can get here?  No: tickets run
-  // concurrently, so the counter is only advanced by the CTA that finishes
-  // LAST (after all others have read it).
+  if (out_local) {
+    __syncthreads();  // this CTA's owners are all assigned and visible
+#pragma unroll
+    for (int it = 0; it < kCache; ++it) {
+      const uint32_t i = begin + it * kBlock + threadIdx.x;
+      if (i < end) out_local[i] = (wr[it] & kPending) ? wait_local(table, bpr[it]) : wr[it];
+    }
+  }
+  // the item counter is only advanced by the CTA that finishes LAST (every other CTA has read items0 by
+  // then); the number of new ids = base at the end of the last chunk travels through the pad word
   __syncthreads();
   if (threadIdx.x == 0) {
-    // total number of new ids = base at the end of the last chunk; publish it
-    // through the chain workspace's pad word so the last finisher can add it.
     if (p == gridDim.x - 1) ws->pad[0] = (uint32_t)base;
-  }
-  // chain_finish with the counter update folded in
-  __syncthreads();
-  if (threadIdx.x == 0) {
     __threadfence();
     const unsigned int prev = atomicAdd(&ws->done, 1u);
     sm.chain.last = (prev == gridDim.x - 1) ? 1u : 0u;
@@ -205,11 +204,32 @@ ht_compact_kernel(Bucket *table, const uint32_t *__restrict__ input, uint32_t n_
     for (uint32_t t = threadIdx.x; t < gridDim.x; t += kBlock) ws->agg[t] = 0ull;
     if (threadIdx.x == 0) {
       __threadfence();
-      *d_num_items = items0 + *((volatile unsigned int *)&ws->pad[0]);
+      const uint32_t total = items0 + *((volatile unsigned int *)&ws->pad[0]);
+      *d_num_items = total;
+      if (count_copy) *count_copy = total;
+      if (count_copy2) *count_copy2 = total;
       ws->pad[0] = 0u;
       ws->ticket = 0u;
       ws->done = 0u;
     }
+  }
+}
+
+// FillWithUnique into an empty table (first fill of a batch): local id = index, count = n
+__global__ void __launch_bounds__(kBlock)
+ht_fill_unique_first_kernel(Bucket *table, uint32_t mask, const uint32_t *__restrict__ input,
+                            uint32_t n_max, const uint32_t *__restrict__ d_n, uint32_t *n2o,
+                            uint32_t *d_num_items, uint32_t *count_copy) {
+  const uint32_t n = load_count(n_max, d_n);
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    *d_num_items = n;
+    if (count_copy) *count_copy = n;
+  }
+  for (uint32_t i = blockIdx.x * kBlock + threadIdx.x; i < n; i += gridDim.x * kBlock) {
+    const uint32_t id = __ldg(input + i);
+    const uint32_t pos = insert_key(table, mask, id);
+    table[pos].local = i;
+    n2o[i] = id;
   }
 }
 
@@ -238,6 +258,39 @@ ht_map_kernel(const Bucket *__restrict__ table, uint32_t mask, const uint32_t *_
 }
 
 }  // namespace
+
+int ht_insert_launch(void *table, size_t capacity, const uint32_t *input, uint32_t n_max,
+                     const uint32_t *d_n, uint32_t *pos, cudaStream_t st) {
+  static const int occ1 = occupancy(ht_insert_kernel, kBlock, 0);
+  const int grid1 = persistent_grid(n_max, kBlock * kInsIlp, occ1, false);
+  ht_insert_kernel<<<grid1, kBlock, 0, st>>>((Bucket *)table, (uint32_t)(capacity - 1), input, n_max, d_n, pos);
+  note_launch();
+  return check_last();
+}
+
+int ht_compact_launch(void *table, size_t capacity, const uint32_t *input, uint32_t n_max,
+                      const uint32_t *d_n, const uint32_t *pos, uint32_t *n2o, uint32_t *d_num_items,
+                      uint32_t *out_local, uint32_t *count_copy, uint32_t *count_copy2, void *chain_ws,
+                      cudaStream_t st) {
+  (void)capacity;
+  static const int occ2 = occupancy(ht_compact_kernel, kBlock, 0);
+  const int grid2 = persistent_grid(n_max, kBlock, occ2, true);
+  ht_compact_kernel<<<grid2, kBlock, 0, st>>>((Bucket *)table, input, n_max, d_n, pos, n2o, d_num_items,
+                                             out_local, count_copy, count_copy2, (ChainWs *)chain_ws);
+  note_launch();
+  return check_last();
+}
+
+int ht_fill_unique_first_launch(void *table, size_t capacity, const uint32_t *input, uint32_t n_max,
+                                const uint32_t *d_n, uint32_t *n2o, uint32_t *d_num_items,
+                                uint32_t *count_copy, cudaStream_t st) {
+  const int grid = persistent_grid(n_max ? n_max : 1, kBlock, 8, false);
+  ht_fill_unique_first_kernel<<<grid, kBlock, 0, st>>>((Bucket *)table, (uint32_t)(capacity - 1), input,
+                                                      n_max, d_n, n2o, d_num_items, count_copy);
+  note_launch();
+  return check_last();
+}
+
 }  // namespace fgnn
 
 using namespace fgnn;
@@ -276,26 +329,37 @@ extern "C" int fgnn_k_ht_fill_unique(void *table, size_t capacity, const uint32_
   return check_last();
 }
 
+static int check_fill_args(void *table, size_t capacity, const uint32_t *input, uint32_t n_max,
+                           uint32_t *pos, uint32_t *n2o, uint32_t *d_num_items, void *chain_ws) {
+  if (!table || !n2o || !d_num_items || !chain_ws || (capacity & (capacity - 1))) return FGNN_ERR_BAD_ARG;
+  if (capacity > 0x80000000ull || n_max >= kPending) return FGNN_ERR_UNSUPPORTED;
+  if (n_max > 0 && (!input || !pos)) return FGNN_ERR_BAD_ARG;
+  return 0;
+}
+
 extern "C" int fgnn_k_ht_fill_duplicates(void *table, size_t capacity, const uint32_t *input,
                                          uint32_t n_max, const uint32_t *d_n, uint32_t *pos,
                                          uint32_t *n2o, uint32_t *d_num_items, void *chain_ws,
                                          fgnn_stream_t stream) {
-  if (!table || !n2o || !d_num_items || !chain_ws || (capacity & (capacity - 1)))
-    return FGNN_ERR_BAD_ARG;
-  if (capacity > 0x80000000ull || n_max >= kPending) return FGNN_ERR_UNSUPPORTED;
+  if (int rc = check_fill_args(table, capacity, input, n_max, pos, n2o, d_num_items, chain_ws)) return rc;
   if (n_max == 0) return 0;
-  if (!input || !pos) return FGNN_ERR_BAD_ARG;
   cudaStream_t st = (cudaStream_t)stream;
-  static const int occ1 = occupancy(ht_insert_kernel, kBlock, 0);
-  static const int occ2 = occupancy(ht_compact_kernel, kBlock, 0);
-  const int grid1 = persistent_grid(n_max, kBlock * kInsIlp, occ1, false);
-  ht_insert_kernel<<<grid1, kBlock, 0, st>>>((Bucket *)table, (uint32_t)(capacity - 1), input, n_max,
-                                            d_n, pos);
-  const int grid2 = persistent_grid(n_max, kBlock, occ2, true);
-  ht_compact_kernel<<<grid2, kBlock, 0, st>>>((Bucket *)table, input, n_max, d_n, pos, n2o,
-                                             d_num_items, (ChainWs *)chain_ws);
-  note_launch(2);
-  return check_last();
+  if (int rc = ht_insert_launch(table, capacity, input, n_max, d_n, pos, st)) return rc;
+  return ht_compact_launch(table, capacity, input, n_max, d_n, pos, n2o, d_num_items, nullptr, nullptr,
+                           nullptr, chain_ws, st);
+}
+
+extern "C" int fgnn_k_ht_fill_duplicates_map(void *table, size_t capacity, const uint32_t *input,
+                                             uint32_t n_max, const uint32_t *d_n, uint32_t *pos,
+                                             uint32_t *n2o, uint32_t *d_num_items, uint32_t *out_local,
+                                             void *chain_ws, fgnn_stream_t stream) {
+  if (int rc = check_fill_args(table, capacity, input, n_max, pos, n2o, d_num_items, chain_ws)) return rc;
+  if (n_max == 0) return 0;
+  if (!out_local) return FGNN_ERR_BAD_ARG;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (int rc = ht_insert_launch(table, capacity, input, n_max, d_n, pos, st)) return rc;
+  return ht_compact_launch(table, capacity, input, n_max, d_n, pos, n2o, d_num_items, out_local, nullptr,
+                           nullptr, chain_ws, st);
 }
 
 extern "C" int fgnn_k_ht_map(const void *table, size_t capacity, const uint32_t *global,

@@ -1,0 +1,79 @@
+// OrderedHashTable device primitives shared by hashtable.cu (stand-alone fill /
+// map kernels) and the samplers that insert their picks while they gather them.
+// Layout and ownership rule: see hashtable.cu.
+#pragma once
+#include "common.cuh"
+
+namespace fgnn {
+
+struct __align__(8) Bucket {
+  uint32_t key;
+  uint32_t local;
+};
+
+constexpr uint32_t kPending = 0x80000000u;
+
+__device__ __forceinline__ uint32_t hash_id(uint32_t id, uint32_t mask) {
+  return ((id * 0x9E3779B1u) >> 7) & mask;
+}
+
+__device__ __forceinline__ uint2 load_bucket(const Bucket *b) {
+  return *reinterpret_cast<const uint2 *>(b);
+}
+
+// finish the probe sequence of `id` starting from a first-probe snapshot `b` of
+// bucket `pos`; returns the bucket position, *local_seen = last observed local
+__device__ __forceinline__ uint32_t resolve_insert(Bucket *table, uint32_t mask, uint32_t id,
+                                                   uint32_t pos, uint2 b, uint32_t *local_seen) {
+  while (true) {
+    if (b.x == id) { *local_seen = b.y; return pos; }
+    if (b.x == kEmpty) {
+      const uint32_t old = atomicCAS(&table[pos].key, kEmpty, id);
+      if (old == kEmpty || old == id) { *local_seen = kEmpty; return pos; }
+    }
+    pos = (pos + 1) & mask;
+    b = load_bucket(table + pos);
+  }
+}
+
+// insert item `index` (its position in the fill's input order) holding `id`;
+// returns its bucket.  The smallest index of a new id becomes its owner.
+__device__ __forceinline__ uint32_t insert_item(Bucket *table, uint32_t mask, uint32_t id,
+                                                uint32_t index, uint32_t pos, uint2 first) {
+  uint32_t seen;
+  const uint32_t bp = resolve_insert(table, mask, id, pos, first, &seen);
+  if (seen > (kPending | index)) atomicMin(&table[bp].local, kPending | index);
+  return bp;
+}
+
+__device__ __forceinline__ uint32_t ld_relaxed_u32(const uint32_t *p) {
+  uint32_t v;
+  asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+
+// optional "insert while sampling" target handed to the sampler kernels
+struct HtInsert {
+  Bucket *table;      // nullptr: do not insert
+  uint32_t mask;
+  uint32_t *pos_out;  // bucket of every emitted item, in output order
+};
+
+// internal launchers used by batch.cu (fgnn_k_sample_batch)
+int sample_khop_launch(int variant, const uint32_t *indptr, const uint32_t *indices,
+                       const uint32_t *input, uint32_t n_max, const uint32_t *d_n, uint32_t fanout,
+                       fgnn_rng rng, uint32_t *out_src, uint32_t *out_dst, uint32_t *out_src_local,
+                       uint32_t *d_num_out, void *chain_ws, HtInsert ht, cudaStream_t stream);
+// compact (+ optional remap of the items to local ids, + optional copies of the new item count)
+int ht_compact_launch(void *table, size_t capacity, const uint32_t *input, uint32_t n_max,
+                      const uint32_t *d_n, const uint32_t *pos, uint32_t *n2o, uint32_t *d_num_items,
+                      uint32_t *out_local, uint32_t *count_copy, uint32_t *count_copy2, void *chain_ws,
+                      cudaStream_t stream);
+int ht_insert_launch(void *table, size_t capacity, const uint32_t *input, uint32_t n_max,
+                     const uint32_t *d_n, uint32_t *pos, cudaStream_t stream);
+// FillWithUnique into an EMPTY table: base is 0 by construction, so the count needs no second kernel
+int ht_fill_unique_first_launch(void *table, size_t capacity, const uint32_t *input, uint32_t n_max,
+                                const uint32_t *d_n, uint32_t *n2o, uint32_t *d_num_items,
+                                uint32_t *count_copy, cudaStream_t stream);
+
+}  // namespace fgnn

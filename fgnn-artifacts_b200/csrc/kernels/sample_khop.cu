@@ -20,7 +20,7 @@
 // the CSR in HBM is read-only.  variant 0 (reservoir / Algorithm R) evaluates
 // the len-f replacement draws in parallel and resolves "last writer wins" with
 // a shared-memory atomicMax.
-#include "common.cuh"
+#include "hashtable.cuh"
 
 namespace fgnn {
 namespace {
@@ -111,7 +111,7 @@ sample_khop_kernel(const uint32_t *__restrict__ indptr, const uint32_t *__restri
                    const uint32_t *__restrict__ d_n, uint32_t fanout, RngKey key,
                    uint32_t *__restrict__ out_src, uint32_t *__restrict__ out_dst,
                    uint32_t *__restrict__ out_src_local, uint32_t *__restrict__ d_num_out,
-                   ChainWs *ws) {
+                   ChainWs *ws, HtInsert ht) {
   extern __shared__ uint32_t s_choice[];  // [kTile][fanout]
   __shared__ TileSmem sm;
 
@@ -194,6 +194,10 @@ sample_khop_kernel(const uint32_t *__restrict__ indptr, const uint32_t *__restri
       out_dst[o] = nbr;
       if (out_src) out_src[o] = sm.rid[s];
       if (out_src_local) out_src_local[o] = t0 + s;
+      if (ht.table) {
+        const uint32_t hp = hash_id(nbr, ht.mask);
+        ht.pos_out[o] = insert_item(ht.table, ht.mask, nbr, (uint32_t)o, hp, load_bucket(ht.table + hp));
+      }
     }
     base += tile_total;
     __syncthreads();
@@ -231,7 +235,7 @@ sample_khop2_kernel(const uint32_t *__restrict__ indptr, const uint32_t *__restr
                     const uint32_t *__restrict__ d_n, uint32_t fanout, RngKey key,
                     uint32_t *__restrict__ out_src, uint32_t *__restrict__ out_dst,
                     uint32_t *__restrict__ out_src_local, uint32_t *__restrict__ d_num_out,
-                    ChainWs *ws) {
+                    ChainWs *ws, HtInsert ht) {
   extern __shared__ uint32_t dyn[];
   __shared__ Tile2Smem<NT> sm;
   const uint32_t fs = fanout | 1u;            // odd row stride: conflict-free [seed][j]
@@ -313,6 +317,17 @@ sample_khop2_kernel(const uint32_t *__restrict__ indptr, const uint32_t *__restr
           ss[u] = lo;
         }
       }
+      // the picked ids go straight into the batch's OrderedHashTable (owner = smallest output index):
+      // first probes of the four ids are issued together, behind the gathers that produced them
+      uint2 hb[4];
+      uint32_t hp[4];
+      if (ht.table) {
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          hp[u] = hash_id(nbr[u], ht.mask);
+          if (ss[u] != kEmpty) hb[u] = load_bucket(ht.table + hp[u]);
+        }
+      }
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
         if (ss[u] != kEmpty) {
@@ -320,6 +335,7 @@ sample_khop2_kernel(const uint32_t *__restrict__ indptr, const uint32_t *__restr
           out_dst[o] = nbr[u];
           if (out_src) out_src[o] = sm.rid[ss[u]];
           if (out_src_local) out_src_local[o] = t0 + ss[u];
+          if (ht.table) ht.pos_out[o] = insert_item(ht.table, ht.mask, nbr[u], (uint32_t)o, hp[u], hb[u]);
         }
       }
     }
@@ -332,7 +348,7 @@ sample_khop2_kernel(const uint32_t *__restrict__ indptr, const uint32_t *__restr
 template <int NT>
 int launch2(const uint32_t *indptr, const uint32_t *indices, const uint32_t *input, uint32_t n_max,
             const uint32_t *d_n, uint32_t fanout, RngKey key, uint32_t *out_src, uint32_t *out_dst,
-            uint32_t *out_src_local, uint32_t *d_num_out, void *chain_ws, cudaStream_t stream) {
+            uint32_t *out_src_local, uint32_t *d_num_out, void *chain_ws, HtInsert ht, cudaStream_t stream) {
   const size_t smem = ((size_t)NT * (fanout | 1u) + 2 * (size_t)NT * fanout) * sizeof(uint32_t);
   auto kern = sample_khop2_kernel<NT>;
   if (smem > 48 * 1024) {
@@ -341,7 +357,7 @@ int launch2(const uint32_t *indptr, const uint32_t *indices, const uint32_t *inp
   }
   const int grid = persistent_grid(n_max, NT, occupancy(kern, NT, smem), true);
   kern<<<grid, NT, smem, stream>>>(indptr, indices, input, n_max, d_n, fanout, key, out_src, out_dst,
-                                   out_src_local, d_num_out, (ChainWs *)chain_ws);
+                                   out_src_local, d_num_out, (ChainWs *)chain_ws, ht);
   note_launch();
   return check_last();
 }
@@ -350,7 +366,7 @@ template <int VARIANT, int NS>
 int launch(const uint32_t *indptr, const uint32_t *indices, const uint32_t *input,
            uint32_t n_max, const uint32_t *d_n, uint32_t fanout, RngKey key,
            uint32_t *out_src, uint32_t *out_dst, uint32_t *out_src_local,
-           uint32_t *d_num_out, void *chain_ws, cudaStream_t stream) {
+           uint32_t *d_num_out, void *chain_ws, HtInsert ht, cudaStream_t stream) {
   const size_t smem = (size_t)kTile * fanout * sizeof(uint32_t);
   auto kern = sample_khop_kernel<VARIANT, NS>;
   if (smem > 48 * 1024) {
@@ -362,38 +378,35 @@ int launch(const uint32_t *indptr, const uint32_t *indices, const uint32_t *inpu
   if (occ < 1) occ = 1;
   const int grid = persistent_grid(n_max, kTile, occ, true);
   kern<<<grid, kBlock, smem, stream>>>(indptr, indices, input, n_max, d_n, fanout, key, out_src,
-                                       out_dst, out_src_local, d_num_out, (ChainWs *)chain_ws);
+                                       out_dst, out_src_local, d_num_out, (ChainWs *)chain_ws, ht);
   note_launch();
   return check_last();
 }
 
 }  // namespace
-}  // namespace fgnn
 
-extern "C" int fgnn_k_sample_khop(int variant, const uint32_t *indptr, const uint32_t *indices,
-                                  const uint32_t *input, uint32_t n_max, const uint32_t *d_n,
-                                  uint32_t fanout, fgnn_rng rng, uint32_t *out_src,
-                                  uint32_t *out_dst, uint32_t *out_src_local,
-                                  uint32_t *d_num_out, void *chain_ws, fgnn_stream_t stream) {
-  using namespace fgnn;
+int sample_khop_launch(int variant, const uint32_t *indptr, const uint32_t *indices,
+                       const uint32_t *input, uint32_t n_max, const uint32_t *d_n, uint32_t fanout,
+                       fgnn_rng rng, uint32_t *out_src, uint32_t *out_dst, uint32_t *out_src_local,
+                       uint32_t *d_num_out, void *chain_ws, HtInsert ht, cudaStream_t st) {
   if (!indptr || !indices || !out_dst || !d_num_out || !chain_ws) return FGNN_ERR_BAD_ARG;
   if (n_max > 0 && !input) return FGNN_ERR_BAD_ARG;
   if (fanout == 0 || fanout > 128) return FGNN_ERR_UNSUPPORTED;
-  if ((uint64_t)n_max * fanout > 0xFFFFFFFFull) return FGNN_ERR_UNSUPPORTED;
+  if ((uint64_t)n_max * fanout > 0x7FFFFFFFull) return FGNN_ERR_UNSUPPORTED;
+  if (ht.table && !ht.pos_out) return FGNN_ERR_BAD_ARG;
   const RngKey key = make_rng_key(rng);
-  cudaStream_t st = (cudaStream_t)stream;
 #define FGNN_GO(V, NS)                                                                      \
   return launch<V, NS>(indptr, indices, input, n_max, d_n, fanout, key, out_src, out_dst,   \
-                       out_src_local, d_num_out, chain_ws, st)
+                       out_src_local, d_num_out, chain_ws, ht, st)
   if (variant == 2) {
     // thread-per-seed Fisher-Yates; 64-seed tiles when the layer is small or the
     // per-thread log would not fit next to a 128-seed tile
     const bool small = (uint64_t)n_max <= (uint64_t)sm_count() * 128ull || fanout > 48;
     if (small)
       return launch2<64>(indptr, indices, input, n_max, d_n, fanout, key, out_src, out_dst,
-                         out_src_local, d_num_out, chain_ws, st);
+                         out_src_local, d_num_out, chain_ws, ht, st);
     return launch2<128>(indptr, indices, input, n_max, d_n, fanout, key, out_src, out_dst,
-                        out_src_local, d_num_out, chain_ws, st);
+                        out_src_local, d_num_out, chain_ws, ht, st);
   } else if (variant == 22) {  // warp-cooperative Fisher-Yates (kept for A/B profiling)
     if (fanout <= 32) FGNN_GO(2, 1);
     if (fanout <= 64) FGNN_GO(2, 2);
@@ -403,4 +416,17 @@ extern "C" int fgnn_k_sample_khop(int variant, const uint32_t *indptr, const uin
   }
 #undef FGNN_GO
   return FGNN_ERR_BAD_ARG;
+}
+
+}  // namespace fgnn
+
+extern "C" int fgnn_k_sample_khop(int variant, const uint32_t *indptr, const uint32_t *indices,
+                                  const uint32_t *input, uint32_t n_max, const uint32_t *d_n,
+                                  uint32_t fanout, fgnn_rng rng, uint32_t *out_src,
+                                  uint32_t *out_dst, uint32_t *out_src_local,
+                                  uint32_t *d_num_out, void *chain_ws, fgnn_stream_t stream) {
+  fgnn::HtInsert none{nullptr, 0, nullptr};
+  return fgnn::sample_khop_launch(variant, indptr, indices, input, n_max, d_n, fanout, rng, out_src,
+                                  out_dst, out_src_local, d_num_out, chain_ws, none,
+                                  (cudaStream_t)stream);
 }

@@ -381,55 +381,45 @@ void Sampler::Enqueue(const TaskPtr &task) {
   const IdType *indptr = d_indptr(), *indices = d_indices();
 
   if (sl.begin) CUDA_CALL(cudaEventRecord(sl.begin, stream));
-  FGNN_CALL(fgnn_k_ht_reset(sl.table->data, ht_cap_, num_items, st));                     // cuda_loops.cc:63
-  FGNN_CALL(fgnn_k_ht_fill_unique(sl.table->data, ht_cap_, (const IdType *)task->output_nodes->data, n_seed, nullptr,
-                                  n2o, num_items, st));                                   // :67-69
-  for (int i = (int)L_ - 1; i >= 0; --i) {                                               // :87
-    uint32_t *n_in = counts + 3 * i, *n_edge = counts + 3 * i + 1, *n_src = counts + 3 * i + 2;
-    CUDA_CALL(cudaMemcpyAsync(n_in, num_items, 4, cudaMemcpyDeviceToDevice, stream));
-    fgnn_rng rng{rc_.seed, task->key, (uint32_t)i};
-    IdType *dst = (IdType *)sl.dst[i]->data, *col = blk->col[i], *row = blk->row[i];
-    const uint32_t nmax = (uint32_t)in_max_[i], f = (uint32_t)fanout_[i];
-    switch (rc_.sample_type) {                                                           // :118-161
-      case kKHop0:
-        FGNN_CALL(fgnn_k_sample_khop(0, indptr, indices, n2o, nmax, n_in, f, rng, nullptr, dst, col, n_edge,
-                                     sl.chain->data, st));
-        break;
-      case kKHop2:
-        FGNN_CALL(fgnn_k_sample_khop(2, indptr, indices, n2o, nmax, n_in, f, rng, nullptr, dst, col, n_edge,
-                                     sl.chain->data, st));
-        break;
-      case kKHop1:
-      case kWeightedKHop:
-      case kWeightedKHopPrefix:
-        FGNN_CALL(fgnn_k_sample_replace((int)rc_.sample_type, indptr, indices,
-                                        prob_ ? (const float *)prob_->data : nullptr,
-                                        alias_ ? (const IdType *)alias_->data : nullptr,
-                                        prefix_ ? (const float *)prefix_->data : nullptr, n2o, nmax, n_in, f, rng,
-                                        nullptr, dst, col, n_edge, sl.ws->data, sl.ws->nbytes, sl.chain->data, st));
-        break;
-      case kWeightedKHopHashDedup:
-        FGNN_CALL(fgnn_k_sample_weighted_hash_dedup(indptr, indices, (const float *)prob_->data,
-                                                    (const IdType *)alias_->data, n2o, nmax, n_in, f, rng, nullptr,
-                                                    dst, col, n_edge, sl.chain->data, st));
-        break;
-      case kRandomWalk:
-        FCHECK_EQ(f, rc_.num_neighbor);
-        FGNN_CALL(fgnn_k_sample_random_walk(indptr, indices, n2o, nmax, n_in, (uint32_t)rc_.random_walk_length,
-                                            rc_.random_walk_restart_prob, (uint32_t)rc_.num_random_walk, f, rng,
-                                            nullptr, dst, col, blk->data[i], n_edge, nullptr, nullptr,
-                                            sl.ws->data, sl.ws->nbytes, sl.chain->data, st));
-        break;
-      default:
-        FCHECK(false) << "unknown sample type";
-    }
-    // populate the hash table with the sampled neighbours, then remap (:176-205)
-    FGNN_CALL(fgnn_k_ht_fill_duplicates(sl.table->data, ht_cap_, dst, (uint32_t)edge_max_[i], n_edge,
-                                        (uint32_t *)sl.pos[i]->data, n2o, num_items, sl.chain->data, st));
-    FGNN_CALL(fgnn_k_ht_map(sl.table->data, ht_cap_, nullptr, (const uint32_t *)sl.pos[i]->data,
-                            (uint32_t)edge_max_[i], n_edge, row, st));
-    CUDA_CALL(cudaMemcpyAsync(n_src, num_items, 4, cudaMemcpyDeviceToDevice, stream));
+  // the whole of DoGPUSample (cuda_loops.cc:50-267) is one call into the kernel layer: reset + seeds, then per
+  // layer sample(+insert) -> compact(+remap); nothing below waits on the host
+  fgnn_sample_plan pl;
+  memset(&pl, 0, sizeof(pl));
+  pl.sample_type = (int32_t)rc_.sample_type;
+  pl.num_layers = (uint32_t)L_;
+  for (size_t i = 0; i < L_; ++i) {
+    pl.fanout[i] = (uint32_t)fanout_[i];
+    pl.in_max[i] = (uint32_t)in_max_[i];
+    pl.dst[i] = (uint32_t *)sl.dst[i]->data;
+    pl.pos[i] = (uint32_t *)sl.pos[i]->data;
   }
+  pl.indptr = indptr;
+  pl.indices = indices;
+  pl.prob_table = prob_ ? (const float *)prob_->data : nullptr;
+  pl.alias_table = alias_ ? (const IdType *)alias_->data : nullptr;
+  pl.prob_prefix_table = prefix_ ? (const float *)prefix_->data : nullptr;
+  pl.walk_len = (uint32_t)rc_.random_walk_length;
+  pl.num_walk = (uint32_t)rc_.num_random_walk;
+  pl.restart_prob = rc_.random_walk_restart_prob;
+  pl.seed = rc_.seed;
+  pl.table = sl.table->data;
+  pl.capacity = ht_cap_;
+  pl.num_items = num_items;
+  pl.chain_ws = sl.chain->data;
+  pl.workspace = sl.ws->data;
+  pl.workspace_bytes = sl.ws->nbytes;
+  fgnn_sample_out so;
+  memset(&so, 0, sizeof(so));
+  so.n2o = n2o;
+  so.counts = counts;
+  for (size_t i = 0; i < L_; ++i) {
+    so.row[i] = blk->row[i];
+    so.col[i] = blk->col[i];
+    so.data[i] = blk->data[i];
+  }
+  if (rc_.sample_type == kRandomWalk)
+    for (size_t i = 0; i < L_; ++i) FCHECK_EQ(fanout_[i], rc_.num_neighbor);
+  FGNN_CALL(fgnn_k_sample_batch(&pl, &so, (const IdType *)task->output_nodes->data, n_seed, nullptr, task->key, st));
   // all counts of the batch go to the host at once
   CUDA_CALL(cudaMemcpyAsync(sl.counts_host->data, counts, L_ * 3 * 4, cudaMemcpyDeviceToHost, stream));
   CUDA_CALL(cudaEventRecord(sl.done, stream));

@@ -22,6 +22,27 @@ class FgnnRng(C.Structure):
     _fields_ = [("seed", C.c_uint64), ("batch_key", C.c_uint64), ("tag", C.c_uint32)]
 
 
+MAX_LAYERS = 8
+_P8 = C.c_void_p * MAX_LAYERS
+_U8 = C.c_uint32 * MAX_LAYERS
+
+
+class SamplePlan(C.Structure):
+    """fgnn_sample_plan (include/fgnn_kernels.h)"""
+    _fields_ = [("sample_type", C.c_int32), ("num_layers", C.c_uint32), ("fanout", _U8), ("in_max", _U8),
+                ("indptr", C.c_void_p), ("indices", C.c_void_p), ("prob_table", C.c_void_p),
+                ("alias_table", C.c_void_p), ("prob_prefix_table", C.c_void_p), ("walk_len", C.c_uint32),
+                ("num_walk", C.c_uint32), ("restart_prob", C.c_double), ("seed", C.c_uint64),
+                ("table", C.c_void_p), ("capacity", C.c_size_t), ("num_items", C.c_void_p),
+                ("chain_ws", C.c_void_p), ("workspace", C.c_void_p), ("workspace_bytes", C.c_size_t),
+                ("dst", _P8), ("pos", _P8)]
+
+
+class SampleOut(C.Structure):
+    """fgnn_sample_out (include/fgnn_kernels.h)"""
+    _fields_ = [("n2o", C.c_void_p), ("row", _P8), ("col", _P8), ("data", _P8), ("counts", C.c_void_p)]
+
+
 class KernelError(RuntimeError):
     pass
 
@@ -43,6 +64,8 @@ _SIGS = {
     "fgnn_k_ht_fill_unique": [_vp, _sz, _vp, _u32, _vp, _vp, _vp, _vp],
     "fgnn_k_ht_fill_duplicates": [_vp, _sz, _vp, _u32, _vp, _vp, _vp, _vp, _vp, _vp],
     "fgnn_k_ht_map": [_vp, _sz, _vp, _vp, _u32, _vp, _vp, _vp],
+    "fgnn_k_ht_fill_duplicates_map": [_vp, _sz, _vp, _u32, _vp, _vp, _vp, _vp, _vp, _vp, _vp],
+    "fgnn_k_sample_batch": [C.POINTER(SamplePlan), C.POINTER(SampleOut), _vp, _u32, _vp, _u64, _vp],
     "fgnn_k_cache_table_build": [_vp, _sz, _vp, _sz, _vp],
     "fgnn_k_cache_split": [_vp, _vp, _u32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp],
     "fgnn_k_row_copy": [_vp, _vp, _vp, _vp, _u64, _u32, _vp, _sz, _vp],
@@ -193,6 +216,18 @@ def ht_fill_duplicates(table, capacity, inp, n_max, d_n, pos, n2o, d_num_items, 
     _check(load().fgnn_k_ht_fill_duplicates(_ptr(table), capacity, _ptr(inp), n_max, _ptr(d_n), _ptr(pos),
                                             _ptr(n2o), _ptr(d_num_items), _ptr(chain_ws), _stream()),
            "ht_fill_duplicates")
+
+
+def ht_fill_duplicates_map(table, capacity, inp, n_max, d_n, pos, n2o, d_num_items, out_local, chain_ws):
+    _check(load().fgnn_k_ht_fill_duplicates_map(_ptr(table), capacity, _ptr(inp), n_max, _ptr(d_n), _ptr(pos),
+                                                _ptr(n2o), _ptr(d_num_items), _ptr(out_local), _ptr(chain_ws),
+                                                _stream()), "ht_fill_duplicates_map")
+
+
+def sample_batch(plan, out, seeds, n_seeds_max, d_n_seeds, batch_key):
+    """DoGPUSample for one mini-batch (fgnn_k_sample_batch) on the current torch stream."""
+    _check(load().fgnn_k_sample_batch(C.byref(plan), C.byref(out), _ptr(seeds), n_seeds_max, _ptr(d_n_seeds),
+                                      batch_key & 0xFFFFFFFFFFFFFFFF, _stream()), "sample_batch")
 
 
 def ht_map(table, capacity, glob, pos, n_max, d_n, out_local):

@@ -6,9 +6,14 @@ enqueues the whole batch without a host round trip: every count stays in HBM
 from PredictNumNodes (common.cc:330-339).
 
 Used by bench.py (kernel-resident leg) and the GPU tests.  The production host
-runtime is the C++ engine in csrc/runtime (samgraph_* C-ABI); this class is the
-same sequence of kernel calls driven from Python.
+runtime is the C++ engine in csrc/runtime (samgraph_* C-ABI); this class issues
+the same two calls per batch (fgnn_k_sample_batch, fgnn_k_gather_cached) from
+Python.  Like the engine's sampler it owns `num_slots` independent sets of
+scratch + output buffers, so several batches can be in flight on different
+streams.
 """
+import ctypes as C
+
 import torch
 
 from . import kernels as K
@@ -25,9 +30,61 @@ def predict_num_nodes(batch, fanouts, upto=None):
     return count
 
 
+class Slot:
+    """Scratch + outputs of one batch in flight (SampleSlot + TaskBlock of csrc/runtime/rt_engine.cc)."""
+
+    def __init__(self, hp):
+        i32 = dict(dtype=torch.int32, device=hp.dev)
+        L = hp.L
+        self.table = torch.empty(K.ht_bytes(hp.cap) // 4, **i32)
+        self.n2o = torch.empty(hp.max_nodes + 1, **i32)       # == input_nodes after the last layer
+        self.num_items = torch.zeros(1, **i32)
+        self.chain = K.new_chain_ws(hp.dev)
+        self.dst = [torch.empty(max(1, m), **i32) for m in hp.edge_max]
+        self.col = [torch.empty(max(1, m), **i32) for m in hp.edge_max]
+        self.row = [torch.empty(max(1, m), **i32) for m in hp.edge_max]
+        self.pos = [torch.empty(max(1, m), **i32) for m in hp.edge_max]
+        self.data = [torch.empty(max(1, m), **i32) for m in hp.edge_max] if hp.sample_type == "random_walk" else None
+        # counts[l] = (num_dst, num_edge, num_src) of layer l
+        self.counts = torch.zeros((L, 3), **i32)
+        self.ws = None
+        if hp.sample_type in ("khop1", "weighted_khop", "weighted_khop_prefix"):
+            nb = max(K.sample_replace_workspace_bytes(hp.in_max[i], hp.fanouts[i]) for i in range(L))
+            self.ws = torch.empty(nb, dtype=torch.uint8, device=hp.dev)
+        elif hp.sample_type == "random_walk":
+            nb = max(K.sample_random_walk_workspace_bytes(hp.in_max[i], hp.fanouts[i]) for i in range(L))
+            self.ws = torch.empty(nb, dtype=torch.uint8, device=hp.dev)
+        pl = K.SamplePlan()
+        pl.sample_type = SAMPLE_TYPES[hp.sample_type]
+        pl.num_layers = L
+        for i in range(L):
+            pl.fanout[i] = hp.fanouts[i]
+            pl.in_max[i] = hp.in_max[i]
+            pl.dst[i] = self.dst[i].data_ptr()
+            pl.pos[i] = self.pos[i].data_ptr()
+        pl.indptr, pl.indices = hp.indptr.data_ptr(), hp.indices.data_ptr()
+        pl.prob_table = hp.prob.data_ptr() if hp.prob is not None else None
+        pl.alias_table = hp.alias.data_ptr() if hp.alias is not None else None
+        pl.prob_prefix_table = hp.prefix.data_ptr() if hp.prefix is not None else None
+        pl.walk_len = hp.rw.get("random_walk_length", 0)
+        pl.num_walk = hp.rw.get("num_random_walk", 0)
+        pl.restart_prob = hp.rw.get("random_walk_restart_prob", 0.0)
+        pl.seed = hp.seed & 0xFFFFFFFFFFFFFFFF
+        pl.table, pl.capacity = self.table.data_ptr(), hp.cap
+        pl.num_items, pl.chain_ws = self.num_items.data_ptr(), self.chain.data_ptr()
+        pl.workspace = self.ws.data_ptr() if self.ws is not None else None
+        pl.workspace_bytes = self.ws.numel() if self.ws is not None else 0
+        out = K.SampleOut()
+        out.n2o, out.counts = self.n2o.data_ptr(), self.counts.data_ptr()
+        for i in range(L):
+            out.row[i], out.col[i] = self.row[i].data_ptr(), self.col[i].data_ptr()
+            out.data[i] = self.data[i].data_ptr() if self.data is not None else None
+        self.plan, self.out = pl, out
+
+
 class HotPath:
     def __init__(self, indptr, indices, num_nodes, fanouts, batch_size, sample_type="khop2", seed=0x5EED,
-                 prob_table=None, alias_table=None, prefix_table=None, rw=None, device="cuda"):
+                 prob_table=None, alias_table=None, prefix_table=None, rw=None, device="cuda", num_slots=1):
         K.load()
         self.dev = device
         self.indptr, self.indices = indptr, indices
@@ -39,7 +96,6 @@ class HotPath:
         self.seed = seed
         self.prob, self.alias, self.prefix = prob_table, alias_table, prefix_table
         self.rw = rw or {}
-        i32 = dict(dtype=torch.int32, device=device)
         # layer input bounds: S_l for l = L-1 .. 0 (cuda_loops.cc:87)
         self.in_max = [0] * self.L
         cur = batch_size
@@ -49,24 +105,8 @@ class HotPath:
         self.max_nodes = predict_num_nodes(batch_size, self.fanouts)
         self.edge_max = [self.in_max[i] * self.fanouts[i] for i in range(self.L)]
         self.cap = K.ht_capacity(self.max_nodes)
-        self.table = torch.empty(K.ht_bytes(self.cap) // 4, **i32)
-        self.n2o = torch.empty(self.max_nodes + 1, **i32)       # == input_nodes after the last layer
-        self.num_items = torch.zeros(1, **i32)
-        self.chain = K.new_chain_ws(device)
-        self.dst = [torch.empty(max(1, m), **i32) for m in self.edge_max]
-        self.col = [torch.empty(max(1, m), **i32) for m in self.edge_max]
-        self.row = [torch.empty(max(1, m), **i32) for m in self.edge_max]
-        self.pos = [torch.empty(max(1, m), **i32) for m in self.edge_max]
-        self.data = [torch.empty(max(1, m), **i32) for m in self.edge_max] if sample_type == "random_walk" else None
-        # counts[l] = (num_dst, num_edge, num_src) of layer l
-        self.counts = torch.zeros((self.L, 3), **i32)
-        self.ws = None
-        if sample_type in ("khop1", "weighted_khop", "weighted_khop_prefix"):
-            nb = max(K.sample_replace_workspace_bytes(self.in_max[i], self.fanouts[i]) for i in range(self.L))
-            self.ws = torch.empty(nb, dtype=torch.uint8, device=device)
-        elif sample_type == "random_walk":
-            nb = max(K.sample_random_walk_workspace_bytes(self.in_max[i], self.fanouts[i]) for i in range(self.L))
-            self.ws = torch.empty(nb, dtype=torch.uint8, device=device)
+        self.slots = [Slot(self) for _ in range(max(1, num_slots))]
+        self._alias_slot(0)
         # cache state (set by build_cache)
         self.cache_table = None
         self.shards = None
@@ -79,44 +119,24 @@ class HotPath:
         self.label_src = None
         self.label_out = None
         self.stats = torch.zeros(2, dtype=torch.int64, device=device)
-        self.split_counts = torch.zeros(2, **i32)
+        self.split_counts = torch.zeros(2, dtype=torch.int32, device=device)
+
+    def _alias_slot(self, s):
+        """Single-slot callers (tests, smoke) read the results as attributes of the HotPath itself."""
+        sl = self.slots[s]
+        self.table, self.n2o, self.num_items, self.chain = sl.table, sl.n2o, sl.num_items, sl.chain
+        self.dst, self.col, self.row, self.pos, self.data, self.counts = sl.dst, sl.col, sl.row, sl.pos, sl.data, sl.counts
 
     # ------------------------------------------------------------------
-    def sample(self, seeds, n_seeds, batch_key):
-        """DoGPUSample: seeds (device int32/u32) -> per-layer (row, col[, data]) + input_nodes."""
-        K.ht_reset(self.table, self.cap, self.num_items)
-        K.ht_fill_unique(self.table, self.cap, seeds, n_seeds, None, self.n2o, self.num_items)
-        st = SAMPLE_TYPES[self.sample_type]
-        for i in range(self.L - 1, -1, -1):
-            f = self.fanouts[i]
-            n_in = self.counts[i, 0:1]
-            n_edge = self.counts[i, 1:2]
-            n_in.copy_(self.num_items)                      # layer input = running unique list
-            r = K.rng(self.seed, batch_key, i)
-            if st in (0, 5):
-                K.sample_khop(0 if st == 0 else 2, self.indptr, self.indices, self.n2o, self.in_max[i], n_in, f, r,
-                              None, self.dst[i], self.col[i], n_edge, self.chain)
-            elif st in (1, 2, 4):
-                K.sample_replace(st, self.indptr, self.indices, self.prob, self.alias, self.prefix, self.n2o,
-                                 self.in_max[i], n_in, f, r, None, self.dst[i], self.col[i], n_edge, self.ws,
-                                 self.chain)
-            elif st == 6:
-                K.sample_weighted_hash_dedup(self.indptr, self.indices, self.prob, self.alias, self.n2o,
-                                             self.in_max[i], n_in, f, r, None, self.dst[i], self.col[i], n_edge,
-                                             self.chain)
-            else:
-                K.sample_random_walk(self.indptr, self.indices, self.n2o, self.in_max[i], n_in,
-                                     self.rw["random_walk_length"], self.rw["random_walk_restart_prob"],
-                                     self.rw["num_random_walk"], f, r, None, self.dst[i], self.col[i], self.data[i],
-                                     n_edge, None, None, self.ws, self.chain)
-            K.ht_fill_duplicates(self.table, self.cap, self.dst[i], self.edge_max[i], n_edge, self.pos[i], self.n2o,
-                                 self.num_items, self.chain)
-            K.ht_map(self.table, self.cap, None, self.pos[i], self.edge_max[i], n_edge, self.row[i])
-            self.counts[i, 2:3].copy_(self.num_items)
+    def sample(self, seeds, n_seeds, batch_key, slot=0):
+        """DoGPUSample: seeds (device int32/u32) -> per-layer (row, col[, data]) + input_nodes; one C call."""
+        sl = self.slots[slot]
+        K.sample_batch(sl.plan, sl.out, seeds, n_seeds, None, batch_key)
 
     # ------------------------------------------------------------------
-    def presample_count(self, freq):
-        K.freq_count(freq, self.n2o, self.max_nodes, self.num_items)
+    def presample_count(self, freq, slot=0):
+        sl = self.slots[slot]
+        K.freq_count(freq, sl.n2o, self.max_nodes, sl.num_items)
 
     def build_cache(self, ranking_nodes, cache_percentage, feat_src, row_bytes, feat_mask=0xFFFFFFFFFFFFFFFF,
                     num_shards=1, shard_id=0, peer_ptrs=None):
@@ -144,18 +164,27 @@ class HotPath:
         self.label_src = label_src
         self.label_out = torch.empty(self.batch_size, dtype=torch.int64, device=self.dev)
 
-    def extract(self, seeds=None, n_seeds=0):
-        """DoCacheFeatureCopy + DoCPULabelExtractAndCopy, fused gather."""
-        K.gather_cached(self.feat_out, self.n2o, self.max_nodes, self.num_items, self.cache_table, self.shard_ptrs,
+    def gather(self, slot=0):
+        """DoCacheFeatureCopy: the fused cache-aware feature gather of the slot's input_nodes."""
+        sl = self.slots[slot]
+        K.gather_cached(self.feat_out, sl.n2o, self.max_nodes, sl.num_items, self.cache_table, self.shard_ptrs,
                         self.num_shards, self.miss_src, self.row_bytes, self.stats, self.miss_mask)
+
+    def gather_labels(self, seeds, n_seeds):
+        """DoCPULabelExtractAndCopy, on the GPU (GPUExtract with D = 1, int64)."""
+        K.row_copy(self.label_out, None, self.label_src, seeds, n_seeds, None, 8)
+
+    def extract(self, seeds=None, n_seeds=0, slot=0):
+        self.gather(slot)
         if self.label_src is not None and seeds is not None:
-            K.row_copy(self.label_out, None, self.label_src, seeds, n_seeds, None, 8)
+            self.gather_labels(seeds, n_seeds)
 
-    def split(self, bufs):
+    def split(self, bufs, slot=0):
         """GetMissCacheIndex: explicit index lists (reference-compatible output)."""
-        K.cache_split(self.cache_table, self.n2o, self.max_nodes, self.num_items, bufs[0], bufs[1], bufs[2], bufs[3],
-                      self.split_counts, self.chain)
+        sl = self.slots[slot]
+        K.cache_split(self.cache_table, sl.n2o, self.max_nodes, sl.num_items, bufs[0], bufs[1], bufs[2], bufs[3],
+                      self.split_counts, sl.chain)
 
-    def step(self, seeds, n_seeds, batch_key):
-        self.sample(seeds, n_seeds, batch_key)
-        self.extract(seeds, n_seeds)
+    def step(self, seeds, n_seeds, batch_key, slot=0):
+        self.sample(seeds, n_seeds, batch_key, slot)
+        self.extract(seeds, n_seeds, slot)

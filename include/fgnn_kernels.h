@@ -161,6 +161,62 @@ int fgnn_k_ht_map(const void *table, size_t capacity, const uint32_t *global,
                   const uint32_t *pos, uint32_t n_max, const uint32_t *d_n,
                   uint32_t *out_local, fgnn_stream_t stream);
 
+/* FillWithDuplicates + GPUMapEdges in one pass (cuda_hashtable.cu:725-807 followed by
+ * cuda_mapping.cu:68-81): like fgnn_k_ht_fill_duplicates, and out_local[i] receives
+ * the local id of input[i] for every item of the fill. */
+int fgnn_k_ht_fill_duplicates_map(void *table, size_t capacity,
+                                  const uint32_t *input, uint32_t n_max,
+                                  const uint32_t *d_n, uint32_t *pos,
+                                  uint32_t *n2o, uint32_t *d_num_items,
+                                  uint32_t *out_local, void *chain_ws,
+                                  fgnn_stream_t stream);
+
+/* ---- one whole mini-batch: DoGPUSample (cuda_loops.cc:50-267) ------------------- */
+/* Enqueues hash-table reset, FillWithUnique(seeds) and, for layer i = L-1 .. 0,
+ * sample -> FillWithDuplicates -> MapEdges on `stream` without any host round trip.
+ * The uniform k-hop samplers insert their picks into the hash table while they
+ * gather them and the remap is folded into the compaction pass, so a layer is two
+ * launches (the reference: 8 kernels, 2 scans, ~12 stream syncs per layer).
+ *   plan : what to sample and the per-stream scratch (reused by every batch of a slot)
+ *   out  : where the batch's results go:
+ *            n2o            running unique list; after the call n2o[0..num_src(0)) == input_nodes
+ *            row[i]/col[i]  TrainGraph of layer i: row = neighbour local id, col = seed local id
+ *                           (cuda_loops.cc:210-221); data[i] = visit counts (random walk only)
+ *            counts         device u32[L][3] = {num_dst, num_edge, num_src} per layer
+ * Layer i uses fanout[i]; in_max[i] bounds its inputs (PredictNumNodes, common.cc:330-339);
+ * dst/pos/row/col/data[i] hold in_max[i]*fanout[i] entries. */
+#define FGNN_MAX_LAYERS 8
+typedef struct fgnn_sample_plan {
+  int32_t sample_type; /* SampleType, common.h:50-58 */
+  uint32_t num_layers;
+  uint32_t fanout[FGNN_MAX_LAYERS];
+  uint32_t in_max[FGNN_MAX_LAYERS];
+  const uint32_t *indptr, *indices;
+  const float *prob_table;
+  const uint32_t *alias_table;
+  const float *prob_prefix_table;
+  uint32_t walk_len, num_walk; /* random walk (sample_type 3): fanout[i] = top-K */
+  double restart_prob;
+  uint64_t seed;
+  void *table; /* fgnn_k_ht_bytes(capacity) */
+  size_t capacity;
+  uint32_t *num_items; /* device u32 */
+  void *chain_ws;
+  void *workspace; /* max over layers of the sampler's *_workspace_bytes, or NULL */
+  size_t workspace_bytes;
+  uint32_t *dst[FGNN_MAX_LAYERS]; /* scratch: sampled global ids */
+  uint32_t *pos[FGNN_MAX_LAYERS]; /* scratch: their hash buckets */
+} fgnn_sample_plan;
+typedef struct fgnn_sample_out {
+  uint32_t *n2o;
+  uint32_t *row[FGNN_MAX_LAYERS], *col[FGNN_MAX_LAYERS], *data[FGNN_MAX_LAYERS];
+  uint32_t *counts;
+} fgnn_sample_out;
+int fgnn_k_sample_batch(const fgnn_sample_plan *plan, const fgnn_sample_out *out,
+                        const uint32_t *seeds, uint32_t n_seeds_max,
+                        const uint32_t *d_n_seeds, uint64_t batch_key,
+                        fgnn_stream_t stream);
+
 /* ---- feature cache ---------------------------------------------------------- */
 /* SampleCacheTableInit / DistCacheManager ctor steps 1-2 (dist_engine.cc:193-229,
  * dist_cache_manager_host.cc:84-95): table[v]=EMPTY; table[rank[i]]=i, i<num_cached */

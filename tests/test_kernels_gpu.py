@@ -200,6 +200,35 @@ def test_hashtable_matches_oracle(K, oracle, n_seed, n_dup, universe):
     assert np.array_equal(ht.unique(), seeds)
 
 
+@pytest.mark.parametrize("n_seed,n_dup,universe", [(0, 1, 10), (8, 33, 100), (100, 5000, 300), (8000, 200000, 50000),
+                                                   (1000, 1500000, 1 << 20), (1, 100000, 3)])
+def test_hashtable_fill_and_map_fused_matches_oracle(K, oracle, n_seed, n_dup, universe):
+    """fgnn_k_ht_fill_duplicates_map == FillWithDuplicates followed by GPUMapEdges: same unique order, and
+    every item of the fill remapped in the same pass (owners in lower chunks are waited for, not re-probed);
+    1.5 M items exercise chunks longer than the register-cached tiles."""
+    rng = np.random.default_rng(n_seed * 3 + n_dup)
+    seeds = rng.permutation(universe)[:n_seed].astype(np.uint32)
+    max_items = n_seed + 3 * n_dup + 16
+    ht = HT(K, max_items)
+    oh = oracle.hashtable(max_items)
+    ht.fill_unique(seeds)
+    oh.fill_unique(seeds)
+    for rnd in range(3):
+        ids = rng.integers(0, universe, size=n_dup).astype(np.uint32)
+        d = dev(ids)
+        pos = torch.empty(n_dup, dtype=torch.int32, device="cuda")
+        loc = torch.full((n_dup + 1,), -1, dtype=torch.int32, device="cuda")
+        m = max(0, n_dup - rnd)                                                 # ragged device count
+        dn = torch.tensor([m], dtype=torch.int32, device="cuda")
+        K.ht_fill_duplicates_map(ht.table, ht.cap, d, n_dup, dn, pos, ht.n2o, ht.num, loc, ht.ws)
+        oh.fill_duplicates(ids[:m])
+        assert ht.num_items() == oh.num_items
+        assert np.array_equal(ht.unique(), oh.unique())
+        assert np.array_equal(host(loc, m), oh.map(ids[:m]))
+        assert host(loc)[m:].tolist() == [0xFFFFFFFF] * (n_dup + 1 - m)
+        assert int(ht.ws.abs().sum().item()) == 0
+
+
 def test_hashtable_map_absent_is_empty(K):
     ht = HT(K, 100)
     ht.fill_unique(np.array([5, 6, 7], np.uint32))
@@ -456,6 +485,59 @@ def test_random_walk_topk_matches_oracle(K, oracle, gs, n, W, L, Kn, p):
     assert np.array_equal(host(outs[0], m), es) and np.array_equal(host(outs[1], m), ed)
     assert np.array_equal(host(outs[3], m), ew)
     assert int(ws.abs().sum().item()) == 0
+
+
+@pytest.mark.parametrize("sample_type,fanouts,n_seed", [
+    ("khop2", [5, 10, 15], 2000), ("khop2", [25, 10], 777), ("khop0", [5, 10], 1500), ("khop1", [10, 5], 900),
+    ("weighted_khop", [10, 5], 900), ("weighted_khop_prefix", [8, 4], 500), ("weighted_khop_hash_dedup", [6, 3], 400),
+    ("random_walk", [5, 5, 5], 300), ("khop2", [3], 0), ("khop2", [4, 4], 1)])
+def test_sample_batch_call_matches_oracle_driver(K, oracle, gs, gm, sample_type, fanouts, n_seed):
+    """fgnn_k_sample_batch (the one C call the engine makes per mini-batch: fused sample+insert and
+    compact+remap, counts written by the kernels) against the numpy restatement of DoGPUSample
+    (cuda_loops.cc:50-267), for every SampleType; two slots used alternately on two streams."""
+    from fgnn_b200.pipeline import HotPath
+    from oracle.oracle import sample_batch_oracle
+    g = gm if sample_type in ("khop2", "khop0") else gs
+    graph = dict(indptr=g.indptr_np, indices=g.indices_np)
+    kw = {}
+    rw = None
+    if sample_type.startswith("weighted"):
+        prob, alias, prefix = weight_tables(oracle, g.indptr_np, g.indices_np)
+        graph.update(prob_table=prob, alias_table=alias, prob_prefix_table=prefix)
+        kw = dict(prob_table=torch.from_numpy(prob).cuda(), alias_table=dev(alias),
+                  prefix_table=torch.from_numpy(prefix).cuda())
+    if sample_type == "random_walk":
+        rw = dict(random_walk_length=3, random_walk_restart_prob=0.5, num_random_walk=4, num_neighbor=fanouts[0])
+    batch = max(n_seed, 8)
+    hp = HotPath(g.indptr, g.indices, len(g.indptr_np) - 1, fanouts, batch, sample_type, seed=SEED, rw=rw,
+                 num_slots=2, **kw)
+    streams = [torch.cuda.Stream(), torch.cuda.Stream()]
+    runs = []
+    for rep in range(4):                     # slots reused: scratch and chain workspace must come back clean
+        seeds = pick_seeds(g.indptr_np, n_seed, 100 + rep)
+        slot = rep % 2
+        d_seeds = dev(seeds) if n_seed else torch.zeros(1, dtype=torch.int32, device="cuda")
+        torch.cuda.current_stream().synchronize()
+        with torch.cuda.stream(streams[slot]):
+            hp.sample(d_seeds, n_seed, 40 + rep, slot=slot)
+        runs.append((seeds, slot, 40 + rep, d_seeds))
+        if rep % 2 == 1:                     # two batches in flight, then check both
+            torch.cuda.synchronize()
+            for seeds_, slot_, key_, _ in runs[-2:]:
+                exp = sample_batch_oracle(oracle, graph, seeds_, fanouts, sample_type, SEED, key_, rw=rw)
+                sl = hp.slots[slot_]
+                cnt = sl.counts.cpu().numpy().astype(np.int64)
+                n_in = int(sl.num_items.item())
+                assert np.array_equal(host(sl.n2o, n_in), exp["input_nodes"])
+                for i in range(len(fanouts)):
+                    lay = exp["layers"][i]
+                    assert cnt[i].tolist() == [lay["num_dst"], lay["num_edge"], lay["num_src"]]
+                    m = lay["num_edge"]
+                    assert np.array_equal(host(sl.row[i], m), lay["row"])
+                    assert np.array_equal(host(sl.col[i], m), lay["col"])
+                    if sample_type == "random_walk":
+                        assert np.array_equal(host(sl.data[i], m), lay["data"])
+                assert int(sl.chain.abs().sum().item()) == 0
 
 
 # ---------------------------------------------------------------------------

@@ -1,0 +1,118 @@
+#!/usr/bin/env python
+"""Micro-benchmark of the sampling chain (fgnn_k_sample_batch) at the bench.py shape, alone and overlapped
+with the feature gather, for the kernel-fusion variants (FGNN_BATCH_FUSE bit 0: insert while sampling,
+bit 1: remap folded into the compaction).
+
+  python tools/bench_sample.py [--steps 150]
+"""
+import argparse
+import json
+import os
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "fgnn-artifacts_b200"))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--steps", type=int, default=150)
+    ap.add_argument("--workload", default="papers100M")
+    ap.add_argument("--empty-feat", type=int, default=22)
+    ap.add_argument("--cache-pct", type=float, default=0.3)
+    a = ap.parse_args()
+    import torch
+    import bench
+    from fgnn_b200 import kernels as K
+    from fgnn_b200.pipeline import HotPath
+    dev = "cuda:0"
+    torch.cuda.set_device(0)
+    K.load()
+    wl = bench.build_workload(a, dev)
+    V, D = wl["V"], wl["D"]
+    BATCH, FANOUTS = bench.BATCH, bench.FANOUTS
+    spe = (wl["T"] + BATCH - 1) // BATCH
+    perm = wl["train"]
+    SL = 4
+    hp = HotPath(wl["indptr"], wl["indices"], V, FANOUTS, BATCH, "khop2", seed=1, device=dev, num_slots=SL)
+    rank = torch.randperm(V, device=dev).to(torch.int32)
+    hp.build_cache(rank, a.cache_pct, wl["host_feat"], D * 4, wl["feat_mask"])
+    # every row "hit": table over the cached fraction only -> make all nodes map into the cache (mod)
+    hp.cache_table = (torch.arange(V, device=dev, dtype=torch.int64) % hp.num_cached).to(torch.int32)
+    hp.set_labels(wl["label"])
+    streams = [torch.cuda.Stream(device=dev) for _ in range(SL)]
+    xs = torch.cuda.Stream(device=dev, priority=-1)
+
+    def seeds_of(k):
+        s = k % (spe - 1)
+        return perm[s * BATCH:(s + 1) * BATCH], BATCH
+
+    def run(slots, with_gather, steps):
+        sampled = [torch.cuda.Event() for _ in range(slots)]
+        gathered = [torch.cuda.Event() for _ in range(slots)]
+        main = torch.cuda.current_stream()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        for st in streams + [xs]:
+            st.wait_stream(main)
+        e0.record()
+        for st in streams + [xs]:
+            st.wait_stream(main)
+        for k in range(steps):
+            sd, n = seeds_of(k)
+            sl = k % slots
+            with torch.cuda.stream(streams[sl]):
+                if with_gather:
+                    streams[sl].wait_event(gathered[sl])
+                hp.sample(sd, n, 7000 + k, slot=sl)
+                sampled[sl].record()
+            if with_gather:
+                with torch.cuda.stream(xs):
+                    xs.wait_event(sampled[sl])
+                    hp.gather(sl)
+                    hp.gather_labels(sd, n)
+                    gathered[sl].record()
+        for st in streams + [xs]:
+            main.wait_stream(st)
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / steps * 1e3
+
+    os.environ["FGNN_TUNING_DYNAMIC"] = "1"
+    for fuse, hint in ((0, 0), (0, 1), (2, 0), (2, 1), (3, 1)):
+        os.environ["FGNN_BATCH_FUSE"] = str(fuse)
+        os.environ["FGNN_GATHER_L2HINT"] = str(hint)
+        res = {"fuse": fuse, "l2_evict_first": hint}
+        for slots in (1, 3):
+            run(slots, False, 10)
+            res["sample_only_us_slots%d" % slots] = round(run(slots, False, a.steps), 1)
+        for slots in (1, 2, 3, 4):
+            run(slots, True, 10)
+            res["with_gather_us_slots%d" % slots] = round(run(slots, True, a.steps), 1)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for k in range(50):
+            hp.gather(0)
+        e1.record()
+        torch.cuda.synchronize()
+        res["gather_alone_us"] = round(e0.elapsed_time(e1) / 50 * 1e3, 1)
+        print("SAMPLE_JSON " + json.dumps(res))
+        sys.stdout.flush()
+    os.environ.pop("FGNN_BATCH_FUSE")
+    # gather alone for reference
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for k in range(50):
+        hp.gather(0)
+    e1.record()
+    torch.cuda.synchronize()
+    print("SAMPLE_JSON " + json.dumps({"gather_alone_us": round(e0.elapsed_time(e1) / 50 * 1e3, 1),
+                                       "n_in": int(hp.slots[0].num_items.item())}))
+
+
+if __name__ == "__main__":
+    main()
