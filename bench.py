@@ -37,7 +37,7 @@ BATCH = 8000
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=604)      # four papers100M epochs at batch 8000 (151 steps each)
+    ap.add_argument("--steps", type=int, default=1510)     # ten papers100M epochs at batch 8000 (151 steps each)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default=os.environ.get("FGNN_BENCH_WORKLOAD", "papers100M"))
@@ -49,22 +49,66 @@ def parse():
                     help="mini-batches in flight on separate streams (device-resident leg)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-partition", action="store_true",
+                    help="N > 1: skip the extra leg that stripes the feature cache over the GPUs (NVLink peer loads)")
     return ap.parse_args()
 
 
 # ---------------------------------------------------------------------------
 class ClockSampler:
+    """SM clock + throttle reasons sampled DURING the timed region.  NVML in a background thread (5 ms period:
+    the default timed region lasts ~0.15 s, too short for `nvidia-smi -lms`, whose first sample arrives after its
+    own start-up); nvidia-smi is the fallback when the NVML binding is unavailable."""
     QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
              "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    REASONS = ((0x8, "hw_slowdown"), (0x40, "hw_thermal_slowdown"), (0x20, "sw_thermal_slowdown"), (0x4, "sw_power_cap"))
 
     def __init__(self, gpu_index):
         self.idx = gpu_index
-        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
         self.p = None
+        self.f = None
+        self.thread = None
+        self.stop_flag = False
+        self.sm, self.mx, self.reasons = [], [], set()
+
+    def _nvml_handle(self):
+        import pynvml
+        import torch
+        pynvml.nvmlInit()
+        try:
+            uuid = str(torch.cuda.get_device_properties(self.idx).uuid)
+            return pynvml, pynvml.nvmlDeviceGetHandleByUUID(("GPU-" + uuid).encode())
+        except Exception:
+            return pynvml, pynvml.nvmlDeviceGetHandleByIndex(self.idx)
+
+    def _loop(self, nv, h):
+        get_reasons = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or \
+            getattr(nv, "nvmlDeviceGetCurrentClocksThrottleReasons")
+        mx = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
+        while not self.stop_flag:
+            try:
+                self.sm.append(float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)))
+                self.mx.append(float(mx))
+                r = int(get_reasons(h))
+                for bit, name in self.REASONS:
+                    if r & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            time.sleep(0.005)
 
     def start(self):
         try:
+            import threading
+            nv, h = self._nvml_handle()
+            self.thread = threading.Thread(target=self._loop, args=(nv, h), daemon=True)
+            self.thread.start()
+            return
+        except Exception:
+            self.thread = None
+        try:
+            self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
             self.p = subprocess.Popen(["nvidia-smi", "-i", str(self.idx), "--query-gpu=" + self.QUERY,
                                        "--format=csv,noheader,nounits", "-lms", "100"],
                                       stdout=self.f, stderr=subprocess.DEVNULL)
@@ -72,6 +116,12 @@ class ClockSampler:
             self.p = None
 
     def stop(self):
+        if self.thread is not None:
+            self.stop_flag = True
+            self.thread.join(timeout=2)
+            return {"sm_mhz": statistics.median(self.sm) if self.sm else None,
+                    "sm_max_mhz": max(self.mx) if self.mx else None, "reasons": sorted(self.reasons),
+                    "samples": len(self.sm), "source": "nvml, 5 ms period, timed region only"}
         if self.p is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         time.sleep(0.15)
@@ -100,7 +150,7 @@ class ClockSampler:
         except OSError:
             pass
         return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "reasons": sorted(reasons), "samples": len(sm), "source": "nvidia-smi -lms 100"}
 
 
 def step_of(k, rank, world, steps_per_epoch):
@@ -187,19 +237,28 @@ def run_ours(args):
         hi = min(wl["T"], lo + BATCH)
         return perm[lo:hi], hi - lo
 
-    # ---- PreSC: one pre-sampling epoch -> hotness ranking -> cache (cuda/pre_sampler.cc:57-110)
+    # ---- PreSC: one pre-sampling epoch -> hotness ranking -> cache (cuda/pre_sampler.cc:57-110).
+    # N > 1: every rank pre-samples its own share of the epoch's mini-batches, the visit counters are summed with
+    # one NCCL all-reduce, rank 0 ranks the vertices and the ranking is broadcast once (the reference publishes
+    # sampler 0's ranking through shared memory, dist_engine.cc:119-123).  No collective after this point.
+    from fgnn_b200 import partition as P
     t0 = time.time()
     freq = torch.zeros(V, dtype=torch.int32, device=dev)
-    for s in range(steps_per_epoch):
+    for s in range(rank, steps_per_epoch, world):
         lo = s * BATCH
         hi = min(wl["T"], lo + BATCH)
         hp.sample(perm[lo:hi], hi - lo, 1_000_000 + s)
         hp.presample_count(freq)
+    P.allreduce_freq(freq)
     rank_nodes = torch.empty(V, dtype=torch.int32, device=dev)
-    wsr = torch.empty(K.presc_rank_workspace_bytes(V), dtype=torch.uint8, device=dev)
-    K.presc_rank(freq, V, rank_nodes, wsr)
+    if rank == 0:
+        wsr = torch.empty(K.presc_rank_workspace_bytes(V), dtype=torch.uint8, device=dev)
+        K.presc_rank(freq, V, rank_nodes, wsr)
+        torch.cuda.synchronize()
+        del wsr
+    P.broadcast_ranking(rank_nodes, src=0)
     torch.cuda.synchronize()
-    del wsr, freq
+    del freq
     presc_s = time.time() - t0
     hp.set_labels(wl["label"])
 
@@ -207,8 +266,9 @@ def run_ours(args):
     s_streams = [torch.cuda.Stream(device=dev) for _ in range(S)]
     x_stream = torch.cuda.Stream(device=dev, priority=-1)
 
-    def measure(cache_pct, Ksteps, W, key0, profile=False):
-        """Build the cache at `cache_pct`, run W warm-up + Ksteps timed steps; device-timed.
+    def measure(cache_pct, Ksteps, W, key0, profile=False, partition=False):
+        """Build the cache at `cache_pct` (replicated per GPU, or with partition=True striped over the ranks'
+        GPUs and read through NVLink peer mappings), run W warm-up + Ksteps timed steps; device-timed.
         Like the engine's pump: batch k is sampled on slot k % S (own stream, own hash table and scratch) while
         the extraction stream gathers the features of batch k-1; a slot is resampled only after its previous
         batch has been gathered."""
@@ -216,7 +276,14 @@ def run_ours(args):
         hp.cache = None
         hp.feat_out = None
         torch.cuda.empty_cache()
-        hp.build_cache(rank_nodes, cache_pct, wl["host_feat"], row_bytes, wl["feat_mask"])
+        shards = None
+        if partition:
+            shards = P.CacheShards(rank_nodes, int(V * cache_pct), wl["host_feat"], row_bytes, wl["feat_mask"],
+                                   rank, world, dev)
+            hp.build_cache(rank_nodes, cache_pct, wl["host_feat"], row_bytes, wl["feat_mask"], num_shards=world,
+                           shard_id=rank, peer_ptrs=shards.ptrs, fill_local=False)
+        else:
+            hp.build_cache(rank_nodes, cache_pct, wl["host_feat"], row_bytes, wl["feat_mask"])
         torch.cuda.synchronize()
         cache_s = time.time() - t0
         hist = torch.zeros((Ksteps, hp.L, 3), dtype=torch.int32, device=dev)
@@ -288,6 +355,10 @@ def run_ours(args):
         r["gather_ms"] = sum(e[2].elapsed_time(e[3]) for e in ev)    # the gather kernel alone, on its stream
         r["extract_ms"] = sum(e[2].elapsed_time(e[4]) for e in ev)   # gather + label gather
         r["hits"], r["misses"] = [int(x) for x in hp.stats.tolist()]
+        if shards is not None:
+            r["shard_bytes"] = shards.nbytes
+            hp.cache_table = hp.shard_ptrs = None
+            shards.close()
         return r
 
     Ksteps, W = args.steps, max(3, args.warmup)
@@ -312,6 +383,24 @@ def run_ours(args):
     torch.cuda.synchronize()
     gather_alone_ms = ga0.elapsed_time(ga1) / 20
     ms_total, edges_all = aggregate(ms_total, edges, dev)
+
+    # ---- N > 1: the same workload with the cache striped over the ranks' GPUs (north_star):
+    # every GPU keeps 1/N of the rows, (N-1)/N of the hit rows are NVLink peer loads inside the gather kernel.
+    part = None
+    if world > 1 and not args.no_partition:
+        hp.cache = None
+        torch.cuda.empty_cache()
+        kp = min(Ksteps, 2 * steps_per_epoch)
+        rp = measure(args.cache_pct, kp, W, 3_000_000, partition=True)
+        p_ms, p_edges = aggregate(rp["ms_total"], rp["edges"], dev)
+        remote = rp["hits"] * (world - 1) / world * row_bytes       # slots are striped slot % N: uniform
+        part = {"note": "cache striped over the %d GPUs (slot %% N), remote rows read by NVLink peer loads inside "
+                        "fgnn_k_gather_cached; population = PreSC ranking broadcast + each rank fills its stripe" % world,
+                "edges_per_s": p_edges / (p_ms * 1e-3), "ms_per_step": p_ms / kp, "steps": kp,
+                "gather_ms_per_step": rp["gather_ms"] / kp, "shard_GB_per_gpu": rp["shard_bytes"] / 1e9,
+                "nvlink_peer_GBps_per_gpu": remote / (rp["gather_ms"] * 1e-3) / 1e9 if rp["gather_ms"] else None,
+                "nvlink_peak_GBps": 900.0, "cache_hit_rate": rp["hits"] / max(1, rp["hits"] + rp["misses"]),
+                "extract_GBps_per_gpu": rp["n_in_total"] * row_bytes / (rp["gather_ms"] * 1e-3) / 1e9}
 
     # ---- roofline of the dominant kernel: the fused cache-aware feature gather -----------
     peak, peak_kind = peaks()
@@ -340,7 +429,9 @@ def run_ours(args):
                    "e2e_cache_percentage": E2E_CACHE_PCT,
                    "host_feat_rows": int(wl["host_feat"].shape[0]),
                    "l2_policy": "inputs larger than L2 (6.9 GB topology, %.1f GB cache)" % (hp.num_cached * row_bytes / 1e9),
-                   "sharding": "seed mini-batches split across ranks, topology + cache replicated"},
+                   "sharding": "seed mini-batches split across ranks (no data-path collective); topology replicated; "
+                               "cache replicated for `value` (the 57 GB table fits one B200), striped over the GPUs "
+                               "with NVLink peer loads in extra.partitioned_cache; PreSC ranking: NCCL all-reduce + broadcast at init"},
         "clocks": clk, "gpu_launches": int(launches),
         "roofline": roofline,
         "extra": {"sample_only_edges_per_s": edges / (sample_ms * 1e-3) if sample_ms else None,
@@ -354,6 +445,8 @@ def run_ours(args):
                   "note": "sample_ms is the sampling chain's time on its own stream while other slots and the "
                           "gather run concurrently; value uses the wall time of the whole overlapped loop"},
     }
+    if part is not None:
+        out["extra"]["partitioned_cache"] = part
     if r25 is not None:
         k25 = min(Ksteps, steps_per_epoch)
         out["extra"]["cache25"] = {

@@ -1,4 +1,5 @@
 // Library-level entry points of the kernel C-ABI.
+#include <stdlib.h>
 #include <string.h>
 
 #include "common.cuh"
@@ -17,6 +18,16 @@ int sm_count() {
     cached[dev] = n;
   }
   return cached[dev];
+}
+int grid_share_div() {
+  static int d = 0;
+  static const bool dynamic = getenv("FGNN_TUNING_DYNAMIC") && atoi(getenv("FGNN_TUNING_DYNAMIC")) != 0;
+  if (d == 0 || dynamic) {
+    const char *v = getenv("FGNN_GRID_DIV");
+    d = v && *v ? atoi(v) : 1;
+    if (d < 1) d = 1;
+  }
+  return d;
 }
 }  // namespace fgnn
 

@@ -35,10 +35,14 @@ inline int occupancy(Kern kern, int block, size_t smem) {
 
 // persistent grid: enough CTAs to cover n_max at `min_items` per CTA, capped
 // at sm_count * ctas_per_sm (and the chain limit when chained).
+int grid_share_div();  // api.cu: FGNN_GRID_DIV (>= 1), read once
 inline int persistent_grid(uint64_t n_max, uint32_t min_items, int ctas_per_sm,
-                           bool chained) {
+                           bool chained, bool whole_gpu = false) {
   uint64_t want = (n_max + min_items - 1) / min_items;
   uint64_t cap = (uint64_t)sm_count() * (uint64_t)ctas_per_sm;
+  // sampling-side kernels of several slots run next to each other on different streams: with
+  // FGNN_GRID_DIV = d each launch takes at most 1/d of the resident CTA slots, so d launches co-reside
+  if (!whole_gpu) cap = (cap + grid_share_div() - 1) / grid_share_div();
   if (chained && cap > (uint64_t)kMaxChainCtas) cap = kMaxChainCtas;
   if (want > cap) want = cap;
   if (want < 1) want = 1;

@@ -452,6 +452,168 @@ gather_bulk_kernel(char *__restrict__ out, const uint32_t *__restrict__ nodes, u
   }
 }
 
+
+// ---------------------------------------------------------------------------
+// Bulk-copy gather with DYNAMIC work distribution.
+//
+// gather_bulk_kernel above cuts the rows into one static contiguous range per warp.  That is optimal when the
+// kernel owns the GPU, but in the pipelined loop the sampling kernels of the other slots hold SM resources when
+// the gather launches: some of its 148 CTAs are placed tens of microseconds late and, with a static partition,
+// the whole kernel waits for them (bench r1_p: 0.109 ms alone, 0.18 ms in the loop).  Here warps take
+// 32-row super-groups from a global ticket counter, three tickets ahead (the index pipeline needs the node ids
+// of the next two super-groups), so late CTAs simply take fewer tickets.  Everything else — per-warp
+// shared-memory ring, cp.async.bulk loads counted on mbarriers, one bulk store per stage — is unchanged.
+// `tick` = {next ticket, finished CTAs}; the last CTA to finish re-zeroes it for the next launch.
+// ---------------------------------------------------------------------------
+constexpr int kSgQueue = 16;  // >= S - 2 super-groups can lie between the issue and the store cursor
+
+template <int S, int NW>
+__global__ void __launch_bounds__(NW * 32)
+gather_bulk_dyn_kernel(char *__restrict__ out, const uint32_t *__restrict__ nodes, uint32_t n_max,
+                       const uint32_t *__restrict__ d_n, const uint32_t *__restrict__ table,
+                       RowSrc rs, uint32_t G, uint32_t stage_bytes, int mode,
+                       unsigned long long *d_stats, unsigned int *tick) {
+  rs.shard0 = (const char *)__ldg((const unsigned long long *)rs.shards);
+  const bool hint = (mode & 2) != 0;
+  const int miss_by_ldg = mode & 1;
+  const uint64_t pol = l2_evict_first_policy();
+  constexpr uint32_t A = S - 2;
+  static_assert(S - 2 <= kSgQueue, "super-group queue too short");
+  extern __shared__ __align__(128) unsigned char s_raw[];
+  __shared__ __align__(8) unsigned long long s_bar[NW][S];
+  __shared__ uint32_t s_sgbase[NW][kSgQueue];
+  const uint32_t n = load_count(n_max, d_n);
+  const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const uint32_t nsg = (n + 31u) / 32u;
+  const uint32_t row_bytes = (uint32_t)rs.row_bytes;
+  unsigned char *stage0 = s_raw + (size_t)warp * S * stage_bytes;
+  if (lane == 0) {
+#pragma unroll
+    for (int s = 0; s < S; ++s) mbar_init(smem_u32(&s_bar[warp][s]), 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncwarp();
+  uint32_t hits = 0, misses = 0;
+  auto take = [&]() -> uint32_t {  // row base of this warp's next super-group, kEmpty when none is left
+    uint32_t t = 0;
+    if (lane == 0) t = atomicAdd(tick, 1u);
+    t = __shfl_sync(0xFFFFFFFFu, t, 0);
+    return t < nsg ? t * 32u : kEmpty;
+  };
+  auto load_node = [&](uint32_t base) -> uint32_t {
+    return (base != kEmpty && base + lane < n) ? __ldg(nodes + base + lane) : kEmpty;
+  };
+  auto subs_of = [&](uint32_t base) -> uint32_t {
+    const uint32_t rows = n - base < 32u ? n - base : 32u;
+    return (rows + G - 1) / G;
+  };
+
+  // index pipeline: super-group being issued (i), the next one (n) and the one after (nn)
+  uint32_t base_i = take();
+  uint32_t base_n = base_i != kEmpty ? take() : kEmpty;
+  uint32_t base_nn = base_n != kEmpty ? take() : kEmpty;
+  uint32_t node_i = load_node(base_i), node_n = load_node(base_n), node_nn = load_node(base_nn);
+  uint32_t slot_i = node_i != kEmpty ? __ldg(table + node_i) : kEmpty;
+  uint32_t slot_n = node_n != kEmpty ? __ldg(table + node_n) : kEmpty;
+  const char *sp = node_i != kEmpty ? rs.resolve(node_i, slot_i) : nullptr;
+  if (node_i != kEmpty) { if (slot_i != kEmpty) ++hits; else ++misses; }
+  bool exhausted = base_i == kEmpty;
+  uint32_t subs_i = exhausted ? 0u : subs_of(base_i);
+  uint32_t q_issue = 0, sub_issue = 0, issued = 0;
+  uint32_t q_store = 0, sub_store = 0, stored = 0;
+  if (lane == 0) s_sgbase[warp][0] = base_i;
+  __syncwarp();
+
+  while (true) {
+    while (!exhausted && issued <= stored + A) {
+      // the stage about to be refilled was stored two stores ago: one younger store may still be reading
+      if (lane == 0) bulk_wait_read<1>();
+      __syncwarp();
+      const uint32_t s = issued % S;
+      const uint32_t bar = smem_u32(&s_bar[warp][s]);
+      unsigned char *st = stage0 + (size_t)s * stage_bytes;
+      const bool mine = (lane / G) == sub_issue && node_i != kEmpty;
+      const bool by_bulk = mine && (slot_i != kEmpty || !miss_by_ldg);
+      const uint32_t nbulk = __popc(__ballot_sync(0xFFFFFFFFu, by_bulk));
+      if (lane == 0) mbar_expect_tx(bar, nbulk * row_bytes);
+      __syncwarp();
+      if (by_bulk) {
+        if (hint) bulk_g2s(smem_u32(st + (size_t)(lane - sub_issue * G) * row_bytes), sp, row_bytes, bar, pol);
+        else bulk_g2s(smem_u32(st + (size_t)(lane - sub_issue * G) * row_bytes), sp, row_bytes, bar);
+      }
+      uint32_t ldg_rows = __ballot_sync(0xFFFFFFFFu, mine && !by_bulk);
+      while (ldg_rows) {  // host-resident rows: warp-wide 16-byte loads into the stage
+        const int r = __ffs(ldg_rows) - 1;
+        ldg_rows &= ldg_rows - 1;
+        const char *p = shfl_ptr(sp, r);
+        for (uint32_t c = lane * 16u; c < row_bytes; c += 32u * 16u)
+          *reinterpret_cast<uint4 *>(st + (size_t)(r - sub_issue * G) * row_bytes + c) = ld_nc_na_v4(p + c);
+      }
+      ++issued;
+      if (++sub_issue == subs_i) {  // rotate the index pipeline into the next super-group
+        base_i = base_n; node_i = node_n; slot_i = slot_n;
+        base_n = base_nn; node_n = node_nn;
+        slot_n = node_n != kEmpty ? __ldg(table + node_n) : kEmpty;
+        base_nn = base_n != kEmpty ? take() : kEmpty;
+        node_nn = load_node(base_nn);
+        sub_issue = 0;
+        ++q_issue;
+        if (base_i == kEmpty) {
+          exhausted = true;
+        } else {
+          sp = node_i != kEmpty ? rs.resolve(node_i, slot_i) : nullptr;
+          if (node_i != kEmpty) { if (slot_i != kEmpty) ++hits; else ++misses; }
+          subs_i = subs_of(base_i);
+          if (lane == 0) s_sgbase[warp][q_issue % kSgQueue] = base_i;
+          __syncwarp();
+        }
+      }
+    }
+    if (stored == issued) break;
+    const uint32_t s = stored % S;
+    mbar_wait(smem_u32(&s_bar[warp][s]), (stored / S) & 1u);
+    const uint32_t base = s_sgbase[warp][q_store % kSgQueue];
+    const uint32_t row0 = base + sub_store * G;
+    const uint32_t rows_here = n - row0 < G ? n - row0 : G;
+    fence_proxy_async();  // generic-proxy stage writes (miss rows) -> async proxy
+    __syncwarp();
+    if (lane == 0) {
+      if (hint) bulk_s2g(out + (size_t)row0 * row_bytes, smem_u32(stage0 + (size_t)s * stage_bytes), rows_here * row_bytes, pol);
+      else bulk_s2g(out + (size_t)row0 * row_bytes, smem_u32(stage0 + (size_t)s * stage_bytes), rows_here * row_bytes);
+      bulk_commit();
+    }
+    ++stored;
+    if (++sub_store == subs_of(base)) { sub_store = 0; ++q_store; }
+  }
+  if (lane == 0) bulk_wait_read<0>();
+  if (d_stats) {
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) {
+      hits += __shfl_down_sync(0xFFFFFFFFu, hits, d);
+      misses += __shfl_down_sync(0xFFFFFFFFu, misses, d);
+    }
+    if (lane == 0) {
+      if (hits) atomicAdd(d_stats + 0, (unsigned long long)hits);
+      if (misses) atomicAdd(d_stats + 1, (unsigned long long)misses);
+    }
+  }
+  // every warp of this CTA has drawn its last ticket: the last CTA re-arms the counter
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned int prev = atomicAdd(tick + 1, 1u);
+    if (prev == gridDim.x - 1) {
+      tick[0] = 0u;
+      __threadfence();
+      tick[1] = 0u;
+    }
+  }
+}
+
+// ticket counters of the dynamic gather: one pair per launch in flight (round robin; a pair is re-zeroed by
+// the launch that used it, and 64 gathers are never in flight at once)
+constexpr int kTickSlots = 64;
+__device__ unsigned int g_gather_tick[kTickSlots][2];
+
 inline int vec_width(size_t row_bytes, const void *a, const void *b, const void *c = nullptr) {
   const uintptr_t bits = (uintptr_t)row_bytes | (uintptr_t)a | (uintptr_t)b | (uintptr_t)c;
   if ((bits & 15) == 0) return 16;
@@ -463,7 +625,7 @@ inline int vec_width(size_t row_bytes, const void *a, const void *b, const void 
 // exactly one resident wave (ncu r1_a: a fixed 8 CTAs/SM grid ran 1.33 waves
 // because only 6 CTAs of the 40-register uint4 kernel fit -> 25 % tail)
 inline int copy_grid(uint64_t chunks, int occ) {
-  return persistent_grid(chunks, kBlock * kUnroll, occ, false);
+  return persistent_grid(chunks, kBlock * kUnroll, occ, false, true);
 }
 
 }  // namespace
@@ -499,7 +661,7 @@ namespace fgnn {
 namespace {
 // A/B switches for profiling (read once): FGNN_GATHER_IMPL = flat | group | bulk
 struct GatherTuning {
-  int impl;         // 0 flat, 1 group, 2 bulk
+  int impl;         // 0 flat, 1 group, 2 bulk (static partition), 3 bulk with dynamic tickets
   int stages;       // bulk: ring depth per warp
   int warps;        // bulk: warps per CTA
   uint32_t stage_cap;  // bulk: max bytes per stage
@@ -519,6 +681,7 @@ GatherTuning read_tuning() {
   if (v && !strcmp(v, "flat")) g.impl = 0;
   if (v && !strcmp(v, "group")) g.impl = 1;
   if (v && !strcmp(v, "bulk")) g.impl = 2;
+  if (v && !strcmp(v, "dyn")) g.impl = 3;
   g.stages = env_int("FGNN_BULK_STAGES", 8);
   g.warps = env_int("FGNN_BULK_WARPS", 8);
   g.stage_cap = (uint32_t)env_int("FGNN_BULK_STAGE_BYTES", 2048);
@@ -549,7 +712,7 @@ int launch_bulk(char *out, const uint32_t *nodes, uint32_t n_max, const uint32_t
   int occ = tuning().ctas_per_sm ? tuning().ctas_per_sm : occupancy(kern, NW * 32, smem);
   // at least kMinSub sub-groups per warp so the ring fills
   const uint64_t subs = ((uint64_t)n_max + G - 1) / G;
-  const int grid = persistent_grid(subs, NW * 4, occ, false);
+  const int grid = persistent_grid(subs, NW * 4, occ, false, true);
   kern<<<grid, NW * 32, smem, st>>>(out, nodes, n_max, d_n, table, rs, G, stage_bytes,
                                     (tuning().miss_ldg ? 1 : 0) | (tuning().l2_hint ? 2 : 0), d_stats);
   return 0;
@@ -566,6 +729,59 @@ int launch_bulk_s(int stages, char *out, const uint32_t *nodes, uint32_t n_max, 
     case 12: return launch_bulk<12, NW>(out, nodes, n_max, d_n, table, rs, G, stage_bytes, d_stats, st);
     case 16: return launch_bulk<16, NW>(out, nodes, n_max, d_n, table, rs, G, stage_bytes, d_stats, st);
     default: return launch_bulk<8, NW>(out, nodes, n_max, d_n, table, rs, G, stage_bytes, d_stats, st);
+  }
+}
+
+// ticket pair for the next dynamic-gather launch of this process (one device per process in the engine and the
+// benches; the address is re-resolved when the current device changes)
+inline int next_tick(unsigned int **out) {
+  static unsigned int *tick_base = nullptr;
+  static int tick_dev = -1;
+  static unsigned int seq = 0;
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (!tick_base || tick_dev != dev) {
+    cudaError_t e = cudaGetSymbolAddress((void **)&tick_base, g_gather_tick);
+    if (e != cudaSuccess) return (int)e;
+    tick_dev = dev;
+  }
+  *out = tick_base + 2 * (seq++ % kTickSlots);
+  return 0;
+}
+
+template <int S, int NW>
+int launch_bulk_dyn(char *out, const uint32_t *nodes, uint32_t n_max, const uint32_t *d_n,
+                    const uint32_t *table, const RowSrc &rs, uint32_t G, uint32_t stage_bytes,
+                    unsigned long long *d_stats, cudaStream_t st) {
+  auto kern = gather_bulk_dyn_kernel<S, NW>;
+  const size_t smem = (size_t)NW * S * stage_bytes;
+  static size_t configured = 0;
+  if (smem > configured) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+    configured = smem;
+  }
+  unsigned int *tick = nullptr;
+  if (int rc = next_tick(&tick)) return rc;
+  int occ = tuning().ctas_per_sm ? tuning().ctas_per_sm : occupancy(kern, NW * 32, smem);
+  const uint64_t sgs = ((uint64_t)n_max + 31) / 32;
+  const int grid = persistent_grid(sgs, NW * 2, occ, false, true);  // >= 2 super-groups per warp
+  kern<<<grid, NW * 32, smem, st>>>(out, nodes, n_max, d_n, table, rs, G, stage_bytes,
+                                    (tuning().miss_ldg ? 1 : 0) | (tuning().l2_hint ? 2 : 0), d_stats, tick);
+  return 0;
+}
+
+template <int NW>
+int launch_bulk_dyn_s(int stages, char *out, const uint32_t *nodes, uint32_t n_max, const uint32_t *d_n,
+                      const uint32_t *table, const RowSrc &rs, uint32_t G, uint32_t stage_bytes,
+                      unsigned long long *d_stats, cudaStream_t st) {
+  switch (stages) {
+    case 3: return launch_bulk_dyn<3, NW>(out, nodes, n_max, d_n, table, rs, G, stage_bytes, d_stats, st);
+    case 4: return launch_bulk_dyn<4, NW>(out, nodes, n_max, d_n, table, rs, G, stage_bytes, d_stats, st);
+    case 6: return launch_bulk_dyn<6, NW>(out, nodes, n_max, d_n, table, rs, G, stage_bytes, d_stats, st);
+    case 12: return launch_bulk_dyn<12, NW>(out, nodes, n_max, d_n, table, rs, G, stage_bytes, d_stats, st);
+    case 16: return launch_bulk_dyn<16, NW>(out, nodes, n_max, d_n, table, rs, G, stage_bytes, d_stats, st);
+    default: return launch_bulk_dyn<8, NW>(out, nodes, n_max, d_n, table, rs, G, stage_bytes, d_stats, st);
   }
 }
 }  // namespace
@@ -591,7 +807,7 @@ extern "C" int fgnn_k_gather_cached(void *out, const uint32_t *nodes, uint32_t n
     rs.miss_src = (const char *)miss_src;
     rs.miss_mask = miss_mask;
     rs.row_bytes = row_bytes;
-    if (tn.impl == 2) {
+    if (tn.impl >= 2) {
       // stage = the most rows (power of two, <= 32) that fit the stage cap; the ring depth
       // shrinks for long rows so that warps * stages * stage_bytes stays within shared memory
       uint32_t G = 32;
@@ -604,7 +820,13 @@ extern "C" int fgnn_k_gather_cached(void *out, const uint32_t *nodes, uint32_t n
         stages = stages > 12 ? 12 : stages > 8 ? 8 : stages > 6 ? 6 : stages > 4 ? 4 : 3;
       if ((size_t)warps * stages * stage_bytes <= kSmemBudget) {
         int rc;
-        if (warps == 4)
+        if (tn.impl == 3 && warps == 4)
+          rc = launch_bulk_dyn_s<4>(stages, (char *)out, nodes, n_max, d_n, table, rs, G, stage_bytes, d_stats, st);
+        else if (tn.impl == 3 && warps == 16)
+          rc = launch_bulk_dyn_s<16>(stages, (char *)out, nodes, n_max, d_n, table, rs, G, stage_bytes, d_stats, st);
+        else if (tn.impl == 3)
+          rc = launch_bulk_dyn_s<8>(stages, (char *)out, nodes, n_max, d_n, table, rs, G, stage_bytes, d_stats, st);
+        else if (warps == 4)
           rc = launch_bulk_s<4>(stages, (char *)out, nodes, n_max, d_n, table, rs, G, stage_bytes, d_stats, st);
         else if (warps == 16)
           rc = launch_bulk_s<16>(stages, (char *)out, nodes, n_max, d_n, table, rs, G, stage_bytes, d_stats, st);
@@ -622,7 +844,7 @@ extern "C" int fgnn_k_gather_cached(void *out, const uint32_t *nodes, uint32_t n
     static const int occ_g = occupancy(gather_group_kernel, kBlock, 0);
     const int occ = tn.ctas_per_sm ? tn.ctas_per_sm : occ_g;
     const uint64_t groups = ((uint64_t)n_max + G - 1) / G;
-    const int grid = persistent_grid(groups, kBlock / 32, occ, false);
+    const int grid = persistent_grid(groups, kBlock / 32, occ, false, true);
     gather_group_kernel<<<grid, kBlock, 0, st>>>((char *)out, nodes, n_max, d_n, table, rs, cpr, G, d_stats);
     note_launch();
     return check_last();

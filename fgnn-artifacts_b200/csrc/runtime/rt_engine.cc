@@ -79,6 +79,11 @@ struct SharedRing {
   // partitioned cache: one IPC handle per trainer
   unsigned char ipc_handle[16][FGNN_IPC_HANDLE_BYTES];
   uint64_t shard_rows[16];
+  // device queue: the slot PAYLOADS live in trainer HBM, slot s on trainer s % T at local
+  // index s / T; samplers write them with peer copies over NVLink, only the SlotHeader stays in host memory
+  uint32_t devq_enabled, devq_trainers;
+  std::atomic<uint32_t> devq_ready[16];
+  unsigned char devq_handle[16][FGNN_IPC_HANDLE_BYTES];
   char *base() { return reinterpret_cast<char *>(this); }
   IdType *ranking() { return reinterpret_cast<IdType *>(base() + ranking_off); }
   char *slot(uint64_t i) { return base() + slots_off + (i % num_slots) * slot_bytes; }
@@ -838,6 +843,11 @@ void Engine::CreateSharedState() {  // dist_engine.cc:115-153 + memory_queue.cc:
   ring_->ranking_off = hdr;
   ring_->slots_off = hdr + rank_bytes;
   ring_->presample_done = 0;
+  // SAMGRAPH_NVLINK_QUEUE=0 restores the reference's D2H -> pinned slot -> H2D bounce (task_queue.cc:131-137,241-255)
+  ring_->devq_enabled = (IsEnvSet("SAMGRAPH_NVLINK_QUEUE") && GetEnv("SAMGRAPH_NVLINK_QUEUE") == "0") ? 0u : 1u;
+  ring_->devq_trainers = (uint32_t)std::min<size_t>(rc.num_train_worker, 16);
+  if (rc.num_train_worker > 16) ring_->devq_enabled = 0;
+  for (int t = 0; t < 16; ++t) ring_->devq_ready[t] = 0;
   for (uint32_t i = 0; i < nslots; ++i) reinterpret_cast<SlotHeader *>(ring_->slot(i))->ready = 0;
 }
 
@@ -994,13 +1004,44 @@ void Engine::TrainInit(int worker_id, Context ctx) {  // dist_engine.cc:366-465
   extractor_.reset(new Extractor(dataset_.get(), ctx, rc.UseGPUCache() ? ring_->ranking() : nullptr, nullptr, 0,
                                  partition ? worker_id : 0, partition ? T : 1, ring_));
   Profiler::Get().LogInit(kLogInitL2BuildCache, tc.Passed());
+  if (ring_->devq_enabled) {
+    const uint32_t Tq = ring_->devq_trainers;
+    FCHECK_LT((uint32_t)worker_id, Tq);
+    const uint32_t mine = ring_->num_slots > (uint32_t)worker_id ? (ring_->num_slots - worker_id + Tq - 1) / Tq : 0;
+    devq_base_.assign(Tq, nullptr);
+    FGNN_CALL(fgnn_k_shard_alloc((void **)&devq_base_[worker_id], std::max<size_t>(mine, 1) * ring_->slot_bytes));
+    FGNN_CALL(fgnn_k_ipc_export(devq_base_[worker_id], ring_->devq_handle[worker_id]));
+    devq_own_ = worker_id;
+    ring_->devq_ready[worker_id].store(1, std::memory_order_release);
+  }
   // steps this trainer consumes: step % T == worker_id (train_graphsage.py:298)
   num_local_step_ = num_step_ / T + ((size_t)worker_id < num_step_ % T ? 1 : 0);
   Profiler::Get().LogInit(kLogInitL1Trainer, t0.Passed());
   initialized_ = true;
 }
 
-// ---- arch5 transport: Task <-> record in a pinned shared slot (task_queue.cc:154-347) ----
+// Payload address of ring slot `idx` in trainer HBM; maps the owning trainer's part of the device ring on first
+// use (CUDA IPC, peer access enabled lazily: copies to/from it travel over NVLink, or stay inside the GPU when
+// sampler and trainer share one).
+char *Engine::DevSlot(uint64_t idx) {
+  const uint32_t Tq = ring_->devq_trainers;
+  if (devq_base_.empty()) devq_base_.assign(Tq, nullptr);
+  const uint64_t s = idx % ring_->num_slots;
+  const uint32_t t = (uint32_t)(s % Tq);
+  if (!devq_base_[t]) {
+    while (ring_->devq_ready[t].load(std::memory_order_acquire) == 0) {
+      if (stop_) return nullptr;
+      std::this_thread::sleep_for(std::chrono::microseconds(50));
+    }
+    void *p = nullptr;
+    FGNN_CALL(fgnn_k_ipc_open(ring_->devq_handle[t], &p));
+    devq_base_[t] = (char *)p;
+  }
+  return devq_base_[t] + (s / Tq) * ring_->slot_bytes;
+}
+
+// ---- arch5 transport: Task <-> record in a queue slot (task_queue.cc:154-347).  Header in pinned shared host
+// memory; payload either next to it (host bounce, the reference's path) or in the trainers' HBM (device queue). ----
 void Engine::SendTask(const TaskPtr &t) {
   Timer ts;
   sem_wait(&ring_->free_slots);
@@ -1020,12 +1061,17 @@ void Engine::SendTask(const TaskPtr &t) {
   h->key = t->key;
   h->input_size = t->input_nodes->NumItems();
   h->output_size = t->output_nodes->NumItems();
-  char *p = slot + ((sizeof(SlotHeader) + 255) & ~(size_t)255);
+  const size_t hdr_bytes = (sizeof(SlotHeader) + 255) & ~(size_t)255;
+  char *const payload = ring_->devq_enabled ? DevSlot(idx) : slot;
+  if (!payload) return;  // shutting down
+  char *p = payload + hdr_bytes;
+  double sent_bytes = 0;
   auto put = [&](const TensorPtr &x) {
     if (!x) return;
-    FCHECK_LE((size_t)(p - slot) + x->nbytes, (size_t)ring_->slot_bytes) << "task exceeds the queue slot";
-    CUDA_CALL(cudaMemcpyAsync(p, x->data, x->nbytes, cudaMemcpyDeviceToHost, st));
+    FCHECK_LE((size_t)(p - payload) + x->nbytes, (size_t)ring_->slot_bytes) << "task exceeds the queue slot";
+    CUDA_CALL(cudaMemcpyAsync(p, x->data, x->nbytes, cudaMemcpyDefault, st));  // D2H, or D2D into the trainer's HBM
     p += (x->nbytes + 255) & ~(size_t)255;
+    sent_bytes += (double)x->nbytes;
   };
   put(t->input_nodes);
   put(t->output_nodes);
@@ -1040,6 +1086,7 @@ void Engine::SendTask(const TaskPtr &t) {
   CUDA_CALL(cudaStreamSynchronize(st));
   h->ready.store(1, std::memory_order_release);
   sem_post(&ring_->used_slots);
+  (void)sent_bytes;
   Profiler::Get().LogStep(t->key, kLogL1SendTime, ts.Passed());
   Profiler::Get().LogEpochAdd(t->key, kLogEpochSampleSendTime, ts.Passed());
 }
@@ -1061,10 +1108,12 @@ TaskPtr Engine::RecvTask(bool block) {
   CUDA_CALL(cudaSetDevice(dev));
   auto task = std::make_shared<Task>();
   task->key = h->key;
-  const char *p = slot + ((sizeof(SlotHeader) + 255) & ~(size_t)255);
+  const char *payload = ring_->devq_enabled ? DevSlot(idx) : slot;
+  if (!payload) return nullptr;
+  const char *p = payload + ((sizeof(SlotHeader) + 255) & ~(size_t)255);
   auto get = [&](size_t n, const char *name) {
     auto t = Tensor::Device(kI32, {n}, dev, st, name);
-    CUDA_CALL(cudaMemcpyAsync(t->data, p, n * 4, cudaMemcpyHostToDevice, st));
+    CUDA_CALL(cudaMemcpyAsync(t->data, p, n * 4, cudaMemcpyDefault, st));  // H2D, or D2D out of the device ring
     p += (n * 4 + 255) & ~(size_t)255;
     return t;
   };
@@ -1258,6 +1307,10 @@ void Engine::Shutdown() {
   inflight_.clear();
   x_inflight_.clear();
   if (extractor_) { cudaSetDevice(extractor_->device()); cudaStreamSynchronize(extractor_->stream()); }
+  for (int t = 0; t < (int)devq_base_.size(); ++t)
+    if (devq_base_[t] && t != devq_own_) { fgnn_k_ipc_close(devq_base_[t]); devq_base_[t] = nullptr; }
+  // the own part of the device ring is left to process exit: a sampler may still be copying into it
+  cudaGetLastError();
 }
 
 }  // namespace rt

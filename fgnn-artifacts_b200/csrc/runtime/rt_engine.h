@@ -87,6 +87,7 @@ class Engine {
   void SendTask(const TaskPtr &t);
   void DoPreSample();
   void CreateSharedState();
+  char *DevSlot(uint64_t idx);
 
   bool initialized_ = false;
   std::atomic<bool> stop_{false};
@@ -110,6 +111,8 @@ class Engine {
   std::atomic<uint64_t> outer_counter_{0};
 
   SharedRing *ring_ = nullptr;  // arch5
+  std::vector<char *> devq_base_;  // device queue: base of every trainer's part of the ring (own or IPC-mapped)
+  int devq_own_ = -1;
   void *shared_base_ = nullptr;
   size_t shared_bytes_ = 0;
 };

@@ -139,9 +139,11 @@ class HotPath:
         K.freq_count(freq, sl.n2o, self.max_nodes, sl.num_items)
 
     def build_cache(self, ranking_nodes, cache_percentage, feat_src, row_bytes, feat_mask=0xFFFFFFFFFFFFFFFF,
-                    num_shards=1, shard_id=0, peer_ptrs=None):
+                    num_shards=1, shard_id=0, peer_ptrs=None, fill_local=True):
         """GPUCacheManager / DistCacheManager ctor (cuda_cache_manager_host.cc:60-127): node->slot table and
-        the cached rows.  With num_shards > 1 only rows slot % num_shards == shard_id are stored locally."""
+        the cached rows.  With num_shards > 1 only rows slot % num_shards == shard_id are stored locally;
+        `peer_ptrs` then lists the base pointer of every shard (own + NVLink peer mappings, see
+        fgnn_b200/partition.py) and, with fill_local=False, the caller has already filled its own shard."""
         V = self.num_nodes
         self.row_bytes = row_bytes
         self.num_cached = int(V * cache_percentage)
@@ -149,15 +151,20 @@ class HotPath:
         K.cache_table_build(self.cache_table, V, ranking_nodes, self.num_cached)
         self.num_shards = num_shards
         local_rows = (self.num_cached - shard_id + num_shards - 1) // num_shards if self.num_cached > shard_id else 0
-        self.cache = torch.empty((max(1, local_rows), row_bytes), dtype=torch.uint8, device=self.dev)
-        if local_rows:
-            idx = ranking_nodes[shard_id:self.num_cached:num_shards].contiguous()
-            K.row_copy(self.cache, None, feat_src, idx, local_rows, None, row_bytes, feat_mask)
+        self.cache = None
+        if fill_local:
+            self.cache = torch.empty((max(1, local_rows), row_bytes), dtype=torch.uint8, device=self.dev)
+            if local_rows:
+                idx = ranking_nodes[shard_id:self.num_cached:num_shards].contiguous()
+                K.row_copy(self.cache, None, feat_src, idx, local_rows, None, row_bytes, feat_mask)
         self.miss_src, self.miss_mask = feat_src, feat_mask
         if peer_ptrs is None:
+            assert fill_local and num_shards == 1
             peer_ptrs = [self.cache.data_ptr()]
+        assert len(peer_ptrs) == num_shards
         self.shard_ptrs = torch.tensor(peer_ptrs, dtype=torch.int64, device=self.dev)
-        self.feat_out = torch.empty((self.max_nodes, row_bytes), dtype=torch.uint8, device=self.dev)
+        if self.feat_out is None:
+            self.feat_out = torch.empty((self.max_nodes, row_bytes), dtype=torch.uint8, device=self.dev)
         return local_rows
 
     def set_labels(self, label_src):

@@ -23,6 +23,7 @@ def _free_port():
 
 def _worker(rank, world, port, ret):
     sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "fgnn-artifacts_b200"))
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     dist.init_process_group("gloo", rank=rank, world_size=world)
     import bench
@@ -31,7 +32,15 @@ def _worker(rank, world, port, ret):
     gathered = [None] * world
     dist.all_gather_object(gathered, mine)
     ms, edges = bench.aggregate(10.0 + rank, 1000 * (rank + 1), device="cpu")
-    ret[rank] = (gathered, ms, edges)
+    # partitioned-cache init plumbing (fgnn_b200/partition.py): PreSC counters summed, ranking broadcast from
+    # rank 0, one opaque 64-byte IPC handle per rank all-gathered in rank order
+    from fgnn_b200 import partition as P
+    freq = torch.arange(16, dtype=torch.int32) * (rank + 1)
+    P.allreduce_freq(freq)
+    ranking = torch.arange(16, dtype=torch.int32).flip(0) if rank == 0 else torch.zeros(16, dtype=torch.int32)
+    P.broadcast_ranking(ranking, src=0)
+    handles = P.exchange_handles(bytes([rank + 1] * 64), "cpu")
+    ret[rank] = (gathered, ms, edges, freq.tolist(), ranking.tolist(), handles)
     dist.destroy_process_group()
 
 
@@ -42,7 +51,25 @@ def test_rank_sharding_and_aggregation_world2():
     ret = mgr.dict()
     mp.spawn(_worker, args=(world, port, ret), nprocs=world, join=True)
     for rank in range(world):
-        gathered, ms, edges = ret[rank]
+        gathered, ms, edges, freq, ranking, handles = ret[rank]
+        assert freq == [3 * i for i in range(16)]
+        assert ranking == list(range(15, -1, -1))
+        assert handles == [bytes([r + 1] * 64) for r in range(world)]
         flat = [s for g in gathered for s in g]
         assert len(set(flat)) == len(flat), "ranks must work on disjoint mini-batches"
         assert ms == 11.0 and edges == 3000          # max over ranks, sum over ranks
+
+
+def test_cache_striping_covers_every_slot_once():
+    sys.path.insert(0, os.path.join(ROOT, "fgnn-artifacts_b200"))
+    from fgnn_b200 import partition as P
+    for num_cached in (0, 1, 7, 64, 1001):
+        for T in (1, 2, 3, 8):
+            rows = [P.stripe_rows(num_cached, T, t) for t in range(T)]
+            assert sum(rows) == num_cached
+            seen = set()
+            for s in range(num_cached):
+                o, r = P.slot_owner(s, T)
+                assert 0 <= o < T and r < rows[o]
+                seen.add((o, r))
+            assert len(seen) == num_cached

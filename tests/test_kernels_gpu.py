@@ -335,7 +335,7 @@ def test_gather_cached_matches_reference_pipeline(K, oracle, num_shards, dim, pc
     assert stats.tolist() == [len(cs), len(ms)]
 
 
-@pytest.mark.parametrize("impl", ["bulk", "group", "flat"])
+@pytest.mark.parametrize("impl", ["bulk", "dyn", "group", "flat"])
 @pytest.mark.parametrize("row_bytes,n,n_max,pct,shards", [
     (512, 0, 64, 0.5, 1), (512, 1, 1, 0.5, 1), (512, 3, 3, 1.0, 1), (512, 33, 40, 0.0, 1),
     (512, 70001, 70001, 0.9, 1), (512, 70001, 90000, 1.0, 3), (400, 12345, 12345, 0.7, 2),

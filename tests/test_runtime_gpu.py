@@ -48,6 +48,7 @@ def run_driver(tmp_path, scenario):
     out = os.path.join(str(tmp_path), "out.npz")
     json.dump(scenario, open(sc_path, "w"))
     env = dict(os.environ, SAMGRAPH_LOG_LEVEL="warn")
+    env.update(scenario.get("env", {}))
     r = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "runtime_driver.py"), sc_path, out],
                        capture_output=True, text=True, timeout=600, env=env)
     assert r.returncode == 0, "driver failed:\n%s\n%s" % (r.stdout[-3000:], r.stderr[-3000:])
@@ -114,14 +115,16 @@ def test_arch1_all_features_resident(tmp_path, oracle, dataset):
     assert all(float(data["miss/%d" % int(k)]) == 0.0 for k in data["keys"])
 
 
-@pytest.mark.parametrize("S,T", [(1, 1), (2, 2)])
-def test_arch5_forked_sampler_and_trainer_processes(tmp_path, oracle, dataset, S, T):
+@pytest.mark.parametrize("S,T,nvlink_queue", [(1, 1, 1), (2, 2, 1), (1, 2, 0)])
+def test_arch5_forked_sampler_and_trainer_processes(tmp_path, oracle, dataset, S, T, nvlink_queue):
     """Factored mode on one GPU (the scripts' --single-gpu placement): sampler and trainer processes forked
-    after data_init, tasks through the pinned shared-memory queue, cache partitioned over the T trainers
-    (CUDA IPC peer mappings)."""
+    after data_init, cache partitioned over the T trainers (CUDA IPC peer mappings).  Tasks travel through the
+    device queue (payload slots in trainer HBM written by the samplers through IPC mappings) or,
+    with SAMGRAPH_NVLINK_QUEUE=0, through the reference's pinned shared-memory bounce."""
     cfg = base_config(dataset["path"], arch="arch5", cache=0.4)
     cfg.update(num_sample_worker=S, num_train_worker=T)
-    sc = {"mode": "arch5", "config": cfg, "sample_devices": ["cuda:0"] * S, "train_devices": ["cuda:0"] * T}
+    sc = {"mode": "arch5", "config": cfg, "sample_devices": ["cuda:0"] * S, "train_devices": ["cuda:0"] * T,
+          "env": {"SAMGRAPH_NVLINK_QUEUE": str(nvlink_queue)}}
     out = run_driver(tmp_path, sc)
     meta = np.load(out)
     assert int(meta["bad"]) == 0

@@ -22,6 +22,8 @@ def main():
     ap.add_argument("--workload", default="papers100M")
     ap.add_argument("--empty-feat", type=int, default=22)
     ap.add_argument("--cache-pct", type=float, default=0.3)
+    ap.add_argument("--sweep", default="fuse", choices=["fuse", "overlap"],
+                    help="fuse: kernel-fusion variants; overlap: how the sampling slots and the gather share the GPU\n                    (FGNN_GRID_DIV, gather implementation / CTA shape)")
     a = ap.parse_args()
     import torch
     import bench
@@ -35,7 +37,7 @@ def main():
     BATCH, FANOUTS = bench.BATCH, bench.FANOUTS
     spe = (wl["T"] + BATCH - 1) // BATCH
     perm = wl["train"]
-    SL = 4
+    SL = 6
     hp = HotPath(wl["indptr"], wl["indices"], V, FANOUTS, BATCH, "khop2", seed=1, device=dev, num_slots=SL)
     rank = torch.randperm(V, device=dev).to(torch.int32)
     hp.build_cache(rank, a.cache_pct, wl["host_feat"], D * 4, wl["feat_mask"])
@@ -81,6 +83,39 @@ def main():
         return e0.elapsed_time(e1) / steps * 1e3
 
     os.environ["FGNN_TUNING_DYNAMIC"] = "1"
+    if a.sweep == "overlap":
+        base = {"FGNN_GRID_DIV": "1", "FGNN_GATHER_IMPL": "bulk", "FGNN_BULK_WARPS": "8", "FGNN_BULK_STAGES": "8",
+                "FGNN_GATHER_CTAS_PER_SM": "0"}
+        variants = [{}, {"FGNN_GRID_DIV": "2"}, {"FGNN_GRID_DIV": "3"}, {"FGNN_GRID_DIV": "4"},
+                    {"FGNN_GATHER_IMPL": "dyn"}, {"FGNN_GATHER_IMPL": "dyn", "FGNN_GRID_DIV": "2"},
+                    {"FGNN_GATHER_IMPL": "dyn", "FGNN_GRID_DIV": "3"},
+                    {"FGNN_GATHER_IMPL": "dyn", "FGNN_BULK_WARPS": "4", "FGNN_GATHER_CTAS_PER_SM": "2"},
+                    {"FGNN_GATHER_IMPL": "dyn", "FGNN_BULK_WARPS": "4", "FGNN_GATHER_CTAS_PER_SM": "2", "FGNN_GRID_DIV": "2"},
+                    {"FGNN_GATHER_IMPL": "dyn", "FGNN_BULK_WARPS": "16", "FGNN_BULK_STAGES": "6"},
+                    {"FGNN_BULK_WARPS": "4", "FGNN_GATHER_CTAS_PER_SM": "2", "FGNN_GRID_DIV": "2"}]
+        for var in variants:
+            env = dict(base, **var)
+            os.environ.update(env)
+            res = dict(var)
+            run(1, False, 10)
+            res["sample_only_us_slots1"] = round(run(1, False, a.steps), 1)
+            res["sample_only_us_slots3"] = round(run(3, False, a.steps), 1)
+            for slots in (2, 3, 4, 6):
+                run(slots, True, 10)
+                res["with_gather_us_slots%d" % slots] = round(run(slots, True, a.steps), 1)
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            for k in range(5):
+                hp.gather(0)
+            e0.record()
+            for k in range(50):
+                hp.gather(0)
+            e1.record()
+            torch.cuda.synchronize()
+            res["gather_alone_us"] = round(e0.elapsed_time(e1) / 50 * 1e3, 1)
+            print("OVERLAP_JSON " + json.dumps(res))
+            sys.stdout.flush()
+        return
     for fuse, hint in ((0, 0), (0, 1), (2, 0), (2, 1), (3, 1)):
         os.environ["FGNN_BATCH_FUSE"] = str(fuse)
         os.environ["FGNN_GATHER_L2HINT"] = str(hint)
