@@ -21,8 +21,8 @@ int sm_count() {
 }
 int grid_share_div() {
   static int d = 0;
-  static const bool dynamic = getenv("FGNN_TUNING_DYNAMIC") && atoi(getenv("FGNN_TUNING_DYNAMIC")) != 0;
-  if (d == 0 || dynamic) {
+  const char *dyn = getenv("FGNN_TUNING_DYNAMIC");  // sweeps: re-read per call
+  if (d == 0 || (dyn && atoi(dyn) != 0)) {
     const char *v = getenv("FGNN_GRID_DIV");
     d = v && *v ? atoi(v) : 1;
     if (d < 1) d = 1;

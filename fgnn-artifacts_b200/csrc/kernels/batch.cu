@@ -29,6 +29,8 @@ extern "C" int fgnn_k_sample_batch(const fgnn_sample_plan *pl, const fgnn_sample
   // A/B switch for profiling: bit 0 = samplers insert their picks while gathering them (measured SLOWER on
   // B200, r1_n: 177 vs 145 us per batch — the smem-limited sampler CTAs have too few threads to hide the
   // table's L2 latency — so it is off), bit 1 = remap folded into the compaction pass (on)
+  // bit 2 = khop2 writes a padded [seed][fanout] block and ONE chained scan (in the unique/remap pass) compacts
+  // the edges and numbers the new ids (3 launches per layer, one look-back chain instead of two)
   const char *fz = getenv("FGNN_BATCH_FUSE");
   const int fuse = fz && *fz ? atoi(fz) : 2;
 
@@ -48,6 +50,16 @@ extern "C" int fgnn_k_sample_batch(const fgnn_sample_plan *pl, const fgnn_sample
     fgnn_rng rng{pl->seed, batch_key, (uint32_t)i};
     uint32_t *dst = pl->dst[i], *col = out->col[i];
     bool inserted = false;
+    if (pl->sample_type == 5 && (fuse & 4)) {
+      rc = sample_khop2_pad_launch(pl->indptr, pl->indices, out->n2o, nmax, n_in, f, rng, dst, st);
+      if (rc) return rc;
+      rc = ht_insert_launch(pl->table, pl->capacity, dst, emax, n_in, pl->pos[i], st, f);
+      if (rc) return rc;
+      rc = ht_compact_pad_launch(pl->table, dst, nmax, n_in, f, pl->pos[i], out->n2o, pl->num_items, out->row[i],
+                                 col, n_edge, n_src, n_in_next, pl->chain_ws, st);
+      if (rc) return rc;
+      continue;
+    }
     switch (pl->sample_type) {  // cuda_loops.cc:118-161
       case 0:
       case 5: {

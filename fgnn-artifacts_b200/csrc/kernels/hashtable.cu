@@ -58,8 +58,10 @@ constexpr int kInsIlp = 4;
 // whenever the snapshot already shows a smaller owner index / an assigned id.
 __global__ void __launch_bounds__(kBlock)
 ht_insert_kernel(Bucket *table, uint32_t mask, const uint32_t *__restrict__ input,
-                 uint32_t n_max, const uint32_t *__restrict__ d_n, uint32_t *__restrict__ pos_out) {
-  const uint32_t n = load_count(n_max, d_n);
+                 uint32_t n_max, const uint32_t *__restrict__ d_n, uint32_t mult,
+                 uint32_t *__restrict__ pos_out) {
+  // mult > 1: `input` is a padded [seed][mult] block (EMPTY = hole) and *d_n counts seeds
+  const uint32_t n = mult > 1 ? load_count(n_max / mult, d_n) * mult : load_count(n_max, d_n);
   const uint32_t stride = gridDim.x * kBlock;
   for (uint32_t i0 = blockIdx.x * kBlock + threadIdx.x; i0 < n; i0 += stride * kInsIlp) {
     uint32_t id[kInsIlp], pos[kInsIlp];
@@ -72,11 +74,11 @@ ht_insert_kernel(Bucket *table, uint32_t mask, const uint32_t *__restrict__ inpu
     }
 #pragma unroll
     for (int u = 0; u < kInsIlp; ++u)
-      if (i0 + u * stride < n) b[u] = load_bucket(table + pos[u]);
+      if (id[u] != kEmpty) b[u] = load_bucket(table + pos[u]);
 #pragma unroll
     for (int u = 0; u < kInsIlp; ++u) {
       const uint32_t i = i0 + u * stride;
-      if (i < n) {
+      if (id[u] != kEmpty) {  // in range and not a hole
         pos_out[i] = insert_item(table, mask, id[u], i, pos[u], b[u]);
       }
     }
@@ -215,6 +217,139 @@ ht_compact_kernel(Bucket *table, const uint32_t *__restrict__ input, uint32_t n_
   }
 }
 
+// FillWithDuplicates (second half) + compact_edge + GPUMapEdges for a PADDED sampler output
+// (sample_khop2_pad_kernel): item i = seed i / fanout, pick i % fanout, EMPTY = hole.  ONE chained scan carries
+// both running counts, packed {valid edges : 31 | new ids : 31}; per valid item the kernel writes the compact COO
+//   col[e] = i / fanout            (the seed's local id: seeds are the first entries of the unique list)
+//   row[e] = local id of dst[i]    (owners first, then everyone reads its bucket; see ht_compact_kernel)
+// in seed-major order, exactly what sample + count_edge + compact_edge + FillWithDuplicates + MapEdges of the
+// reference produce (cuda_sampling_khop2.cu:121-175, cuda_hashtable.cu:725-807, cuda_mapping.cu:68-81).
+__global__ void __launch_bounds__(kBlock)
+ht_compact_pad_kernel(Bucket *table, const uint32_t *__restrict__ dst, uint32_t n_seed_max,
+                      const uint32_t *__restrict__ d_n_seed, uint32_t fanout,
+                      const uint32_t *__restrict__ pos, uint32_t *__restrict__ n2o, uint32_t *d_num_items,
+                      uint32_t *__restrict__ out_row, uint32_t *__restrict__ out_col, uint32_t *count_edge,
+                      uint32_t *count_src, uint32_t *count_next, ChainWs *ws) {
+  __shared__ CompactSmem sm;
+  const uint32_t n = load_count(n_seed_max, d_n_seed) * fanout;
+  const uint32_t p = chain_ticket(ws, &sm.chain);
+  uint32_t begin, end;
+  chunk_range(n, p, gridDim.x, kBlock, &begin, &end);
+  const uint32_t items0 = *d_num_items;  // stable: only the last finisher updates it, at the end
+
+  constexpr int kCache = 4;  // a chunk is <= 4 tiles up to ~0.9 M items on a full grid
+  uint32_t bpr[kCache], wr[kCache], idr[kCache];
+  unsigned long long partial = 0;
+#pragma unroll
+  for (int it = 0; it < kCache; ++it) {
+    const uint32_t i = begin + it * kBlock + threadIdx.x;
+    bpr[it] = 0;
+    wr[it] = 0;
+    idr[it] = kEmpty;
+    if (i < end) idr[it] = __ldg(dst + i);
+    if (idr[it] != kEmpty) bpr[it] = pos[i];
+  }
+#pragma unroll
+  for (int it = 0; it < kCache; ++it) {
+    const uint32_t i = begin + it * kBlock + threadIdx.x;
+    if (idr[it] != kEmpty) {
+      wr[it] = table[bpr[it]].local;
+      partial += (1ull << 31) + ((wr[it] == (kPending | i)) ? 1ull : 0ull);
+    }
+  }
+  for (uint32_t i = begin + kCache * kBlock + threadIdx.x; i < end; i += kBlock) {
+    if (__ldg(dst + i) != kEmpty)
+      partial += (1ull << 31) + ((table[pos[i]].local == (kPending | i)) ? 1ull : 0ull);
+  }
+  unsigned long long chunk_total;
+  const unsigned long long base = chain_scan(ws, &sm.chain, p, partial, &chunk_total);
+  uint32_t base_edge = (uint32_t)(base >> 31), base_new = (uint32_t)(base & 0x7FFFFFFFull);
+
+  uint32_t eoff[kCache];
+#pragma unroll
+  for (int it = 0; it < kCache; ++it) {
+    const uint32_t t0 = begin + it * kBlock;
+    eoff[it] = 0;
+    if (t0 < end) {  // uniform across the CTA
+      const uint32_t i = t0 + threadIdx.x;
+      const uint32_t valid = idr[it] != kEmpty ? 1u : 0u;
+      const uint32_t isnew = (valid && wr[it] == (kPending | i)) ? 1u : 0u;
+      uint32_t tile_total;
+      const uint32_t excl = block_excl_scan((valid << 16) | isnew, sm.warp, &tile_total);
+      if (isnew) {
+        const uint32_t local = items0 + base_new + (excl & 0xFFFFu);
+        table[bpr[it]].local = local;
+        n2o[local] = idr[it];
+        wr[it] = local;
+      }
+      eoff[it] = base_edge + (excl >> 16);
+      if (valid) out_col[eoff[it]] = i / fanout;
+      base_edge += tile_total >> 16;
+      base_new += tile_total & 0xFFFFu;
+    }
+  }
+  for (uint32_t t0 = begin + kCache * kBlock; t0 < end; t0 += kBlock) {  // long chunks: tile by tile
+    const uint32_t i = t0 + threadIdx.x;
+    uint32_t valid = 0, isnew = 0, bp = 0, w = 0, id = kEmpty;
+    if (i < end) id = __ldg(dst + i);
+    if (id != kEmpty) {
+      valid = 1;
+      bp = pos[i];
+      w = table[bp].local;
+      isnew = (w == (kPending | i)) ? 1u : 0u;
+    }
+    uint32_t tile_total;
+    const uint32_t excl = block_excl_scan((valid << 16) | isnew, sm.warp, &tile_total);
+    if (isnew) {
+      w = items0 + base_new + (excl & 0xFFFFu);
+      table[bp].local = w;
+      n2o[w] = id;
+    }
+    const uint32_t e = base_edge + (excl >> 16);
+    base_edge += tile_total >> 16;
+    base_new += tile_total & 0xFFFFu;
+    __syncthreads();  // owners of this tile are written
+    if (valid) {
+      out_col[e] = i / fanout;
+      out_row[e] = (w & kPending) ? wait_local(table, bp) : w;
+    }
+  }
+  __syncthreads();  // this CTA's owners are all assigned and visible
+#pragma unroll
+  for (int it = 0; it < kCache; ++it)
+    if (idr[it] != kEmpty) out_row[eoff[it]] = (wr[it] & kPending) ? wait_local(table, bpr[it]) : wr[it];
+
+  // totals travel through the pad words; the CTA that finishes LAST publishes them (every other CTA has
+  // read items0 by then) and re-arms the workspace
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    if (p == gridDim.x - 1) {
+      ws->pad[0] = base_new;
+      ws->pad[1] = base_edge;
+    }
+    __threadfence();
+    const unsigned int prev = atomicAdd(&ws->done, 1u);
+    sm.chain.last = (prev == gridDim.x - 1) ? 1u : 0u;
+  }
+  __syncthreads();
+  if (sm.chain.last) {
+    for (uint32_t t = threadIdx.x; t < gridDim.x; t += kBlock) ws->agg[t] = 0ull;
+    if (threadIdx.x == 0) {
+      __threadfence();
+      const uint32_t total = items0 + *((volatile unsigned int *)&ws->pad[0]);
+      const uint32_t edges = *((volatile unsigned int *)&ws->pad[1]);
+      *d_num_items = total;
+      if (count_edge) *count_edge = edges;
+      if (count_src) *count_src = total;
+      if (count_next) *count_next = total;
+      ws->pad[0] = 0u;
+      ws->pad[1] = 0u;
+      ws->ticket = 0u;
+      ws->done = 0u;
+    }
+  }
+}
+
 // FillWithUnique into an empty table (first fill of a batch): local id = index, count = n
 __global__ void __launch_bounds__(kBlock)
 ht_fill_unique_first_kernel(Bucket *table, uint32_t mask, const uint32_t *__restrict__ input,
@@ -260,10 +395,11 @@ ht_map_kernel(const Bucket *__restrict__ table, uint32_t mask, const uint32_t *_
 }  // namespace
 
 int ht_insert_launch(void *table, size_t capacity, const uint32_t *input, uint32_t n_max,
-                     const uint32_t *d_n, uint32_t *pos, cudaStream_t st) {
+                     const uint32_t *d_n, uint32_t *pos, cudaStream_t st, uint32_t mult) {
   static const int occ1 = occupancy(ht_insert_kernel, kBlock, 0);
   const int grid1 = persistent_grid(n_max, kBlock * kInsIlp, occ1, false);
-  ht_insert_kernel<<<grid1, kBlock, 0, st>>>((Bucket *)table, (uint32_t)(capacity - 1), input, n_max, d_n, pos);
+  ht_insert_kernel<<<grid1, kBlock, 0, st>>>((Bucket *)table, (uint32_t)(capacity - 1), input, n_max, d_n,
+                                            mult ? mult : 1u, pos);
   note_launch();
   return check_last();
 }
@@ -277,6 +413,19 @@ int ht_compact_launch(void *table, size_t capacity, const uint32_t *input, uint3
   const int grid2 = persistent_grid(n_max, kBlock, occ2, true);
   ht_compact_kernel<<<grid2, kBlock, 0, st>>>((Bucket *)table, input, n_max, d_n, pos, n2o, d_num_items,
                                              out_local, count_copy, count_copy2, (ChainWs *)chain_ws);
+  note_launch();
+  return check_last();
+}
+
+int ht_compact_pad_launch(void *table, const uint32_t *dst, uint32_t n_seed_max, const uint32_t *d_n_seed,
+                          uint32_t fanout, const uint32_t *pos, uint32_t *n2o, uint32_t *d_num_items,
+                          uint32_t *out_row, uint32_t *out_col, uint32_t *count_edge, uint32_t *count_src,
+                          uint32_t *count_next, void *chain_ws, cudaStream_t st) {
+  static const int occ = occupancy(ht_compact_pad_kernel, kBlock, 0);
+  const int grid = persistent_grid((uint64_t)n_seed_max * fanout, kBlock, occ, true);
+  ht_compact_pad_kernel<<<grid, kBlock, 0, st>>>((Bucket *)table, dst, n_seed_max, d_n_seed, fanout, pos, n2o,
+                                                 d_num_items, out_row, out_col, count_edge, count_src,
+                                                 count_next, (ChainWs *)chain_ws);
   note_launch();
   return check_last();
 }
@@ -344,7 +493,7 @@ extern "C" int fgnn_k_ht_fill_duplicates(void *table, size_t capacity, const uin
   if (int rc = check_fill_args(table, capacity, input, n_max, pos, n2o, d_num_items, chain_ws)) return rc;
   if (n_max == 0) return 0;
   cudaStream_t st = (cudaStream_t)stream;
-  if (int rc = ht_insert_launch(table, capacity, input, n_max, d_n, pos, st)) return rc;
+  if (int rc = ht_insert_launch(table, capacity, input, n_max, d_n, pos, st, 1)) return rc;
   return ht_compact_launch(table, capacity, input, n_max, d_n, pos, n2o, d_num_items, nullptr, nullptr,
                            nullptr, chain_ws, st);
 }
@@ -357,7 +506,7 @@ extern "C" int fgnn_k_ht_fill_duplicates_map(void *table, size_t capacity, const
   if (n_max == 0) return 0;
   if (!out_local) return FGNN_ERR_BAD_ARG;
   cudaStream_t st = (cudaStream_t)stream;
-  if (int rc = ht_insert_launch(table, capacity, input, n_max, d_n, pos, st)) return rc;
+  if (int rc = ht_insert_launch(table, capacity, input, n_max, d_n, pos, st, 1)) return rc;
   return ht_compact_launch(table, capacity, input, n_max, d_n, pos, n2o, d_num_items, out_local, nullptr,
                            nullptr, chain_ws, st);
 }

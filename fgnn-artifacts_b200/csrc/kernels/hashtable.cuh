@@ -69,8 +69,17 @@ int ht_compact_launch(void *table, size_t capacity, const uint32_t *input, uint3
                       const uint32_t *d_n, const uint32_t *pos, uint32_t *n2o, uint32_t *d_num_items,
                       uint32_t *out_local, uint32_t *count_copy, uint32_t *count_copy2, void *chain_ws,
                       cudaStream_t stream);
+// mult > 1: `input` is a padded [seed][mult] block with EMPTY holes and *d_n counts seeds
 int ht_insert_launch(void *table, size_t capacity, const uint32_t *input, uint32_t n_max,
-                     const uint32_t *d_n, uint32_t *pos, cudaStream_t stream);
+                     const uint32_t *d_n, uint32_t *pos, cudaStream_t stream, uint32_t mult = 1);
+// padded k-hop sampling (no compaction) + the compaction pass that also assigns the new ids and remaps
+int sample_khop2_pad_launch(const uint32_t *indptr, const uint32_t *indices, const uint32_t *input,
+                            uint32_t n_max, const uint32_t *d_n, uint32_t fanout, fgnn_rng rng,
+                            uint32_t *out_dst_padded, cudaStream_t stream);
+int ht_compact_pad_launch(void *table, const uint32_t *dst, uint32_t n_seed_max, const uint32_t *d_n_seed,
+                          uint32_t fanout, const uint32_t *pos, uint32_t *n2o, uint32_t *d_num_items,
+                          uint32_t *out_row, uint32_t *out_col, uint32_t *count_edge, uint32_t *count_src,
+                          uint32_t *count_next, void *chain_ws, cudaStream_t stream);
 // FillWithUnique into an EMPTY table: base is 0 by construction, so the count needs no second kernel
 int ht_fill_unique_first_launch(void *table, size_t capacity, const uint32_t *input, uint32_t n_max,
                                 const uint32_t *d_n, uint32_t *n2o, uint32_t *d_num_items,

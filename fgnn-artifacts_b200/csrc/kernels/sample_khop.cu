@@ -362,6 +362,104 @@ int launch2(const uint32_t *indptr, const uint32_t *indices, const uint32_t *inp
   return check_last();
 }
 
+
+// ---------------------------------------------------------------------------
+// variant 2 inside fgnn_k_sample_batch: PADDED output, no compaction here.
+//
+// The kernel above spends most of its ~20-40 us on things that are not sampling: a first pass over the
+// seeds to count edges, the chunk-chained scan that turns the counts into output offsets (a chain of
+// dependent L2 round trips across up to 688 tickets), a block scan and a binary search per edge.  Inside
+// a mini-batch none of that is needed: the unique/remap pass that follows already runs ONE chained scan,
+// and it can carry the edge offsets next to the new-id offsets.  So here every seed simply owns `fanout`
+// output slots: dst[i*fanout + j] = j-th pick or EMPTY.  One thread per seed: three dependent loads
+// (id -> indptr pair -> up to `fanout` independent neighbour gathers), the same virtual Fisher-Yates and
+// Philox counters as sample_khop2_kernel (so the compacted result is bit-identical), and a coalesced
+// write of the tile through shared memory.  No scan, no ticket, no cross-CTA traffic.
+// ---------------------------------------------------------------------------
+template <int NT>
+__global__ void __launch_bounds__(NT)
+sample_khop2_pad_kernel(const uint32_t *__restrict__ indptr, const uint32_t *__restrict__ indices,
+                        const uint32_t *__restrict__ input, uint32_t n_max,
+                        const uint32_t *__restrict__ d_n, uint32_t fanout, RngKey key,
+                        uint32_t *__restrict__ out_dst) {
+  extern __shared__ uint32_t dyn[];
+  const uint32_t fs = fanout | 1u;            // odd row stride: conflict-free [seed][j]
+  uint32_t *s_choice = dyn;                   // [NT][fs]   positions, then the gathered ids
+  uint32_t *s_mkey = dyn + NT * fs;           // [fanout][NT]
+  uint32_t *s_mval = s_mkey + NT * fanout;    // [fanout][NT]
+  const uint32_t n = load_count(n_max, d_n);
+  const uint32_t tid = threadIdx.x;
+  for (uint32_t t0 = blockIdx.x * NT; t0 < n; t0 += gridDim.x * NT) {
+    const uint32_t i = t0 + tid;
+    uint32_t *choice = s_choice + tid * fs;
+    if (i < n) {
+      const uint32_t v = __ldg(input + i);
+      const uint32_t o = __ldg(indptr + v);
+      const uint32_t deg = __ldg(indptr + v + 1) - o;
+      uint32_t cnt = deg < fanout ? deg : fanout;
+      if (deg > fanout) {  // cuda_sampling_khop2.cu:72-83 on a virtual copy of the row
+        uint4 blk = make_uint4(0, 0, 0, 0);
+        for (uint32_t j = 0; j < fanout; ++j) {
+          if ((j & 3u) == 0) blk = philox_block(key, i, j >> 2);
+          const uint32_t k = pick_word(blk, j & 3u) % (deg - j);
+          const uint32_t last = deg - j - 1;
+          uint32_t vk = k, vlast = last;
+#pragma unroll 4
+          for (uint32_t t = 0; t < j; ++t) {  // latest write wins
+            const uint32_t kk = s_mkey[t * NT + tid];
+            const uint32_t vv = s_mval[t * NT + tid];
+            if (kk == k) vk = vv;
+            if (kk == last) vlast = vv;
+          }
+          s_mkey[j * NT + tid] = k;
+          s_mval[j * NT + tid] = vlast;
+          choice[j] = vk;
+        }
+      } else {
+        for (uint32_t j = 0; j < cnt; ++j) choice[j] = j;
+      }
+      // gather: 8 independent 4-byte loads in flight per thread
+      const uint32_t *row = indices + (size_t)o;
+      for (uint32_t j0 = 0; j0 < fanout; j0 += 8) {
+        uint32_t nb[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          const uint32_t j = j0 + u;
+          nb[u] = kEmpty;
+          if (j < cnt) nb[u] = __ldg(row + choice[j]);
+        }
+#pragma unroll
+        for (int u = 0; u < 8; ++u)
+          if (j0 + u < fanout) choice[j0 + u] = nb[u];
+      }
+    }
+    __syncthreads();
+    // the tile's padded block is contiguous: coalesced copy out of shared memory
+    const uint32_t rows = n - t0 < (uint32_t)NT ? n - t0 : (uint32_t)NT;
+    uint32_t *dst = out_dst + (size_t)t0 * fanout;
+    for (uint32_t e = tid; e < rows * fanout; e += NT) {
+      const uint32_t r = e / fanout;
+      dst[e] = s_choice[r * fs + (e - r * fanout)];
+    }
+    __syncthreads();
+  }
+}
+
+template <int NT>
+int launch2_pad(const uint32_t *indptr, const uint32_t *indices, const uint32_t *input, uint32_t n_max,
+                const uint32_t *d_n, uint32_t fanout, RngKey key, uint32_t *out_dst, cudaStream_t stream) {
+  const size_t smem = ((size_t)NT * (fanout | 1u) + 2 * (size_t)NT * fanout) * sizeof(uint32_t);
+  auto kern = sample_khop2_pad_kernel<NT>;
+  if (smem > 48 * 1024) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+  }
+  const int grid = persistent_grid(n_max, NT, occupancy(kern, NT, smem), false);
+  kern<<<grid, NT, smem, stream>>>(indptr, indices, input, n_max, d_n, fanout, key, out_dst);
+  note_launch();
+  return check_last();
+}
+
 template <int VARIANT, int NS>
 int launch(const uint32_t *indptr, const uint32_t *indices, const uint32_t *input,
            uint32_t n_max, const uint32_t *d_n, uint32_t fanout, RngKey key,
@@ -416,6 +514,21 @@ int sample_khop_launch(int variant, const uint32_t *indptr, const uint32_t *indi
   }
 #undef FGNN_GO
   return FGNN_ERR_BAD_ARG;
+}
+
+
+int sample_khop2_pad_launch(const uint32_t *indptr, const uint32_t *indices, const uint32_t *input,
+                            uint32_t n_max, const uint32_t *d_n, uint32_t fanout, fgnn_rng rng,
+                            uint32_t *out_dst_padded, cudaStream_t st) {
+  if (!indptr || !indices || !out_dst_padded) return FGNN_ERR_BAD_ARG;
+  if (n_max > 0 && !input) return FGNN_ERR_BAD_ARG;
+  if (fanout == 0 || fanout > 128) return FGNN_ERR_UNSUPPORTED;
+  if ((uint64_t)n_max * fanout > 0x7FFFFFFFull) return FGNN_ERR_UNSUPPORTED;
+  if (n_max == 0) return 0;
+  const RngKey key = make_rng_key(rng);
+  const bool small = (uint64_t)n_max <= (uint64_t)sm_count() * 128ull || fanout > 48;
+  if (small) return launch2_pad<64>(indptr, indices, input, n_max, d_n, fanout, key, out_dst_padded, st);
+  return launch2_pad<128>(indptr, indices, input, n_max, d_n, fanout, key, out_dst_padded, st);
 }
 
 }  // namespace fgnn

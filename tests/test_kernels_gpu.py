@@ -491,12 +491,21 @@ def test_random_walk_topk_matches_oracle(K, oracle, gs, n, W, L, Kn, p):
     ("khop2", [5, 10, 15], 2000), ("khop2", [25, 10], 777), ("khop0", [5, 10], 1500), ("khop1", [10, 5], 900),
     ("weighted_khop", [10, 5], 900), ("weighted_khop_prefix", [8, 4], 500), ("weighted_khop_hash_dedup", [6, 3], 400),
     ("random_walk", [5, 5, 5], 300), ("khop2", [3], 0), ("khop2", [4, 4], 1)])
-def test_sample_batch_call_matches_oracle_driver(K, oracle, gs, gm, sample_type, fanouts, n_seed):
+@pytest.mark.parametrize("fuse,grid_div", [(2, 1), (6, 1), (0, 1), (6, 16), (2, 16)])
+def test_sample_batch_call_matches_oracle_driver(K, oracle, gs, gm, sample_type, fanouts, n_seed, fuse, grid_div,
+                                                 monkeypatch):
     """fgnn_k_sample_batch (the one C call the engine makes per mini-batch: fused sample+insert and
     compact+remap, counts written by the kernels) against the numpy restatement of DoGPUSample
     (cuda_loops.cc:50-267), for every SampleType; two slots used alternately on two streams."""
     from fgnn_b200.pipeline import HotPath
     from oracle.oracle import sample_batch_oracle
+    if (fuse, grid_div) != (2, 1) and sample_type != "khop2":
+        pytest.skip("FGNN_BATCH_FUSE only changes the uniform k-hop kernel sequence")
+    # FGNN_GRID_DIV = 16 shrinks every persistent grid: chunks of the chained scans span many tiles
+    monkeypatch.setenv("FGNN_TUNING_DYNAMIC", "1")
+    monkeypatch.setenv("FGNN_GRID_DIV", str(grid_div))
+    # bit 1: remap folded into the compaction pass; bit 2: padded sampler + one dual-count chained scan
+    monkeypatch.setenv("FGNN_BATCH_FUSE", str(fuse))
     g = gm if sample_type in ("khop2", "khop0") else gs
     graph = dict(indptr=g.indptr_np, indices=g.indices_np)
     kw = {}
