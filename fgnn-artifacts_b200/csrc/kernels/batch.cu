@@ -30,9 +30,10 @@ extern "C" int fgnn_k_sample_batch(const fgnn_sample_plan *pl, const fgnn_sample
   // B200, r1_n: 177 vs 145 us per batch — the smem-limited sampler CTAs have too few threads to hide the
   // table's L2 latency — so it is off), bit 1 = remap folded into the compaction pass (on)
   // bit 2 = khop2 writes a padded [seed][fanout] block and ONE chained scan (in the unique/remap pass) compacts
-  // the edges and numbers the new ids (3 launches per layer, one look-back chain instead of two)
+  // the edges and numbers the new ids (3 launches per layer, one look-back chain instead of two; ncu r1_q c4/c7:
+  // sampler 18+39 us -> 10+24 us per batch; on)
   const char *fz = getenv("FGNN_BATCH_FUSE");
-  const int fuse = fz && *fz ? atoi(fz) : 2;
+  const int fuse = fz && *fz ? atoi(fz) : 6;
 
   // Reset (cuda_loops.cc:63) + FillWithUnique of the seeds (:67-69); the seed count doubles as the
   // input count of the first sampled layer

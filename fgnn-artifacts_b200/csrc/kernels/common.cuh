@@ -11,6 +11,10 @@ namespace fgnn {
 constexpr uint32_t kEmpty = 0xFFFFFFFFu;
 constexpr int kBlock = 256;          // threads per CTA for all tiled kernels
 constexpr int kMaxChainCtas = 4096;  // FGNN_CHAIN_WS_BYTES = 16 + 8*4096
+// Tickets up to which chain_scan sums the lower aggregates directly instead of looking back.  Measured on B200
+// (r1_q c5): with 688-888 tickets the direct sum is SLOWER than the look-back (ht_compact 24 -> 39 us: every
+// CTA polls all lower tickets), so it is only used for tiny grids where the look-back has nothing to amortise.
+constexpr unsigned kChainDirectMax = 32;
 
 // ---------------------------------------------------------------------------
 // launch bookkeeping
@@ -225,8 +229,27 @@ __device__ __forceinline__ unsigned long long chain_scan(
   const unsigned long long total = block_sum_u64<NT>(thread_partial, sm->warp64);
   if (threadIdx.x < 32) {
     const int lane = threadIdx.x;
-    if (lane == 0) st_relaxed_u64(&ws->agg[p], (p == 0 ? kPre : kAgg) | total);
     unsigned long long excl = 0;
+    if (gridDim.x <= kChainDirectMax) {
+      // Direct sum: every ticket publishes its aggregate right after its own first pass and nobody waits for a
+      // PREFIX, so the scan has no serial chain at all: warp 0 loads the (<= 1024) lower aggregates, 32 at a
+      // time, all independent.  The look-back below costs ~P/32 dependent L2 round trips (ncu r1_q: 20-25 us
+      // for the 688-888-ticket kernels of a GraphSAGE batch, most of their duration).
+      if (lane == 0) st_relaxed_u64(&ws->agg[p], kAgg | total);
+      unsigned long long c = 0;
+      for (int t = lane; t < (int)p; t += 32) {
+        unsigned long long v = ld_relaxed_u64(&ws->agg[t]);
+        while (!(v >> 62)) {
+          __nanosleep(64);
+          v = ld_relaxed_u64(&ws->agg[t]);
+        }
+        c += v & kVal;
+      }
+#pragma unroll
+      for (int d = 16; d > 0; d >>= 1) c += __shfl_down_sync(0xFFFFFFFFu, c, d);
+      excl = c;  // valid in lane 0
+    } else {
+    if (lane == 0) st_relaxed_u64(&ws->agg[p], (p == 0 ? kPre : kAgg) | total);
     if (p > 0) {
       int newest = (int)p - 1;  // window = tickets newest, newest-1, ..., newest-31 (lane order)
       while (true) {
@@ -249,6 +272,7 @@ __device__ __forceinline__ unsigned long long chain_scan(
         newest -= 32;
       }
       if (lane == 0) st_relaxed_u64(&ws->agg[p], kPre | ((excl + total) & kVal));
+    }
     }
     if (lane == 0) sm->excl = excl;
   }

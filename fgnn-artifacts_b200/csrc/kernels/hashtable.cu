@@ -179,10 +179,6 @@ ht_compact_kernel(Bucket *table, const uint32_t *__restrict__ input, uint32_t n_
       n2o[w] = __ldg(input + i);
     }
     base += tile_total;
-    if (out_local) {  // long chunks: remap tile by tile (owners of this tile are written above)
-      __syncthreads();
-      if (i < end) out_local[i] = (w & kPending) ? wait_local(table, bp) : w;
-    }
   }
   if (out_local) {
     __syncthreads();  // this CTA's owners are all assigned and visible
@@ -191,6 +187,10 @@ ht_compact_kernel(Bucket *table, const uint32_t *__restrict__ input, uint32_t n_
       const uint32_t i = begin + it * kBlock + threadIdx.x;
       if (i < end) out_local[i] = (wr[it] & kPending) ? wait_local(table, bpr[it]) : wr[it];
     }
+    // long chunks: second walk, only now may the CTA wait on lower tickets (waiting inside the loop above
+    // delayed this CTA's own owners and, through them, every higher ticket: ncu r1_q, 24 -> 156 us)
+    for (uint32_t i = begin + kCache * kBlock + threadIdx.x; i < end; i += kBlock)
+      out_local[i] = wait_local(table, pos[i]);
   }
   // the item counter is only advanced by the CTA that finishes LAST (every other CTA has read items0 by
   // then); the number of new ids = base at the end of the last chunk travels through the pad word
@@ -224,7 +224,7 @@ ht_compact_kernel(Bucket *table, const uint32_t *__restrict__ input, uint32_t n_
 //   row[e] = local id of dst[i]    (owners first, then everyone reads its bucket; see ht_compact_kernel)
 // in seed-major order, exactly what sample + count_edge + compact_edge + FillWithDuplicates + MapEdges of the
 // reference produce (cuda_sampling_khop2.cu:121-175, cuda_hashtable.cu:725-807, cuda_mapping.cu:68-81).
-__global__ void __launch_bounds__(kBlock)
+__global__ void __launch_bounds__(kBlock, 4)
 ht_compact_pad_kernel(Bucket *table, const uint32_t *__restrict__ dst, uint32_t n_seed_max,
                       const uint32_t *__restrict__ d_n_seed, uint32_t fanout,
                       const uint32_t *__restrict__ pos, uint32_t *__restrict__ n2o, uint32_t *d_num_items,
@@ -237,7 +237,7 @@ ht_compact_pad_kernel(Bucket *table, const uint32_t *__restrict__ dst, uint32_t 
   chunk_range(n, p, gridDim.x, kBlock, &begin, &end);
   const uint32_t items0 = *d_num_items;  // stable: only the last finisher updates it, at the end
 
-  constexpr int kCache = 4;  // a chunk is <= 4 tiles up to ~0.9 M items on a full grid
+  constexpr int kCache = 6;  // one resident wave (>= 4 CTAs/SM = 592 tickets) covers ~0.9 M items in <= 6 tiles
   uint32_t bpr[kCache], wr[kCache], idr[kCache];
   unsigned long long partial = 0;
 #pragma unroll
@@ -288,36 +288,41 @@ ht_compact_pad_kernel(Bucket *table, const uint32_t *__restrict__ dst, uint32_t 
       base_new += tile_total & 0xFFFFu;
     }
   }
-  for (uint32_t t0 = begin + kCache * kBlock; t0 < end; t0 += kBlock) {  // long chunks: tile by tile
+  const uint32_t edge_after_cache = base_edge;
+  for (uint32_t t0 = begin + kCache * kBlock; t0 < end; t0 += kBlock) {  // long chunks, first walk: owners + col
     const uint32_t i = t0 + threadIdx.x;
-    uint32_t valid = 0, isnew = 0, bp = 0, w = 0, id = kEmpty;
+    uint32_t valid = 0, isnew = 0, bp = 0, id = kEmpty;
     if (i < end) id = __ldg(dst + i);
     if (id != kEmpty) {
       valid = 1;
       bp = pos[i];
-      w = table[bp].local;
-      isnew = (w == (kPending | i)) ? 1u : 0u;
+      isnew = (table[bp].local == (kPending | i)) ? 1u : 0u;
     }
     uint32_t tile_total;
     const uint32_t excl = block_excl_scan((valid << 16) | isnew, sm.warp, &tile_total);
     if (isnew) {
-      w = items0 + base_new + (excl & 0xFFFFu);
-      table[bp].local = w;
-      n2o[w] = id;
+      const uint32_t local = items0 + base_new + (excl & 0xFFFFu);
+      table[bp].local = local;
+      n2o[local] = id;
     }
-    const uint32_t e = base_edge + (excl >> 16);
+    if (valid) out_col[base_edge + (excl >> 16)] = i / fanout;
     base_edge += tile_total >> 16;
     base_new += tile_total & 0xFFFFu;
-    __syncthreads();  // owners of this tile are written
-    if (valid) {
-      out_col[e] = i / fanout;
-      out_row[e] = (w & kPending) ? wait_local(table, bp) : w;
-    }
   }
   __syncthreads();  // this CTA's owners are all assigned and visible
 #pragma unroll
   for (int it = 0; it < kCache; ++it)
     if (idr[it] != kEmpty) out_row[eoff[it]] = (wr[it] & kPending) ? wait_local(table, bpr[it]) : wr[it];
+  // long chunks, second walk: only now may the CTA wait on lower tickets
+  uint32_t e_walk = edge_after_cache;
+  for (uint32_t t0 = begin + kCache * kBlock; t0 < end; t0 += kBlock) {
+    const uint32_t i = t0 + threadIdx.x;
+    const uint32_t valid = (i < end && __ldg(dst + i) != kEmpty) ? 1u : 0u;
+    uint32_t tile_total;
+    const uint32_t excl = block_excl_scan(valid, sm.warp, &tile_total);
+    if (valid) out_row[e_walk + excl] = wait_local(table, pos[i]);
+    e_walk += tile_total;
+  }
 
   // totals travel through the pad words; the CTA that finishes LAST publishes them (every other CTA has
   // read items0 by then) and re-arms the workspace
@@ -421,6 +426,8 @@ int ht_compact_pad_launch(void *table, const uint32_t *dst, uint32_t n_seed_max,
                           uint32_t fanout, const uint32_t *pos, uint32_t *n2o, uint32_t *d_num_items,
                           uint32_t *out_row, uint32_t *out_col, uint32_t *count_edge, uint32_t *count_src,
                           uint32_t *count_next, void *chain_ws, cudaStream_t st) {
+  // ONE resident wave: tickets beyond residency start a second round of the whole latency chain (measured r1_q c6:
+  // 1024 tickets on 740 resident slots, 56 us instead of 24 us)
   static const int occ = occupancy(ht_compact_pad_kernel, kBlock, 0);
   const int grid = persistent_grid((uint64_t)n_seed_max * fanout, kBlock, occ, true);
   ht_compact_pad_kernel<<<grid, kBlock, 0, st>>>((Bucket *)table, dst, n_seed_max, d_n_seed, fanout, pos, n2o,

@@ -288,7 +288,7 @@ Sampler::Sampler(const Dataset *ds, Context ctx, int worker_id, int num_worker, 
     if (rc_.sample_type == kRandomWalk)
       ws_bytes = std::max(ws_bytes, fgnn_k_sample_random_walk_workspace_bytes((uint32_t)in_max_[i], (uint32_t)fanout_[i]));
   }
-  size_t nslots = 3;
+  size_t nslots = 4;  // r1_q c7: 4 slots + padded sampler 205 us/step, 3 slots 212 us (6 slots 200 us, +54 MB tables)
   if (IsEnvSet("FGNN_SAMPLER_SLOTS")) nslots = (size_t)std::max(1, atoi(GetEnv("FGNN_SAMPLER_SLOTS").c_str()));
   nslots = std::min<size_t>(nslots, 8);
   slots_.resize(nslots);

@@ -22,7 +22,7 @@ def main():
     ap.add_argument("--workload", default="papers100M")
     ap.add_argument("--empty-feat", type=int, default=22)
     ap.add_argument("--cache-pct", type=float, default=0.3)
-    ap.add_argument("--sweep", default="fuse", choices=["fuse", "overlap"],
+    ap.add_argument("--sweep", default="fuse", choices=["fuse", "overlap", "profile"],
                     help="fuse: kernel-fusion variants; overlap: how the sampling slots and the gather share the GPU\n                    (FGNN_GRID_DIV, gather implementation / CTA shape)")
     a = ap.parse_args()
     import torch
@@ -82,17 +82,23 @@ def main():
         torch.cuda.synchronize()
         return e0.elapsed_time(e1) / steps * 1e3
 
+    if a.sweep == "profile":
+        # for `ncu --profile-from-start off`: one slot, sampling chain only, environment as given
+        run(1, False, 10)
+        torch.cuda.synchronize()
+        torch.cuda.profiler.start()
+        us = run(1, False, a.steps)
+        torch.cuda.profiler.stop()
+        print("PROFILE_JSON " + json.dumps({"sample_only_us_slots1": round(us, 1)}))
+        return
     os.environ["FGNN_TUNING_DYNAMIC"] = "1"
     if a.sweep == "overlap":
         base = {"FGNN_GRID_DIV": "1", "FGNN_GATHER_IMPL": "bulk", "FGNN_BULK_WARPS": "8", "FGNN_BULK_STAGES": "8",
-                "FGNN_GATHER_CTAS_PER_SM": "0"}
-        variants = [{}, {"FGNN_GRID_DIV": "2"}, {"FGNN_GRID_DIV": "3"}, {"FGNN_GRID_DIV": "4"},
-                    {"FGNN_GATHER_IMPL": "dyn"}, {"FGNN_GATHER_IMPL": "dyn", "FGNN_GRID_DIV": "2"},
-                    {"FGNN_GATHER_IMPL": "dyn", "FGNN_GRID_DIV": "3"},
-                    {"FGNN_GATHER_IMPL": "dyn", "FGNN_BULK_WARPS": "4", "FGNN_GATHER_CTAS_PER_SM": "2"},
-                    {"FGNN_GATHER_IMPL": "dyn", "FGNN_BULK_WARPS": "4", "FGNN_GATHER_CTAS_PER_SM": "2", "FGNN_GRID_DIV": "2"},
-                    {"FGNN_GATHER_IMPL": "dyn", "FGNN_BULK_WARPS": "16", "FGNN_BULK_STAGES": "6"},
-                    {"FGNN_BULK_WARPS": "4", "FGNN_GATHER_CTAS_PER_SM": "2", "FGNN_GRID_DIV": "2"}]
+                "FGNN_GATHER_CTAS_PER_SM": "0", "FGNN_BATCH_FUSE": "2"}
+        dyn16 = {"FGNN_GATHER_IMPL": "dyn", "FGNN_BULK_WARPS": "16", "FGNN_BULK_STAGES": "6"}
+        w16 = {"FGNN_BULK_WARPS": "16", "FGNN_BULK_STAGES": "6"}
+        variants = [{}, {"FGNN_BATCH_FUSE": "6"}, dict(w16), dict(w16, FGNN_BATCH_FUSE="6"),
+                    dict(dyn16, FGNN_BATCH_FUSE="6"), dict(w16, FGNN_BATCH_FUSE="6", FGNN_GRID_DIV="2")]
         for var in variants:
             env = dict(base, **var)
             os.environ.update(env)
