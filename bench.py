@@ -49,6 +49,7 @@ def parse():
                     help="mini-batches in flight on separate streams (device-resident leg)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cache25", action="store_true", help="skip the extra 25 %% cache leg (profiling runs)")
     ap.add_argument("--no-partition", action="store_true",
                     help="N > 1: skip the extra leg that stripes the feature cache over the GPUs (NVLink peer loads)")
     return ap.parse_args()
@@ -170,6 +171,17 @@ def aggregate(ms_total, edges, device):
     e = torch.tensor([edges], dtype=torch.int64, device=device)
     dist.all_reduce(e, op=dist.ReduceOp.SUM)
     return float(t.item()), int(e.item())
+
+
+def ncu_traffic():
+    """DRAM bytes per launch of the dominant kernel from the committed `ncu --set full` capture of this same
+    command (profiles/gather_traffic.json, written by tools/ncu_summary.py traffic); None when absent."""
+    p = os.path.join(ROOT, "profiles", "gather_traffic.json")
+    try:
+        with open(p) as f:
+            return json.load(f)
+    except (OSError, ValueError):
+        return None
 
 
 def peaks():
@@ -336,8 +348,10 @@ def run_ours(args):
         t_start.record()
         for st in s_streams + [x_stream]:
             st.wait_stream(main)
+        th0 = time.perf_counter()
         for k in range(Ksteps):
             one_step(W + k, key0 + W + k, ev[k])
+        host_enqueue_s = time.perf_counter() - th0
         for st in s_streams + [x_stream]:
             main.wait_stream(st)
         t_end.record()
@@ -347,7 +361,7 @@ def run_ours(args):
         if world > 1:
             dist.barrier()
         r = dict(cache_s=cache_s, launches=K.launch_count() - launches0, clk=clocks.stop(),
-                 ms_total=t_start.elapsed_time(t_end))
+                 ms_total=t_start.elapsed_time(t_end), host_enqueue_ms=host_enqueue_s * 1e3)
         h = hist.cpu().numpy().astype("int64")
         r["edges"] = int(h[:, :, 1].sum())
         r["n_in_total"] = int(h[:, 0, 2].sum())       # input_nodes of every step (num_src of layer 0)
@@ -363,7 +377,8 @@ def run_ours(args):
 
     Ksteps, W = args.steps, max(3, args.warmup)
     # reference-like regime first (25 % cache, misses over the host link) ...
-    r25 = measure(0.25, min(Ksteps, steps_per_epoch), W, 2_000_000) if args.cache_pct != 0.25 else None
+    r25 = measure(0.25, min(Ksteps, steps_per_epoch), W, 2_000_000) \
+        if args.cache_pct != 0.25 and not args.no_cache25 else None
     # ... then the headline regime
     r = measure(args.cache_pct, Ksteps, W, 0, profile=True)
     ms_total, edges, n_in_total = r["ms_total"], r["edges"], r["n_in_total"]
@@ -408,7 +423,8 @@ def run_ours(args):
     achieved = alg_bytes / (gather_ms * 1e-3) / 1e9 if gather_ms > 0 else 0.0
     roofline = {"bound": "hbm", "kernel": "gather_bulk_kernel<6,16> (fgnn_k_gather_cached: cp.async.bulk ring, 16 warps x 6 stages)",
                 "achieved": round(achieved, 1), "peak": peak, "peak_kind": peak_kind, "unit": "GB/s",
-                "frac": round(achieved / peak, 4), "traffic": None,
+                "frac": round(achieved / peak, 4),
+                "traffic": (ncu_traffic() or {}).get("dram_bytes_per_launch"), "traffic_capture": ncu_traffic(),
                 "bytes_per_launch": alg_bytes // max(1, Ksteps), "avg_launch_ms": gather_ms / max(1, Ksteps),
                 "share_of_step": round(gather_ms / ms_total, 3),
                 "timing": "CUDA events on the extraction stream around every gather launch of the timed region; "
@@ -441,7 +457,7 @@ def run_ours(args):
                   "cache_hit_rate": hits / max(1, hits + misses), "presc_s": presc_s, "cache_build_s": cache_s,
                   "graph_gen_s": wl["gen_s"], "sample_ms_per_step": sample_ms / Ksteps,
                   "gather_ms_per_step": gather_ms / Ksteps, "extract_ms_per_step": r["extract_ms"] / Ksteps,
-                  "slots": len(hp.slots),
+                  "slots": len(hp.slots), "host_enqueue_ms_per_step": r["host_enqueue_ms"] / Ksteps,
                   "note": "sample_ms is the sampling chain's time on its own stream while other slots and the "
                           "gather run concurrently; value uses the wall time of the whole overlapped loop"},
     }

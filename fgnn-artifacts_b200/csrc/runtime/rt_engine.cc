@@ -789,7 +789,11 @@ void Engine::LoadDataset() {  // engine.cc:73-264
       case kCacheByPreSample: break;
       default: FCHECK(false) << "cache policy " << rc.cache_policy << " is outside the hot-path scope";
     }
-    if (f) ds->ranking_nodes = Tensor::FromMmap(path + f, kI32, {ds->num_node}, "dataset.ranking_nodes");
+    // cache_by_degree / cache_by_random: when the offline tool's file is absent the ranking is computed on the
+    // sampler GPU at init (Engine::DoGpuRanking); the other file-based policies need their file
+    const bool on_gpu_ok = rc.cache_policy == kCacheByDegree || rc.cache_policy == kCacheByRandom;
+    if (f && (FileExists(path + f) || !on_gpu_ok))
+      ds->ranking_nodes = Tensor::FromMmap(path + f, kI32, {ds->num_node}, "dataset.ranking_nodes");
   }
   dataset_ = std::move(ds);
 }
@@ -894,6 +898,8 @@ void Engine::Init() {
     Timer tp;
     DoPreSample();
     Profiler::Get().LogInit(kLogInitL2Presample, tp.Passed());
+  } else if (rc.UseGPUCache() && !dataset_->ranking_nodes) {
+    DoGpuRanking();
   }
   Timer tc;
   const IdType *rank_host = dataset_->ranking_nodes ? (const IdType *)dataset_->ranking_nodes->data : nullptr;
@@ -953,6 +959,43 @@ void Engine::DoPreSample() {
   Profiler::Get().Reset(num_epoch_, num_step_);
 }
 
+// cache_by_degree.cc:36-58 / cache_by_random.cc:36-48 on the sampler GPU, for datasets that ship without the
+// offline tool's ranking file: out-degree histogram of the CSR + the PreSC {key,id} descending sort, or a seeded
+// permutation.  Published exactly like the PreSC ranking.
+void Engine::DoGpuRanking() {
+  RunConfig &rc = RunConfig::Get();
+  const size_t V = dataset_->num_node, E = dataset_->num_edge;
+  Sampler *s = sampler_.get();
+  CUDA_CALL(cudaSetDevice(s->device()));
+  Timer tr;
+  auto rank = Tensor::Device(kI32, {V}, s->device(), s->stream(), "policy_rank");
+  if (rc.cache_policy == kCacheByDegree) {
+    auto deg = Tensor::Device(kI32, {V}, s->device(), s->stream(), "out_degree");
+    auto ws = Tensor::Device(kU8, {fgnn_k_presc_rank_workspace_bytes(V)}, s->device(), s->stream(), "rank_ws");
+    FGNN_CALL(fgnn_k_rank_by_degree(s->d_indices(), E, V, (uint32_t *)deg->data, (uint32_t *)rank->data, ws->data,
+                                    ws->nbytes, (fgnn_stream_t)s->stream()));
+    CUDA_CALL(cudaStreamSynchronize(s->stream()));
+  } else {
+    FCHECK(rc.cache_policy == kCacheByRandom) << "cache policy " << rc.cache_policy << " needs its ranking file";
+    auto ws = Tensor::Device(kU8, {fgnn_k_rank_random_workspace_bytes(V)}, s->device(), s->stream(), "rank_ws");
+    FGNN_CALL(fgnn_k_rank_random(V, rc.seed, (uint32_t *)rank->data, ws->data, ws->nbytes,
+                                 (fgnn_stream_t)s->stream()));
+    CUDA_CALL(cudaStreamSynchronize(s->stream()));
+  }
+  IdType *dst_host;
+  TensorPtr host_rank;
+  if (ring_) {
+    dst_host = ring_->ranking();
+  } else {
+    host_rank = Tensor::Pinned(kI32, {V}, "ranking_nodes");
+    dst_host = (IdType *)host_rank->data;
+  }
+  CUDA_CALL(cudaMemcpyAsync(dst_host, rank->data, V * 4, cudaMemcpyDeviceToHost, s->stream()));
+  CUDA_CALL(cudaStreamSynchronize(s->stream()));
+  if (host_rank) dataset_->ranking_nodes = host_rank;
+  Profiler::Get().LogInit(kLogInitL3PresampleSort, tr.Passed());
+}
+
 void Engine::SampleInit(int worker_id, Context ctx) {  // dist_engine.cc:231-364
   FCHECK(dist_ && !initialized_) << "sample_init is only valid in arch5, once per process";
   RunConfig &rc = RunConfig::Get();
@@ -980,6 +1023,9 @@ void Engine::SampleInit(int worker_id, Context ctx) {  // dist_engine.cc:231-364
     Profiler::Get().LogInit(kLogInitL2Presample, tps.Passed());
   } else if (dataset_->ranking_nodes && worker_id == 0) {
     memcpy(ring_->ranking(), dataset_->ranking_nodes->data, dataset_->num_node * 4);
+  } else if (rc.UseGPUCache() && !dataset_->ranking_nodes) {
+    if (worker_id == 0) DoGpuRanking();
+    pthread_barrier_wait(&ring_->sampler_barrier);
   }
   Profiler::Get().Reset(num_epoch_, num_step_);
   Profiler::Get().LogInit(kLogInitL1Sampler, t0.Passed());

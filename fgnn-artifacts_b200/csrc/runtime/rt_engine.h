@@ -86,6 +86,7 @@ class Engine {
   TaskPtr RecvTask(bool block = true);
   void SendTask(const TaskPtr &t);
   void DoPreSample();
+  void DoGpuRanking();
   void CreateSharedState();
   char *DevSlot(uint64_t idx);
 

@@ -73,6 +73,11 @@ _SIGS = {
     "fgnn_k_freq_count": [_vp, _vp, _u32, _vp, _vp],
     "fgnn_k_presc_rank": [_vp, _sz, _vp, _vp, _sz, _vp],
     "fgnn_k_shuffle": [_vp, _sz, _u64, _u64, _vp, _vp, _sz, _vp],
+    "fgnn_k_build_alias_table": [_vp, _vp, _sz, _sz, _vp, _vp, _vp, _vp, _sz, _vp],
+    "fgnn_k_build_prefix_table": [_vp, _sz, _vp, _vp, _vp],
+    "fgnn_k_out_degree": [_vp, _sz, _vp, _sz, _vp],
+    "fgnn_k_rank_by_degree": [_vp, _sz, _sz, _vp, _vp, _vp, _sz, _vp],
+    "fgnn_k_rank_random": [_sz, _u64, _vp, _vp, _sz, _vp],
     "fgnn_k_shard_alloc": [C.POINTER(_vp), _sz],
     "fgnn_k_shard_free": [_vp],
     "fgnn_k_ipc_export": [_vp, _vp],
@@ -87,6 +92,8 @@ _SIZE_FNS = {
     "fgnn_k_sample_random_walk_workspace_bytes": [_u32, _u32],
     "fgnn_k_presc_rank_workspace_bytes": [_sz],
     "fgnn_k_shuffle_workspace_bytes": [_sz],
+    "fgnn_k_alias_table_workspace_bytes": [_sz],
+    "fgnn_k_rank_random_workspace_bytes": [_sz],
 }
 
 _lib = None
@@ -269,6 +276,40 @@ def presc_rank_workspace_bytes(num_nodes):
 def presc_rank(freq, num_nodes, rank, workspace):
     _check(load().fgnn_k_presc_rank(_ptr(freq), num_nodes, _ptr(rank), _ptr(workspace),
                                     workspace.numel() * workspace.element_size(), _stream()), "presc_rank")
+
+
+def build_alias_table(indptr, indices, num_nodes, num_edges, weights, prob, alias, workspace=None):
+    """prob_table / alias_table from per-edge weights (create_alias_table.cc:96-180), on the GPU."""
+    import torch
+    if workspace is None:
+        workspace = torch.empty(int(load().fgnn_k_alias_table_workspace_bytes(num_edges)), dtype=torch.uint8,
+                                device=prob.device)
+    _check(load().fgnn_k_build_alias_table(_ptr(indptr), _ptr(indices), num_nodes, num_edges, _ptr(weights),
+                                           _ptr(prob), _ptr(alias), _ptr(workspace), workspace.numel(), _stream()),
+           "build_alias_table")
+
+
+def build_prefix_table(indptr, num_nodes, weights, prefix):
+    _check(load().fgnn_k_build_prefix_table(_ptr(indptr), num_nodes, _ptr(weights), _ptr(prefix), _stream()),
+           "build_prefix_table")
+
+
+def out_degree(indices, num_edges, out_deg, num_nodes):
+    _check(load().fgnn_k_out_degree(_ptr(indices), num_edges, _ptr(out_deg), num_nodes, _stream()), "out_degree")
+
+
+def rank_by_degree(indices, num_edges, num_nodes, out_deg, rank, workspace):
+    _check(load().fgnn_k_rank_by_degree(_ptr(indices), num_edges, num_nodes, _ptr(out_deg), _ptr(rank),
+                                        _ptr(workspace), workspace.numel(), _stream()), "rank_by_degree")
+
+
+def rank_random(num_nodes, seed, rank, workspace=None):
+    import torch
+    if workspace is None:
+        workspace = torch.empty(int(load().fgnn_k_rank_random_workspace_bytes(num_nodes)), dtype=torch.uint8,
+                                device=rank.device)
+    _check(load().fgnn_k_rank_random(num_nodes, seed & 0xFFFFFFFFFFFFFFFF, _ptr(rank), _ptr(workspace),
+                                     workspace.numel(), _stream()), "rank_random")
 
 
 def shuffle_workspace_bytes(n):

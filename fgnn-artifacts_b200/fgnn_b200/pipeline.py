@@ -84,7 +84,8 @@ class Slot:
 
 class HotPath:
     def __init__(self, indptr, indices, num_nodes, fanouts, batch_size, sample_type="khop2", seed=0x5EED,
-                 prob_table=None, alias_table=None, prefix_table=None, rw=None, device="cuda", num_slots=1):
+                 prob_table=None, alias_table=None, prefix_table=None, rw=None, device="cuda", num_slots=1,
+                 ht_capacity=None):
         K.load()
         self.dev = device
         self.indptr, self.indices = indptr, indices
@@ -104,7 +105,8 @@ class HotPath:
             cur = cur * (self.fanouts[i] + 1)
         self.max_nodes = predict_num_nodes(batch_size, self.fanouts)
         self.edge_max = [self.in_max[i] * self.fanouts[i] for i in range(self.L)]
-        self.cap = K.ht_capacity(self.max_nodes)
+        # ht_capacity: power-of-two override for experiments; must exceed the batch's unique-node count
+        self.cap = ht_capacity if ht_capacity else K.ht_capacity(self.max_nodes)
         self.slots = [Slot(self) for _ in range(max(1, num_slots))]
         self._alias_slot(0)
         # cache state (set by build_cache)

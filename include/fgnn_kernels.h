@@ -285,6 +285,34 @@ int fgnn_k_presc_rank(const uint32_t *freq, size_t num_nodes,
                       uint32_t *ranking_nodes, void *workspace,
                       size_t workspace_bytes, fgnn_stream_t stream);
 
+/* ---- dataset preparation (reference: offline CPU tools) --------------- */
+/* prob_table / alias_table of the alias sampler from per-edge weights: Vose's method with two FIFO
+ * queues per CSR row, bit-identical to utility/data-process/toolkit/weight/create_alias_table.cc:96-180
+ * for the same weights (alias = neighbour id).  workspace: fgnn_k_alias_table_workspace_bytes(E).
+ * Not re-entrant across streams (one global row ticket). */
+size_t fgnn_k_alias_table_workspace_bytes(size_t num_edges);
+int fgnn_k_build_alias_table(const uint32_t *indptr, const uint32_t *indices,
+                             size_t num_nodes, size_t num_edges, const float *weights,
+                             float *prob_table, uint32_t *alias_table, void *workspace,
+                             size_t workspace_bytes, fgnn_stream_t stream);
+/* prob_prefix_table[off+i] = sequential fp32 sum of the row's weights up to i
+ * (toolkit/weight/create_prob_prefix_table.cc:94-123) */
+int fgnn_k_build_prefix_table(const uint32_t *indptr, size_t num_nodes, const float *weights,
+                              float *prob_prefix_table, fgnn_stream_t stream);
+/* out_degree[v] = occurrences of v in indices (common/graph_loader.cc:109-147) */
+int fgnn_k_out_degree(const uint32_t *indices, size_t num_edges, uint32_t *out_degree,
+                      size_t num_nodes, fgnn_stream_t stream);
+/* cache_by_degree ranking: sort {out_degree, id} descending (toolkit/cache/cache_by_degree.cc:36-58).
+ * out_degree u32[V] is filled as a by-product; workspace: fgnn_k_presc_rank_workspace_bytes(V). */
+int fgnn_k_rank_by_degree(const uint32_t *indices, size_t num_edges, size_t num_nodes,
+                          uint32_t *out_degree, uint32_t *ranking_nodes, void *workspace,
+                          size_t workspace_bytes, fgnn_stream_t stream);
+/* cache_by_random ranking: a seeded uniform permutation of [0, V) (toolkit/cache/cache_by_random.cc:36-48;
+ * Philox-key sort instead of the reference's default-seeded mt19937 Fisher-Yates). */
+size_t fgnn_k_rank_random_workspace_bytes(size_t num_nodes);
+int fgnn_k_rank_random(size_t num_nodes, uint64_t seed, uint32_t *ranking_nodes, void *workspace,
+                       size_t workspace_bytes, fgnn_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

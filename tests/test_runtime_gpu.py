@@ -107,6 +107,33 @@ def test_single_process_engine_matches_oracle(tmp_path, oracle, dataset, sample_
         assert float(data["miss/%d" % k0]) == data["b/%d/feat" % k0].nbytes
 
 
+@pytest.mark.parametrize("policy", ["degree", "random"])
+def test_cache_policy_ranked_on_gpu_when_file_absent(tmp_path, oracle, dataset, policy):
+    """cache_by_degree / cache_by_random without the offline tool's cache_by_*.bin (engine.cc:216-256 loads it):
+    the ranking is computed on the sampler GPU; batches stay bit-exact and the degree policy's miss bytes are
+    those of the top-30% {out_degree, id} vertices (toolkit/cache/cache_by_degree.cc:36-58)."""
+    import samgraph.common as sc
+    cfg = base_config(dataset["path"], cache=0.3)
+    cfg.update(_cache_policy=sc.cache_policies[policy], cache_policy=policy)
+    assert not os.path.exists(os.path.join(dataset["path"], "cache_by_%s.bin" % policy))
+    out = run_driver(tmp_path, {"mode": "single", "config": cfg})
+    data = np.load(out)
+    check_batches(oracle, dataset, cfg, data, int(data["num_step"]))
+    V, D = dataset["feat"].shape
+    ncache = int(V * 0.3)
+    if policy == "degree":
+        deg = np.bincount(dataset["indices"], minlength=V).astype(np.uint32)
+        cached = np.zeros(V, bool)
+        cached[oracle.presc_rank(deg)[:ncache]] = True
+        for k in data["keys"]:
+            nodes = data["b/%d/input_nodes" % int(k)].view(np.uint32)
+            assert float(data["miss/%d" % int(k)]) == float((~cached[nodes]).sum() * D * 4)
+    else:
+        miss = sum(float(data["miss/%d" % int(k)]) for k in data["keys"])
+        rows = sum(len(data["b/%d/input_nodes" % int(k)]) for k in data["keys"])
+        assert 0.55 < miss / (rows * D * 4) < 0.85          # a random 30 % cache misses about 70 % of the rows
+
+
 def test_arch1_all_features_resident(tmp_path, oracle, dataset):
     cfg = base_config(dataset["path"], arch="arch1", cache=0.0)
     out = run_driver(tmp_path, {"mode": "single", "config": cfg})

@@ -22,7 +22,7 @@ def main():
     ap.add_argument("--workload", default="papers100M")
     ap.add_argument("--empty-feat", type=int, default=22)
     ap.add_argument("--cache-pct", type=float, default=0.3)
-    ap.add_argument("--sweep", default="fuse", choices=["fuse", "overlap", "profile"],
+    ap.add_argument("--sweep", default="fuse", choices=["fuse", "overlap", "profile", "diag"],
                     help="fuse: kernel-fusion variants; overlap: how the sampling slots and the gather share the GPU\n                    (FGNN_GRID_DIV, gather implementation / CTA shape)")
     a = ap.parse_args()
     import torch
@@ -38,7 +38,8 @@ def main():
     spe = (wl["T"] + BATCH - 1) // BATCH
     perm = wl["train"]
     SL = 6
-    hp = HotPath(wl["indptr"], wl["indices"], V, FANOUTS, BATCH, "khop2", seed=1, device=dev, num_slots=SL)
+    hp = HotPath(wl["indptr"], wl["indices"], V, FANOUTS, BATCH, "khop2", seed=1, device=dev, num_slots=SL,
+                 ht_capacity=(1 << int(os.environ["FGNN_DIAG_HT_LOG2"])) if os.environ.get("FGNN_DIAG_HT_LOG2") else None)
     rank = torch.randperm(V, device=dev).to(torch.int32)
     hp.build_cache(rank, a.cache_pct, wl["host_feat"], D * 4, wl["feat_mask"])
     # every row "hit": table over the cached fraction only -> make all nodes map into the cache (mod)
@@ -51,7 +52,10 @@ def main():
         s = k % (spe - 1)
         return perm[s * BATCH:(s + 1) * BATCH], BATCH
 
-    def run(slots, with_gather, steps):
+    host_us = [0.0]
+    copy_src = torch.empty((560000, D * 4), dtype=torch.uint8, device=dev)
+
+    def run(slots, with_gather, steps, copy_instead=False, gather_only=False):
         sampled = [torch.cuda.Event() for _ in range(slots)]
         gathered = [torch.cuda.Event() for _ in range(slots)]
         main = torch.cuda.current_stream()
@@ -62,20 +66,27 @@ def main():
         e0.record()
         for st in streams + [xs]:
             st.wait_stream(main)
+        th0 = time.perf_counter()
         for k in range(steps):
             sd, n = seeds_of(k)
             sl = k % slots
-            with torch.cuda.stream(streams[sl]):
-                if with_gather:
-                    streams[sl].wait_event(gathered[sl])
-                hp.sample(sd, n, 7000 + k, slot=sl)
-                sampled[sl].record()
+            if not gather_only:
+                with torch.cuda.stream(streams[sl]):
+                    if with_gather:
+                        streams[sl].wait_event(gathered[sl])
+                    hp.sample(sd, n, 7000 + k, slot=sl)
+                    sampled[sl].record()
             if with_gather:
                 with torch.cuda.stream(xs):
-                    xs.wait_event(sampled[sl])
-                    hp.gather(sl)
+                    if not gather_only:
+                        xs.wait_event(sampled[sl])
+                    if copy_instead:
+                        hp.feat_out[:560000].copy_(copy_src)   # pure streaming copy of the gather's size
+                    else:
+                        hp.gather(sl)
                     hp.gather_labels(sd, n)
                     gathered[sl].record()
+        host_us[0] = (time.perf_counter() - th0) / steps * 1e6
         for st in streams + [xs]:
             main.wait_stream(st)
         e1.record()
@@ -92,6 +103,31 @@ def main():
         print("PROFILE_JSON " + json.dumps({"sample_only_us_slots1": round(us, 1)}))
         return
     os.environ["FGNN_TUNING_DYNAMIC"] = "1"
+    if a.sweep == "diag":
+        # what bounds the overlapped loop?  host enqueue rate, the gather's SM footprint, or shared DRAM time
+        res = {"ht_log2": os.environ.get("FGNN_DIAG_HT_LOG2"), "ht_MB_per_slot": K.ht_bytes(hp.cap) / 1e6}
+        for var in ({}, {"FGNN_BULK_WARPS": "8", "FGNN_BULK_STAGES": "4"}, {"FGNN_BULK_WARPS": "16", "FGNN_BULK_STAGES": "3"},
+                    {"FGNN_BULK_WARPS": "4", "FGNN_BULK_STAGES": "8"}):
+            os.environ.update({"FGNN_BULK_WARPS": "16", "FGNN_BULK_STAGES": "6"})
+            os.environ.update(var)
+            tag = "w%ss%s" % (os.environ["FGNN_BULK_WARPS"], os.environ["FGNN_BULK_STAGES"])
+            run(4, True, 10)
+            res["with_gather_us_slots4_" + tag] = round(run(4, True, a.steps), 1)
+            res["host_enqueue_us_" + tag] = round(host_us[0], 1)
+            run(1, True, 10, gather_only=True)
+            res["gather_only_us_" + tag] = round(run(1, True, a.steps, gather_only=True), 1)
+        os.environ.update({"FGNN_BULK_WARPS": "16", "FGNN_BULK_STAGES": "6"})
+        for slots in (1, 2, 3, 4, 6):
+            run(slots, False, 10)
+            res["sample_only_us_slots%d" % slots] = round(run(slots, False, a.steps), 1)
+            res["sample_only_host_us_slots%d" % slots] = round(host_us[0], 1)
+        run(4, True, 10, copy_instead=True)
+        res["with_copy_us_slots4"] = round(run(4, True, a.steps, copy_instead=True), 1)
+        run(1, True, 10, copy_instead=True, gather_only=True)
+        res["copy_only_us"] = round(run(1, True, a.steps, copy_instead=True, gather_only=True), 1)
+        res["n_in"] = int(hp.slots[0].num_items.item())
+        print("DIAG_JSON " + json.dumps(res))
+        return
     if a.sweep == "overlap":
         base = {"FGNN_GRID_DIV": "1", "FGNN_GATHER_IMPL": "bulk", "FGNN_BULK_WARPS": "8", "FGNN_BULK_STAGES": "8",
                 "FGNN_GATHER_CTAS_PER_SM": "0", "FGNN_BATCH_FUSE": "2"}

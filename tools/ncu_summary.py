@@ -61,5 +61,31 @@ def launch_list(path):
     print("total %.1f us over %d launches" % (tot, sum(a[0] for a in agg.values())))
 
 
+def traffic(path, pattern="gather_bulk"):
+    """JSON for profiles/gather_traffic.json: mean DRAM read+write bytes per launch of the kernels matching
+    `pattern` in an `ncu --set full` report (bench.py reports it as roofline.traffic)."""
+    import json
+    out = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(out.splitlines()))
+    hdr, units = rows[0], rows[1]
+    ki = hdr.index("Kernel Name")
+    ri, wi, ti = hdr.index("dram__bytes_read.sum"), hdr.index("dram__bytes_write.sum"), hdr.index("gpu__time_duration.sum")
+    scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+    tscale = {"ns": 1e-3, "us": 1.0, "ms": 1e3, "usecond": 1.0, "nsecond": 1e-3, "msecond": 1e3}
+    rd, wr, us, name = [], [], [], None
+    for r in rows[2:]:
+        if pattern not in r[ki]:
+            continue
+        name = r[ki].split("(")[0].replace("void ", "").replace("fgnn::<unnamed>::", "")
+        rd.append(float(r[ri]) * scale[units[ri]])
+        wr.append(float(r[wi]) * scale[units[wi]])
+        us.append(float(r[ti]) * tscale.get(units[ti], 1.0))
+    n = max(1, len(rd))
+    print(json.dumps({"kernel": name, "launches": len(rd), "dram_read_bytes_per_launch": sum(rd) / n,
+                      "dram_write_bytes_per_launch": sum(wr) / n, "dram_bytes_per_launch": (sum(rd) + sum(wr)) / n,
+                      "ncu_time_us_per_launch": sum(us) / n, "report": path,
+                      "how": "ncu --set full --clock-control none, bench.py timed region (cold cache, serialised replay)"}))
+
+
 if __name__ == "__main__":
-    {"rep": rep, "list": launch_list}[sys.argv[1]](sys.argv[2])
+    {"rep": rep, "list": launch_list, "traffic": traffic}[sys.argv[1]](*sys.argv[2:])
