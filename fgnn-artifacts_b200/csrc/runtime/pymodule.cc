@@ -120,6 +120,78 @@ PyObject *GetGraphEdge(PyObject *, PyObject *args) {
   const TrainGraph &g = b->graphs[layer];
   return ToCapsule(WHICH == 0 ? g.row : (WHICH == 1 ? g.col : g.data), b, kI32);
 }
+// Block hand-off in CSC form: (indptr, indices, edge_ids | None) of one layer, the arguments of
+// the reference's DGL patch `create_unitgraph_from_csc` (3rdparty/dgl.patch:30-57).  The reference builds COO
+// blocks (adapter.py:92-95) and pays DGL's COO->CSC conversion in the trainer (kLogL1ConvertTime).
+// khop0 / khop2 / hash-dedup / random-walk layers are emitted seed-major, so `indices` IS `row` (zero copy,
+// edge_ids = None = identity) and only the indptr is computed; khop1 / weighted layers are sorted by dst.
+cudaStream_t HandoffStream(int device) {
+  static cudaStream_t streams[64] = {nullptr};
+  FCHECK(device >= 0 && device < 64);
+  if (!streams[device]) CUDA_CALL(cudaStreamCreateWithFlags(&streams[device], cudaStreamNonBlocking));
+  return streams[device];
+}
+PyObject *GetGraphCsc(PyObject *, PyObject *args) {
+  unsigned long long key;
+  int layer;
+  if (!PyArg_ParseTuple(args, "Ki", &key, &layer)) return nullptr;
+  TaskPtr b = Batch(key);
+  if (!b) return nullptr;
+  if (layer < 0 || layer >= (int)b->graphs.size()) {
+    PyErr_SetString(PyExc_IndexError, "samgraph: layer index out of range");
+    return nullptr;
+  }
+  TrainGraph &g = b->graphs[layer];
+  if (!g.row || !g.col || g.row->ctx.device_type != kGPU) {
+    PyErr_SetString(PyExc_RuntimeError, "samgraph: the block's row/col are not on a GPU");
+    return nullptr;
+  }
+  const SampleType st = RunConfig::Get().sample_type;
+  const bool sorted = st == kKHop0 || st == kKHop2 || st == kWeightedKHopHashDedup || st == kRandomWalk ||
+                      g.num_edge == 0;
+  if (!g.csc_indptr) {
+    const int dev = g.row->ctx.device_id;
+    int cur = 0;
+    CUDA_CALL(cudaGetDevice(&cur));
+    if (cur != dev) CUDA_CALL(cudaSetDevice(dev));
+    cudaStream_t s = HandoffStream(dev);
+    const uint32_t e = (uint32_t)g.num_edge, nd = (uint32_t)g.num_dst;
+    TensorPtr indptr = Tensor::Device(kI32, {g.num_dst + 1}, dev, s, "csc_indptr");
+    TensorPtr indices, eids, ws;
+    if (sorted) {
+      indices = g.row;
+      FGNN_CALL(fgnn_k_coo_to_csc((const uint32_t *)g.row->data, (const uint32_t *)g.col->data, e, nullptr, nd, 1,
+                                  (uint32_t *)indptr->data, nullptr, nullptr, nullptr, 0, s));
+    } else {
+      indices = Tensor::Device(kI32, {g.num_edge}, dev, s, "csc_indices");
+      eids = Tensor::Device(kI32, {g.num_edge}, dev, s, "csc_eids");
+      const size_t wb = fgnn_k_coo_to_csc_workspace_bytes(e, nd);
+      ws = Tensor::Device(kU8, {wb}, dev, s, "csc_ws");
+      FGNN_CALL(fgnn_k_coo_to_csc((const uint32_t *)g.row->data, (const uint32_t *)g.col->data, e, nullptr, nd, 0,
+                                  (uint32_t *)indptr->data, (uint32_t *)indices->data, (uint32_t *)eids->data,
+                                  ws->data, wb, s));
+    }
+    CUDA_CALL(cudaStreamSynchronize(s));  // the pool is not stream-ordered: finish before `ws` is recycled
+    if (cur != dev) CUDA_CALL(cudaSetDevice(cur));
+    g.csc_indptr = indptr;
+    g.csc_indices = indices;
+    g.csc_eids = eids;
+  }
+  PyObject *a = ToCapsule(g.csc_indptr, b, kI32);
+  PyObject *c = a ? ToCapsule(g.csc_indices, b, kI32) : nullptr;
+  PyObject *d = nullptr;
+  if (c) {
+    if (g.csc_eids) d = ToCapsule(g.csc_eids, b, kI32);
+    else { d = Py_None; Py_INCREF(d); }
+  }
+  if (!a || !c || !d) {
+    Py_XDECREF(a); Py_XDECREF(c); Py_XDECREF(d);
+    return nullptr;
+  }
+  PyObject *t = PyTuple_Pack(3, a, c, d);
+  Py_DECREF(a); Py_DECREF(c); Py_DECREF(d);
+  return t;
+}
 PyObject *GetInputNodes(PyObject *, PyObject *args) {
   unsigned long long key;
   if (!PyArg_ParseTuple(args, "K", &key)) return nullptr;
@@ -149,6 +221,7 @@ PyMethodDef kMethods[] = {
     {"samgraph_torch_get_graph_row", GetGraphEdge<0>, METH_VARARGS, "DLPack capsule: i32 [num_edge] (neighbour local ids)"},
     {"samgraph_torch_get_graph_col", GetGraphEdge<1>, METH_VARARGS, "DLPack capsule: i32 [num_edge] (seed local ids)"},
     {"samgraph_torch_get_graph_data", GetGraphEdge<2>, METH_VARARGS, "DLPack capsule: i32 [num_edge] (random-walk visit counts)"},
+    {"samgraph_torch_get_graph_csc", GetGraphCsc, METH_VARARGS, "(indptr i32 [num_dst+1], indices i32 [num_edge], edge_ids i32 [num_edge] | None) DLPack capsules"},
     {"samgraph_torch_get_dataset_feat", GetDatasetFeat, METH_NOARGS, "DLPack capsule: host feature table"},
     {"samgraph_torch_get_dataset_label", GetDatasetLabel, METH_NOARGS, "DLPack capsule: host label table"},
     {"samgraph_torch_get_graph_input_nodes", GetInputNodes, METH_VARARGS, "DLPack capsule: i32 [num_input]"},

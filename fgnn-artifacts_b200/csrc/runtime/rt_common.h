@@ -157,6 +157,9 @@ using TensorPtr = std::shared_ptr<Tensor>;
 struct TrainGraph {  // common.h:178-186
   TensorPtr row, col, data;
   size_t num_src = 0, num_dst = 0, num_edge = 0;
+  // CSC form of the same block, built on first request by the hand-off (pymodule.cc GetGraphCsc):
+  // indptr u32[num_dst+1], indices u32[num_edge] (aliases `row` when col is already ascending), edge ids
+  TensorPtr csc_indptr, csc_indices, csc_eids;
 };
 
 struct Task {  // common.h:197-217

@@ -78,6 +78,7 @@ _SIGS = {
     "fgnn_k_out_degree": [_vp, _sz, _vp, _sz, _vp],
     "fgnn_k_rank_by_degree": [_vp, _sz, _sz, _vp, _vp, _vp, _sz, _vp],
     "fgnn_k_rank_random": [_sz, _u64, _vp, _vp, _sz, _vp],
+    "fgnn_k_coo_to_csc": [_vp, _vp, _u32, _vp, _u32, C.c_int, _vp, _vp, _vp, _vp, _sz, _vp],
     "fgnn_k_shard_alloc": [C.POINTER(_vp), _sz],
     "fgnn_k_shard_free": [_vp],
     "fgnn_k_ipc_export": [_vp, _vp],
@@ -94,6 +95,7 @@ _SIZE_FNS = {
     "fgnn_k_shuffle_workspace_bytes": [_sz],
     "fgnn_k_alias_table_workspace_bytes": [_sz],
     "fgnn_k_rank_random_workspace_bytes": [_sz],
+    "fgnn_k_coo_to_csc_workspace_bytes": [_u32, _u32],
 }
 
 _lib = None
@@ -310,6 +312,17 @@ def rank_random(num_nodes, seed, rank, workspace=None):
                                 device=rank.device)
     _check(load().fgnn_k_rank_random(num_nodes, seed & 0xFFFFFFFFFFFFFFFF, _ptr(rank), _ptr(workspace),
                                      workspace.numel(), _stream()), "rank_random")
+
+
+def coo_to_csc(row, col, e_max, d_e, num_dst, col_sorted, indptr, indices=None, edge_ids=None, workspace=None):
+    """(row, col) of one sampled layer -> CSC indptr / indices / edge_ids (include/fgnn_kernels.h)."""
+    import torch
+    if not col_sorted and workspace is None and e_max:
+        workspace = torch.empty(int(load().fgnn_k_coo_to_csc_workspace_bytes(e_max, num_dst)), dtype=torch.uint8,
+                                device=indptr.device)
+    _check(load().fgnn_k_coo_to_csc(_ptr(row), _ptr(col), e_max, _ptr(d_e), num_dst, int(bool(col_sorted)),
+                                    _ptr(indptr), _ptr(indices), _ptr(edge_ids), _ptr(workspace),
+                                    workspace.numel() if workspace is not None else 0, _stream()), "coo_to_csc")
 
 
 def shuffle_workspace_bytes(n):

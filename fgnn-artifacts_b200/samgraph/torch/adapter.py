@@ -42,6 +42,14 @@ def get_graph_data(batch_key, layer_idx):
     return _from_dlpack(c_lib.samgraph_torch_get_graph_data(batch_key, layer_idx))
 
 
+def get_graph_csc(batch_key, layer_idx):
+    """(indptr i32[num_dst+1], indices i32[num_edge], edge_ids i32[num_edge] | None) of one layer: the block in the
+    form `create_unitgraph_from_csc` takes (3rdparty/dgl.patch:30-57).  edge_ids is None when the layer is already
+    ordered by destination (khop0/khop2/hash-dedup/random walk): indices then aliases get_graph_row()."""
+    indptr, indices, eids = c_lib.samgraph_torch_get_graph_csc(batch_key, layer_idx)
+    return _from_dlpack(indptr), _from_dlpack(indices), (None if eids is None else _from_dlpack(eids))
+
+
 def get_dataset_feat():
     return _from_dlpack(c_lib.samgraph_torch_get_dataset_feat())
 
@@ -88,6 +96,33 @@ def get_dgl_blocks_with_weights(batch_key, num_layers, with_feat=True):
                                   get_graph_num_src(batch_key, i), get_graph_num_dst(batch_key, i))
         block.edata["weights"] = get_graph_data(batch_key, i)
         blocks.append(block)
+    return blocks, feat, label
+
+
+def _create_dgl_block_csc(batch_key, layer_idx):
+    import dgl
+    from dgl.heterograph import DGLBlock
+    num_src, num_dst = get_graph_num_src(batch_key, layer_idx), get_graph_num_dst(batch_key, layer_idx)
+    indptr, indices, eids = get_graph_csc(batch_key, layer_idx)
+    if eids is None:
+        eids = torch.arange(indices.shape[0], dtype=indices.dtype, device=indices.device)
+    gidx = dgl.heterograph_index.create_unitgraph_from_csc(2, num_src, num_dst, indptr, indices, eids, "csc")
+    return DGLBlock(gidx, (["_N"], ["_N"]), ["_E"])
+
+
+def get_dgl_blocks_csc(batch_key, num_layers, with_feat=True):
+    """get_dgl_blocks with the blocks created straight from CSC (needs the reference's DGL patch): DGL's own
+    COO->CSC conversion — the reference's "convert" stage — disappears from the trainer."""
+    feat, label = _batch_tensors(batch_key, with_feat)
+    return [_create_dgl_block_csc(batch_key, i) for i in range(num_layers)], feat, label
+
+
+def get_csc_blocks(batch_key, num_layers, with_feat=True):
+    """DGL-free CSC hand-off: [(indptr, indices, edge_ids | None, num_src, num_dst)] per layer (e.g. for
+    torch.sparse_csr_tensor / PyG SparseTensor(rowptr=indptr, col=indices))."""
+    feat, label = _batch_tensors(batch_key, with_feat)
+    blocks = [get_graph_csc(batch_key, i) + (get_graph_num_src(batch_key, i), get_graph_num_dst(batch_key, i))
+              for i in range(num_layers)]
     return blocks, feat, label
 
 

@@ -313,6 +313,22 @@ size_t fgnn_k_rank_random_workspace_bytes(size_t num_nodes);
 int fgnn_k_rank_random(size_t num_nodes, uint64_t seed, uint32_t *ranking_nodes, void *workspace,
                        size_t workspace_bytes, fgnn_stream_t stream);
 
+/* ---- block hand-off in CSC form ------------------------------------------ */
+/* (row, col) COO of one sampled layer -> the three arrays of the reference's DGL patch
+ * `create_unitgraph_from_csc` (3rdparty/dgl.patch:30-57), replacing DGL's own COO->CSC conversion of the
+ * block built at samgraph/torch/adapter.py:92-95 (the stage timed as kLogL1ConvertTime):
+ *   indptr   u32[num_dst+1]  indptr[d] = #edges with col < d
+ *   indices  u32[e]          row ids ordered by (col, edge id)   (stable)
+ *   edge_ids u32[e] or NULL  the permutation (original edge index of every CSC entry)
+ * col_sorted != 0: col is non-decreasing (khop0/khop2/hash-dedup/random-walk blocks are seed-major), the
+ * permutation is the identity, no workspace is needed and `indices` may be NULL or == row.
+ * col_sorted == 0: one radix sort over log2(num_dst) key bits; workspace from
+ * fgnn_k_coo_to_csc_workspace_bytes(e_max, num_dst).  *d_e (may be NULL = e_max) is read on the device. */
+size_t fgnn_k_coo_to_csc_workspace_bytes(uint32_t e_max, uint32_t num_dst);
+int fgnn_k_coo_to_csc(const uint32_t *row, const uint32_t *col, uint32_t e_max, const uint32_t *d_e,
+                      uint32_t num_dst, int col_sorted, uint32_t *indptr, uint32_t *indices,
+                      uint32_t *edge_ids, void *workspace, size_t workspace_bytes, fgnn_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -248,6 +248,27 @@ class Oracle:
                                         _p(np.ascontiguousarray(weights, np.float32), f32p), _p(pre, f32p))
         return pre
 
+    # ---- block hand-off ----
+    @staticmethod
+    def coo_to_csc(row, col, num_dst):
+        """CSC arrays of one sampled layer as the reference's DGL patch consumes them
+        (3rdparty/dgl.patch:30-57 create_unitgraph_from_csc(indptr, indices, edge_ids)); the block itself is
+        built from (row, col) = (src, dst) at samgraph/torch/adapter.py:92-95.  Plain counting sort by dst,
+        stable in the edge id — what DGL's COO->CSC conversion produces for these blocks."""
+        row, col = _u32(row), _u32(col)
+        counts = np.zeros(num_dst + 1, np.int64)
+        for c in col:                      # histogram of dst
+            counts[int(c) + 1] += 1
+        indptr = np.cumsum(counts)
+        fill = indptr[:-1].copy()
+        indices = np.empty(len(row), np.uint32)
+        eids = np.empty(len(row), np.uint32)
+        for e in range(len(row)):          # stable placement
+            k = fill[int(col[e])]
+            indices[k], eids[k] = row[e], e
+            fill[int(col[e])] += 1
+        return indptr.astype(np.uint32), indices, eids
+
 
 class OracleHashTable:
     def __init__(self, oracle, max_items):

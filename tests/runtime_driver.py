@@ -21,6 +21,11 @@ def collect(sam, key, L, out, tag, with_data):
         rec["col%d" % i] = sam.get_graph_col(key, i).cpu().numpy()
         if with_data:
             rec["data%d" % i] = sam.get_graph_data(key, i).cpu().numpy()
+        indptr, indices, eids = sam.get_graph_csc(key, i)          # CSC hand-off
+        rec["csc_indptr%d" % i] = indptr.cpu().numpy()
+        rec["csc_indices%d" % i] = indices.cpu().numpy()
+        rec["csc_eids%d" % i] = np.zeros(0, np.int32) if eids is None else eids.cpu().numpy()
+        rec["csc_identity%d" % i] = np.array(eids is None)
         rec["nsrc%d" % i] = np.array(sam.get_graph_num_src(key, i))
         rec["ndst%d" % i] = np.array(sam.get_graph_num_dst(key, i))
     rec["feat"] = sam.get_graph_feat(key).cpu().numpy()

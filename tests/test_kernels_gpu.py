@@ -602,3 +602,52 @@ def test_epoch_shuffle_matches_oracle(K, oracle, n):
         assert np.array_equal(np.sort(got), np.sort(train))          # a permutation
     if n > 1000:
         assert not np.array_equal(oracle.shuffle(train, SEED, 0), oracle.shuffle(train, SEED, 3))
+
+
+# ---------------------------------------------------------------------------------------------
+# CSC hand-off: indptr / indices / edge ids of one block == stable counting sort by dst
+# ---------------------------------------------------------------------------------------------
+def _csc_expected(row, col, num_dst):
+    perm = np.argsort(col, kind="stable").astype(np.uint32)
+    indptr = np.searchsorted(col[perm], np.arange(num_dst + 1), side="left").astype(np.uint32)
+    return indptr, row[perm], perm
+
+
+@pytest.mark.parametrize("e,num_dst,num_src,sorted_col,live", [
+    (0, 0, 0, True, None), (0, 7, 5, False, None), (1, 1, 1, True, None), (1, 4, 9, False, None),
+    (1000, 64, 500, True, None), (1000, 64, 500, False, None), (5000, 5000, 777, False, 3100),
+    (5000, 300, 777, True, 1), (70000, 8000, 60000, True, 65537), (70000, 8000, 60000, False, None),
+    (1 << 20, 88000, 550000, False, (1 << 20) - 12345), (1 << 20, 88000, 550000, True, None)])
+def test_coo_to_csc_matches_oracle(K, oracle, e, num_dst, num_src, sorted_col, live):
+    rng = np.random.default_rng(e * 31 + num_dst)
+    n_live = e if live is None else live
+    col = rng.integers(0, max(num_dst, 1), size=e).astype(np.uint32)      # some dst nodes get no edge at all
+    if num_dst > 3:
+        col[col == num_dst - 1] = 0                                        # the last dst is always empty
+    if sorted_col:
+        col[:n_live] = np.sort(col[:n_live])
+    row = rng.integers(0, max(num_src, 1), size=e).astype(np.uint32)
+    d_row, d_col = dev(row), dev(col)
+    d_e = None if live is None else dev(np.array([n_live], np.uint32))
+    indptr = torch.full((num_dst + 1,), -1, dtype=torch.int32, device="cuda")
+    indices = torch.full((max(e, 1),), -1, dtype=torch.int32, device="cuda")
+    eids = torch.full((max(e, 1),), -1, dtype=torch.int32, device="cuda")
+    K.coo_to_csc(d_row, d_col, e, d_e, num_dst, sorted_col, indptr, indices, eids)
+    torch.cuda.synchronize()
+    exp_indptr, exp_indices, exp_eids = _csc_expected(row[:n_live], col[:n_live], num_dst)
+    if n_live <= 5000:   # the oracle's plain counting sort (python loops) pins the vectorised expectation
+        o_indptr, o_indices, o_eids = oracle.coo_to_csc(row[:n_live], col[:n_live], num_dst)
+        assert np.array_equal(o_indptr, exp_indptr) and np.array_equal(o_indices, exp_indices)
+        assert np.array_equal(o_eids, exp_eids)
+    assert np.array_equal(host(indptr), exp_indptr)
+    assert np.array_equal(host(indices, n_live), exp_indices)
+    assert np.array_equal(host(eids, n_live), exp_eids)
+    if sorted_col:
+        assert np.array_equal(exp_eids, np.arange(n_live, dtype=np.uint32))
+        # zero-copy form used by the runtime: no indices / edge ids asked for, no workspace
+        indptr2 = torch.full((num_dst + 1,), -1, dtype=torch.int32, device="cuda")
+        K.coo_to_csc(d_row, d_col, e, d_e, num_dst, True, indptr2)
+        torch.cuda.synchronize()
+        assert np.array_equal(host(indptr2), exp_indptr)
+    if e > n_live:        # nothing is written past the live count
+        assert (host(indices)[n_live:e] == 0xFFFFFFFF).all() and (host(eids)[n_live:e] == 0xFFFFFFFF).all()

@@ -291,3 +291,25 @@ def test_live_reference_agrees(oracle, ref):
     feat = rng.standard_normal((V, 9)).astype(np.float32)
     assert np.array_equal(ref.extract(feat, ids), oracle.extract(feat, ids))
     assert ref.predict_num_nodes(8000, [15, 10, 5]) == oracle.predict_num_nodes(8000, [15, 10, 5])
+
+
+def test_coo_to_csc_oracle_is_scipy_csc(oracle):
+    """Block hand-off: the oracle's counting sort by dst == scipy's COO->CSC of the same block
+    (DGL's conversion of the block built at adapter.py:92-95), with edge ids as the data to expose the order."""
+    sp = pytest.importorskip("scipy.sparse")
+    rng = np.random.default_rng(5)
+    for e, num_src, num_dst in [(0, 3, 4), (1, 1, 1), (500, 40, 30), (3000, 1000, 512)]:
+        row = rng.integers(0, num_src, size=e).astype(np.uint32)
+        col = rng.integers(0, num_dst, size=e).astype(np.uint32)
+        indptr, indices, eids = oracle.coo_to_csc(row, col, num_dst)
+        assert indptr[0] == 0 and indptr[-1] == e and len(indptr) == num_dst + 1
+        assert np.array_equal(col[eids], np.repeat(np.arange(num_dst), np.diff(indptr.astype(np.int64))))
+        assert np.array_equal(row[eids], indices)
+        for d in range(num_dst):                       # stable: edge ids ascend inside every column
+            seg = eids[indptr[d]:indptr[d + 1]].astype(np.int64)
+            assert (np.diff(seg) > 0).all()
+        # scipy sums duplicates, so compare the structure through per-(src,dst) multiplicities
+        a = sp.coo_matrix((np.ones(e), (row, col)), shape=(num_src, num_dst)).tocsc()
+        b = sp.csc_matrix((np.ones(e), indices.astype(np.int64), indptr.astype(np.int64)), shape=(num_src, num_dst))
+        b.sum_duplicates()
+        assert (a != b).nnz == 0

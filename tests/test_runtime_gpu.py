@@ -80,6 +80,15 @@ def check_batches(oracle, ds, cfg, data, num_step, keys=None):
             assert int(data[pre + "nsrc%d" % i]) == e["num_src"] and int(data[pre + "ndst%d" % i]) == e["num_dst"]
             if rw:
                 assert np.array_equal(data[pre + "data%d" % i].view(np.uint32), e["data"])
+            # CSC hand-off: indptr / indices / edge ids == stable counting sort of the block by dst
+            indptr, indices, eids = oracle.coo_to_csc(e["row"], e["col"], e["num_dst"])
+            assert np.array_equal(data[pre + "csc_indptr%d" % i].view(np.uint32), indptr)
+            assert np.array_equal(data[pre + "csc_indices%d" % i].view(np.uint32), indices)
+            if bool(data[pre + "csc_identity%d" % i]):
+                assert np.array_equal(eids, np.arange(len(eids), dtype=np.uint32))
+                assert stype in ("khop0", "khop2", "weighted_khop_hash_dedup", "random_walk") or len(eids) == 0
+            else:
+                assert np.array_equal(data[pre + "csc_eids%d" % i].view(np.uint32), eids)
         # extraction: bit-exact rows of the host feature table / labels (CPUExtract semantics)
         assert np.array_equal(data[pre + "feat"].view(np.uint32), oracle.extract(ds["feat"], exp["input_nodes"]).view(np.uint32))
         assert np.array_equal(data[pre + "label"], ds["label"][seeds])
