@@ -68,11 +68,8 @@ struct SlotHeader {
 };
 
 struct SharedRing {
-  pthread_mutex_t mu;
-  sem_t free_slots, used_slots;
+  RingCtl ctl;  // ticket protocol: rt_ring.h
   pthread_barrier_t sampler_barrier, trainer_barrier;
-  uint64_t head, tail;
-  uint32_t num_slots;
   uint64_t slot_bytes;
   uint64_t ranking_off, slots_off;
   std::atomic<uint32_t> presample_done;
@@ -86,8 +83,11 @@ struct SharedRing {
   unsigned char devq_handle[16][FGNN_IPC_HANDLE_BYTES];
   char *base() { return reinterpret_cast<char *>(this); }
   IdType *ranking() { return reinterpret_cast<IdType *>(base() + ranking_off); }
-  char *slot(uint64_t i) { return base() + slots_off + (i % num_slots) * slot_bytes; }
+  char *slot(uint64_t i) { return base() + slots_off + (i % ctl.num_slots) * slot_bytes; }
+  std::atomic<uint32_t> *ready_of(uint64_t i);
 };
+
+std::atomic<uint32_t> *SharedRing::ready_of(uint64_t i) { return &reinterpret_cast<SlotHeader *>(slot(i))->ready; }
 
 // =============================================================================================
 // Sampler: DoShuffle + DoGPUSample (cuda_loops.cc:30-267 == dist_loops.cc:35-269)
@@ -830,19 +830,12 @@ void Engine::CreateSharedState() {  // dist_engine.cc:115-153 + memory_queue.cc:
   shared_base_ = mmap(nullptr, shared_bytes_, PROT_READ | PROT_WRITE, MAP_SHARED | MAP_ANONYMOUS, -1, 0);
   FCHECK(shared_base_ != MAP_FAILED) << "mmap of the shared queue failed";
   ring_ = new (shared_base_) SharedRing();
-  pthread_mutexattr_t ma;
-  pthread_mutexattr_init(&ma);
-  pthread_mutexattr_setpshared(&ma, PTHREAD_PROCESS_SHARED);
-  pthread_mutex_init(&ring_->mu, &ma);
-  sem_init(&ring_->free_slots, 1, nslots);
-  sem_init(&ring_->used_slots, 1, 0);
+  RingInit(&ring_->ctl, nslots, /*process_shared=*/true);
   pthread_barrierattr_t ba;
   pthread_barrierattr_init(&ba);
   pthread_barrierattr_setpshared(&ba, PTHREAD_PROCESS_SHARED);
   pthread_barrier_init(&ring_->sampler_barrier, &ba, (unsigned)rc.num_sample_worker);
   pthread_barrier_init(&ring_->trainer_barrier, &ba, (unsigned)rc.num_train_worker);
-  ring_->head = ring_->tail = 0;
-  ring_->num_slots = nslots;
   ring_->slot_bytes = slot;
   ring_->ranking_off = hdr;
   ring_->slots_off = hdr + rank_bytes;
@@ -1053,7 +1046,7 @@ void Engine::TrainInit(int worker_id, Context ctx) {  // dist_engine.cc:366-465
   if (ring_->devq_enabled) {
     const uint32_t Tq = ring_->devq_trainers;
     FCHECK_LT((uint32_t)worker_id, Tq);
-    const uint32_t mine = ring_->num_slots > (uint32_t)worker_id ? (ring_->num_slots - worker_id + Tq - 1) / Tq : 0;
+    const uint32_t mine = ring_->ctl.num_slots > (uint32_t)worker_id ? (ring_->ctl.num_slots - worker_id + Tq - 1) / Tq : 0;
     devq_base_.assign(Tq, nullptr);
     FGNN_CALL(fgnn_k_shard_alloc((void **)&devq_base_[worker_id], std::max<size_t>(mine, 1) * ring_->slot_bytes));
     FGNN_CALL(fgnn_k_ipc_export(devq_base_[worker_id], ring_->devq_handle[worker_id]));
@@ -1072,7 +1065,7 @@ void Engine::TrainInit(int worker_id, Context ctx) {  // dist_engine.cc:366-465
 char *Engine::DevSlot(uint64_t idx) {
   const uint32_t Tq = ring_->devq_trainers;
   if (devq_base_.empty()) devq_base_.assign(Tq, nullptr);
-  const uint64_t s = idx % ring_->num_slots;
+  const uint64_t s = idx % ring_->ctl.num_slots;
   const uint32_t t = (uint32_t)(s % Tq);
   if (!devq_base_[t]) {
     while (ring_->devq_ready[t].load(std::memory_order_acquire) == 0) {
@@ -1090,10 +1083,9 @@ char *Engine::DevSlot(uint64_t idx) {
 // memory; payload either next to it (host bounce, the reference's path) or in the trainers' HBM (device queue). ----
 void Engine::SendTask(const TaskPtr &t) {
   Timer ts;
-  sem_wait(&ring_->free_slots);
-  pthread_mutex_lock(&ring_->mu);
-  const uint64_t idx = ring_->tail++;
-  pthread_mutex_unlock(&ring_->mu);
+  uint64_t idx = 0;
+  auto ready_of = [this](uint64_t i) { return ring_->ready_of(i); };
+  if (!RingBeginWrite(&ring_->ctl, ready_of, &stop_, &idx)) return;  // shutting down
   char *slot = ring_->slot(idx);
   SlotHeader *h = reinterpret_cast<SlotHeader *>(slot);
   CUDA_CALL(cudaSetDevice(sampler_->device()));
@@ -1130,8 +1122,7 @@ void Engine::SendTask(const TaskPtr &t) {
     put(t->graphs[i].data);
   }
   CUDA_CALL(cudaStreamSynchronize(st));
-  h->ready.store(1, std::memory_order_release);
-  sem_post(&ring_->used_slots);
+  RingEndWrite(&ring_->ctl, &h->ready);
   (void)sent_bytes;
   Profiler::Get().LogStep(t->key, kLogL1SendTime, ts.Passed());
   Profiler::Get().LogEpochAdd(t->key, kLogEpochSampleSendTime, ts.Passed());
@@ -1139,16 +1130,11 @@ void Engine::SendTask(const TaskPtr &t) {
 
 TaskPtr Engine::RecvTask(bool block) {
   Timer tr;
-  while (sem_trywait(&ring_->used_slots) != 0) {
-    if (stop_ || !block) return nullptr;
-    std::this_thread::sleep_for(std::chrono::microseconds(1));
-  }
-  pthread_mutex_lock(&ring_->mu);
-  const uint64_t idx = ring_->head++;
-  pthread_mutex_unlock(&ring_->mu);
+  uint64_t idx = 0;
+  auto ready_of = [this](uint64_t i) { return ring_->ready_of(i); };
+  if (!RingBeginRead(&ring_->ctl, ready_of, &stop_, block, &idx)) return nullptr;
   char *slot = ring_->slot(idx);
   SlotHeader *h = reinterpret_cast<SlotHeader *>(slot);
-  while (h->ready.load(std::memory_order_acquire) == 0) std::this_thread::sleep_for(std::chrono::microseconds(1));
   const int dev = extractor_->device();
   cudaStream_t st = extractor_->stream();
   CUDA_CALL(cudaSetDevice(dev));
@@ -1176,8 +1162,7 @@ TaskPtr Engine::RecvTask(bool block) {
     if (h->have_data) g.data = get(g.num_edge, "train_graph.data");
   }
   CUDA_CALL(cudaStreamSynchronize(st));
-  h->ready.store(0, std::memory_order_release);
-  sem_post(&ring_->free_slots);
+  RingEndRead(&ring_->ctl, &h->ready);
   Profiler::Get().LogStep(task->key, kLogL1RecvTime, tr.Passed());
   return task;
 }

@@ -16,6 +16,7 @@
 
 #include "rt_common.h"
 #include "rt_profiler.h"
+#include "rt_ring.h"
 
 extern "C" void fgnn_rt_step_split(size_t num_step, size_t num_worker, size_t worker_id, size_t *begin,
                                    size_t *count);

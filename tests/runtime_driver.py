@@ -70,7 +70,7 @@ def run_arch5(sc, out_path):
     sam.config(cfg)
     sam.data_init()
     ctx = mp.get_context("fork")
-    barrier = ctx.Barrier(S + T, timeout=120)
+    barrier = ctx.Barrier(S + T, timeout=90)
     L = cfg.get("num_layer", cfg.get("num_fanout", 0))
     num_epoch, num_step = sam.num_epoch(), sam.steps_per_epoch()
 
@@ -105,9 +105,14 @@ def run_arch5(sc, out_path):
             [ctx.Process(target=trainer, args=(i,)) for i in range(T)]
     for p in procs:
         p.start()
+    import time
     bad = 0
+    deadline = time.time() + 150          # a wedged queue must not eat the GPU budget: kill the stragglers
     for p in procs:
-        p.join(300)
+        p.join(max(1.0, deadline - time.time()))
+        if p.is_alive():
+            p.kill()
+            p.join(10)
         bad |= (p.exitcode != 0)
     np.savez(out_path, num_step=np.array(num_step), num_epoch=np.array(num_epoch), bad=np.array(int(bad)))
     sys.exit(1 if bad else 0)

@@ -50,7 +50,7 @@ def run_driver(tmp_path, scenario):
     env = dict(os.environ, SAMGRAPH_LOG_LEVEL="warn")
     env.update(scenario.get("env", {}))
     r = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "runtime_driver.py"), sc_path, out],
-                       capture_output=True, text=True, timeout=600, env=env)
+                       capture_output=True, text=True, timeout=300, env=env)
     assert r.returncode == 0, "driver failed:\n%s\n%s" % (r.stdout[-3000:], r.stderr[-3000:])
     return out
 
