@@ -71,6 +71,8 @@ class ClockSampler:
         self.f = None
         self.thread = None
         self.stop_flag = False
+        self.recording = False       # samples are kept only between begin() and stop(): the timed region
+        self.nv = self.h = None
         self.sm, self.mx, self.reasons = [], [], set()
 
     def _nvml_handle(self):
@@ -83,27 +85,35 @@ class ClockSampler:
         except Exception:
             return pynvml, pynvml.nvmlDeviceGetHandleByIndex(self.idx)
 
-    def _loop(self, nv, h):
-        get_reasons = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or \
-            getattr(nv, "nvmlDeviceGetCurrentClocksThrottleReasons")
-        mx = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
+    def _sample(self, nv, h, mx):
+        try:
+            sm = float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM))
+            get_reasons = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or \
+                getattr(nv, "nvmlDeviceGetCurrentClocksThrottleReasons")
+            r = int(get_reasons(h))
+        except Exception:
+            return
+        self.sm.append(sm)
+        self.mx.append(float(mx))
+        for bit, name in self.REASONS:
+            if r & bit:
+                self.reasons.add(name)
+
+    def _loop(self, nv, h, mx):
         while not self.stop_flag:
-            try:
-                self.sm.append(float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)))
-                self.mx.append(float(mx))
-                r = int(get_reasons(h))
-                for bit, name in self.REASONS:
-                    if r & bit:
-                        self.reasons.add(name)
-            except Exception:
-                pass
-            time.sleep(0.005)
+            if self.recording:
+                self._sample(nv, h, mx)
+            time.sleep(0.005 if self.recording else 0.001)
 
     def start(self):
+        """Bring the sampler up (NVML init + thread start take tens of ms: do it before the timed region);
+        nothing is recorded until begin()."""
         try:
             import threading
             nv, h = self._nvml_handle()
-            self.thread = threading.Thread(target=self._loop, args=(nv, h), daemon=True)
+            mx = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
+            self.nv, self.h, self.mx_clock = nv, h, mx
+            self.thread = threading.Thread(target=self._loop, args=(nv, h, mx), daemon=True)
             self.thread.start()
             return
         except Exception:
@@ -116,13 +126,36 @@ class ClockSampler:
         except Exception:
             self.p = None
 
+    def begin(self):
+        self.recording = True
+
+    def _one_shot_smi(self):
+        try:
+            r = subprocess.run(["nvidia-smi", "-i", str(self.idx), "--query-gpu=" + self.QUERY,
+                                "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=10)
+            c = [x.strip() for x in r.stdout.strip().splitlines()[0].split(",")]
+            self.sm.append(float(c[1]))
+            self.mx.append(float(c[2]))
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), c[5:9]):
+                if v.lower().startswith("active"):
+                    self.reasons.add(name)
+        except Exception:
+            pass
+
     def stop(self):
         if self.thread is not None:
+            if not self.sm:      # region shorter than one period: one sample right at its end, still under load
+                self._sample(self.nv, self.h, self.mx_clock)
+            self.recording = False
             self.stop_flag = True
             self.thread.join(timeout=2)
+            source = "nvml, 5 ms period, timed region only"
+            if not self.sm:      # NVML gave nothing: one nvidia-smi query, taken right after the region
+                self._one_shot_smi()
+                source = "nvidia-smi, one query at the end of the timed region"
             return {"sm_mhz": statistics.median(self.sm) if self.sm else None,
                     "sm_max_mhz": max(self.mx) if self.mx else None, "reasons": sorted(self.reasons),
-                    "samples": len(self.sm), "source": "nvml, 5 ms period, timed region only"}
+                    "samples": len(self.sm), "source": source}
         if self.p is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         time.sleep(0.15)
@@ -335,11 +368,12 @@ def run_ours(args):
         torch.cuda.synchronize()
         hp.stats.zero_()
         torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
         clocks = ClockSampler(local)
         clocks.start()
+        if world > 1:
+            dist.barrier()
         launches0 = K.launch_count()
+        clocks.begin()
         torch.cuda.synchronize()
         t_start = torch.cuda.Event(enable_timing=True)
         t_end = torch.cuda.Event(enable_timing=True)
