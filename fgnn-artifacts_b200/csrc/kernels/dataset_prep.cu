@@ -68,7 +68,7 @@ alias_table_kernel(const uint32_t *__restrict__ indptr, const uint32_t *__restri
     for (uint32_t i = 0; i < len; ++i) {                                                // :128-141
       const float x = __fmul_rn(__fdiv_rn(weights[off + i], sum), flen);
       w[i] = x;
-      al[i] = nb[i];  // entries whose prob ends at 1 never use their alias; keep it a valid neighbour
+      al[i] = 0;  // entries whose prob ends at 1 keep the reference's zero-initialised alias (create_alias_table.cc:210)
       if (x < 1.0f) { smalls[sn++] = i; } else { larges[ln++] = i; }
     }
     uint32_t st = sn == len ? 0 : sn, lt = ln == len ? 0 : ln;  // ring tails

@@ -789,9 +789,10 @@ void Engine::LoadDataset() {  // engine.cc:73-264
       case kCacheByPreSample: break;
       default: FCHECK(false) << "cache policy " << rc.cache_policy << " is outside the hot-path scope";
     }
-    // cache_by_degree / cache_by_random: when the offline tool's file is absent the ranking is computed on the
+    // cache_by_degree / cache_by_random / cache_by_heuristic: when the offline tool's file is absent the ranking is computed on the
     // sampler GPU at init (Engine::DoGpuRanking); the other file-based policies need their file
-    const bool on_gpu_ok = rc.cache_policy == kCacheByDegree || rc.cache_policy == kCacheByRandom;
+    const bool on_gpu_ok = rc.cache_policy == kCacheByDegree || rc.cache_policy == kCacheByRandom ||
+                           rc.cache_policy == kCacheByHeuristic;
     if (f && (FileExists(path + f) || !on_gpu_ok))
       ds->ranking_nodes = Tensor::FromMmap(path + f, kI32, {ds->num_node}, "dataset.ranking_nodes");
   }
@@ -952,7 +953,7 @@ void Engine::DoPreSample() {
   Profiler::Get().Reset(num_epoch_, num_step_);
 }
 
-// cache_by_degree.cc:36-58 / cache_by_random.cc:36-48 on the sampler GPU, for datasets that ship without the
+// cache_by_degree.cc:36-58 / cache_by_random.cc:36-48 / cache_by_heuristic.cc:28-91 on the sampler GPU, for datasets that ship without the
 // offline tool's ranking file: out-degree histogram of the CSR + the PreSC {key,id} descending sort, or a seeded
 // permutation.  Published exactly like the PreSC ranking.
 void Engine::DoGpuRanking() {
@@ -967,6 +968,22 @@ void Engine::DoGpuRanking() {
     auto ws = Tensor::Device(kU8, {fgnn_k_presc_rank_workspace_bytes(V)}, s->device(), s->stream(), "rank_ws");
     FGNN_CALL(fgnn_k_rank_by_degree(s->d_indices(), E, V, (uint32_t *)deg->data, (uint32_t *)rank->data, ws->data,
                                     ws->nbytes, (fgnn_stream_t)s->stream()));
+    CUDA_CALL(cudaStreamSynchronize(s->stream()));
+  } else if (rc.cache_policy == kCacheByHeuristic) {  // cache_by_heuristic.cc:28-91
+    const size_t T = dataset_->train_set->NumItems();
+    auto train = Tensor::Device(kI32, {T}, s->device(), s->stream(), "train_set");
+    auto total = Tensor::Device(kI64, {1}, s->device(), s->stream(), "num_neighbours");
+    CUDA_CALL(cudaMemcpyAsync(train->data, dataset_->train_set->data, T * 4, cudaMemcpyDefault, s->stream()));
+    FGNN_CALL(fgnn_k_row_len_sum(s->d_indptr(), (const uint32_t *)train->data, T, (unsigned long long *)total->data,
+                                 (fgnn_stream_t)s->stream()));
+    unsigned long long n_nbr = 0;
+    CUDA_CALL(cudaMemcpyAsync(&n_nbr, total->data, 8, cudaMemcpyDeviceToHost, s->stream()));
+    CUDA_CALL(cudaStreamSynchronize(s->stream()));
+    auto ws = Tensor::Device(kU8, {fgnn_k_rank_heuristic_workspace_bytes(V, T, (size_t)n_nbr)}, s->device(),
+                             s->stream(), "rank_ws");
+    FGNN_CALL(fgnn_k_rank_by_heuristic(s->d_indptr(), s->d_indices(), V, E, (const uint32_t *)train->data, T,
+                                       (size_t)n_nbr, (uint32_t *)rank->data, ws->data, ws->nbytes,
+                                       (fgnn_stream_t)s->stream()));
     CUDA_CALL(cudaStreamSynchronize(s->stream()));
   } else {
     FCHECK(rc.cache_policy == kCacheByRandom) << "cache policy " << rc.cache_policy << " needs its ranking file";

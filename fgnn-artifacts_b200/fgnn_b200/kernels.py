@@ -78,6 +78,8 @@ _SIGS = {
     "fgnn_k_out_degree": [_vp, _sz, _vp, _sz, _vp],
     "fgnn_k_rank_by_degree": [_vp, _sz, _sz, _vp, _vp, _vp, _sz, _vp],
     "fgnn_k_rank_random": [_sz, _u64, _vp, _vp, _sz, _vp],
+    "fgnn_k_row_len_sum": [_vp, _vp, _sz, _vp, _vp],
+    "fgnn_k_rank_by_heuristic": [_vp, _vp, _sz, _sz, _vp, _sz, _sz, _vp, _vp, _sz, _vp],
     "fgnn_k_coo_to_csc": [_vp, _vp, _u32, _vp, _u32, C.c_int, _vp, _vp, _vp, _vp, _sz, _vp],
     "fgnn_k_shard_alloc": [C.POINTER(_vp), _sz],
     "fgnn_k_shard_free": [_vp],
@@ -96,6 +98,7 @@ _SIZE_FNS = {
     "fgnn_k_alias_table_workspace_bytes": [_sz],
     "fgnn_k_rank_random_workspace_bytes": [_sz],
     "fgnn_k_coo_to_csc_workspace_bytes": [_u32, _u32],
+    "fgnn_k_rank_heuristic_workspace_bytes": [_sz, _sz, _sz],
 }
 
 _lib = None
@@ -312,6 +315,20 @@ def rank_random(num_nodes, seed, rank, workspace=None):
                                 device=rank.device)
     _check(load().fgnn_k_rank_random(num_nodes, seed & 0xFFFFFFFFFFFFFFFF, _ptr(rank), _ptr(workspace),
                                      workspace.numel(), _stream()), "rank_random")
+
+
+def rank_by_heuristic(indptr, indices, num_nodes, num_edges, train_set, num_train, rank):
+    """cache_by_heuristic ranking on the GPU; one host read-back (the neighbour count) sizes the workspace."""
+    import torch
+    total = torch.zeros(1, dtype=torch.int64, device=rank.device)
+    _check(load().fgnn_k_row_len_sum(_ptr(indptr), _ptr(train_set), num_train, _ptr(total), _stream()), "row_len_sum")
+    n_nbr = int(total.item())
+    ws = torch.empty(int(load().fgnn_k_rank_heuristic_workspace_bytes(num_nodes, num_train, n_nbr)),
+                     dtype=torch.uint8, device=rank.device)
+    _check(load().fgnn_k_rank_by_heuristic(_ptr(indptr), _ptr(indices), num_nodes, num_edges, _ptr(train_set),
+                                           num_train, n_nbr, _ptr(rank), _ptr(ws), ws.numel(), _stream()),
+           "rank_by_heuristic")
+    return n_nbr
 
 
 def coo_to_csc(row, col, e_max, d_e, num_dst, col_sorted, indptr, indices=None, edge_ids=None, workspace=None):

@@ -313,6 +313,19 @@ size_t fgnn_k_rank_random_workspace_bytes(size_t num_nodes);
 int fgnn_k_rank_random(size_t num_nodes, uint64_t seed, uint32_t *ranking_nodes, void *workspace,
                        size_t workspace_bytes, fgnn_stream_t stream);
 
+/* cache_by_heuristic ranking (toolkit/cache/cache_by_heuristic.cc:28-91): training nodes, then their first-hop
+ * neighbours in order of first appearance, then everything else by {out_degree, id} descending.  Built from the
+ * sampler's own ordered hash table + the cache_by_degree ranking + the stable split of fgnn_k_cache_split.
+ * num_neighbours = sum of the train nodes' row lengths (fgnn_k_row_len_sum writes it to *d_total on the device;
+ * the caller reads it back once to size the workspace); train_set must not contain duplicates. */
+int fgnn_k_row_len_sum(const uint32_t *indptr, const uint32_t *nodes, size_t n,
+                       unsigned long long *d_total, fgnn_stream_t stream);
+size_t fgnn_k_rank_heuristic_workspace_bytes(size_t num_nodes, size_t num_train, size_t num_neighbours);
+int fgnn_k_rank_by_heuristic(const uint32_t *indptr, const uint32_t *indices, size_t num_nodes,
+                             size_t num_edges, const uint32_t *train_set, size_t num_train,
+                             size_t num_neighbours, uint32_t *ranking_nodes, void *workspace,
+                             size_t workspace_bytes, fgnn_stream_t stream);
+
 /* ---- block hand-off in CSC form ------------------------------------------ */
 /* (row, col) COO of one sampled layer -> the three arrays of the reference's DGL patch
  * `create_unitgraph_from_csc` (3rdparty/dgl.patch:30-57), replacing DGL's own COO->CSC conversion of the

@@ -611,7 +611,7 @@ void fgo_build_alias_table(const uint32_t *indptr, const uint32_t *indices,
     for (uint32_t i = 0; i < len; ++i) { w[i] = weights[off + i]; sum += w[i]; }
     for (uint32_t i = 0; i < len; ++i) { w[i] /= sum; w[i] *= (float)len; }
     for (uint32_t i = 0; i < len; ++i) {
-      alias_table[off + i] = indices[off + i];
+      alias_table[off + i] = 0; /* std::vector<uint32_t> alias_table(num_edges): stays 0 where prob ends at 1 */
       if (w[i] < 1.0) smalls[st++] = i; else larges[lt++] = i;
     }
     while (sh < st && lh < lt) { /* create_alias_table.cc:145-161 */

@@ -248,6 +248,34 @@ class Oracle:
                                         _p(np.ascontiguousarray(weights, np.float32), f32p), _p(pre, f32p))
         return pre
 
+    # ---- cache rankings of the offline tools ----
+    def rank_by_degree(self, indptr, indices):
+        """toolkit/cache/cache_by_degree.cc:29-62: sort {out_degree, id} pairs descending (ties: larger id first);
+        out_degree[v] = occurrences of v in `indices` (common/graph_loader.cc:109-147)."""
+        V = len(indptr) - 1
+        return self.presc_rank(np.bincount(_u32(indices), minlength=V).astype(np.uint32))
+
+    def rank_by_heuristic(self, indptr, indices, train_set):
+        """toolkit/cache/cache_by_heuristic.cc:28-91: (1) the training nodes in train_set order, (2) their first-hop
+        neighbours in order of first appearance (train_set order, CSR order inside a row), (3) every other vertex
+        by {out_degree, id} descending."""
+        V = len(indptr) - 1
+        added = np.zeros(V, bool)
+        rank = []
+        for t in _u32(train_set):
+            rank.append(int(t))
+            added[t] = True                       # (the tool assumes train_set has no duplicates)
+        for t in _u32(train_set):
+            for nb in indices[indptr[t]:indptr[t + 1]]:
+                if not added[nb]:
+                    rank.append(int(nb))
+                    added[nb] = True
+        for v in self.rank_by_degree(indptr, indices):
+            if not added[v]:
+                rank.append(int(v))
+                added[v] = True
+        return np.array(rank, np.uint32)
+
     # ---- block hand-off ----
     @staticmethod
     def coo_to_csc(row, col, num_dst):

@@ -100,3 +100,47 @@ def test_random_ranking_is_a_seeded_permutation(K, V):
     if V > 100:
         assert not np.array_equal(host(a), host(c))
         assert not np.array_equal(host(a), np.arange(V, dtype=np.uint32))
+
+
+# ---------------------------------------------------------------------------------------------
+# cache_by_heuristic ranking (toolkit/cache/cache_by_heuristic.cc:28-91)
+# ---------------------------------------------------------------------------------------------
+def run_heuristic(K, indptr, indices, train):
+    V, E = len(indptr) - 1, len(indices)
+    rank = torch.full((V,), -1, dtype=torch.int32, device="cuda")
+    n_nbr = K.rank_by_heuristic(dev(indptr), dev(indices), V, E, dev(train), len(train), rank)
+    torch.cuda.synchronize()
+    assert n_nbr == int(np.diff(indptr.astype(np.int64))[train].sum())
+    return host(rank)
+
+
+def test_heuristic_ranking_matches_reference_tool_fixture(K, oracle):
+    """Same dataset the reference's own cache-by-heuristic binary was run on (tests/golden/make_golden_tools.py)."""
+    import os
+    from fgnn_b200.synth import make_dataset_numpy
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ref_tools_golden.npz"))
+    ds = make_dataset_numpy(tuple(int(x) for x in g["spec"]), seed=int(g["seed"]))
+    assert int(ds["indices"].astype(np.int64).sum()) == int(g["indices_sum"])
+    got = run_heuristic(K, ds["indptr"], ds["indices"], ds["train_set"])
+    assert np.array_equal(got, g["cache_by_heuristic"])
+    # and the degree ranking of the same fixture
+    V, E = len(ds["indptr"]) - 1, len(ds["indices"])
+    deg = torch.empty(V, dtype=torch.int32, device="cuda")
+    rank = torch.empty(V, dtype=torch.int32, device="cuda")
+    ws = torch.empty(K.presc_rank_workspace_bytes(V), dtype=torch.uint8, device="cuda")
+    K.rank_by_degree(dev(ds["indices"]), E, V, deg, rank, ws)
+    torch.cuda.synchronize()
+    assert np.array_equal(host(rank), g["cache_by_degree"])
+
+
+@pytest.mark.parametrize("graph,n_train", [("small", 0), ("small", 1), ("small", 300), ("medium", 5000),
+                                           ("medium", 1 << 16)])
+def test_heuristic_ranking_matches_oracle(K, oracle, gs, gm, graph, n_train):
+    g = gs if graph == "small" else gm
+    V = len(g.indptr_np) - 1
+    train = np.random.default_rng(n_train + 7).permutation(V)[:n_train].astype(np.uint32)
+    got = run_heuristic(K, g.indptr_np, g.indices_np, train)
+    exp = oracle.rank_by_heuristic(g.indptr_np, g.indices_np, train)
+    assert np.array_equal(got, exp)
+    assert np.array_equal(np.sort(got), np.arange(V, dtype=np.uint32))      # a permutation of the vertices
+    assert np.array_equal(got[:n_train], train)                              # training nodes first, in order

@@ -313,3 +313,50 @@ def test_coo_to_csc_oracle_is_scipy_csc(oracle):
         b = sp.csc_matrix((np.ones(e), indices.astype(np.int64), indptr.astype(np.int64)), shape=(num_src, num_dst))
         b.sum_duplicates()
         assert (a != b).nnz == 0
+
+
+# ---------------------------------------------------------------------------------------------
+# dataset tools: the oracle's restatements vs the REFERENCE's own offline tools (fixture generated by
+# tests/golden/make_golden_tools.py from utility/data-process/toolkit/*, compiled in place)
+# ---------------------------------------------------------------------------------------------
+@pytest.fixture(scope="module")
+def tools_golden():
+    import os
+    from fgnn_b200.synth import make_dataset_numpy
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ref_tools_golden.npz"))
+    ds = make_dataset_numpy(tuple(int(x) for x in g["spec"]), seed=int(g["seed"]))
+    # the fixture is only meaningful for the dataset it was generated from
+    assert int(ds["indptr"].astype(np.int64).sum()) == int(g["indptr_sum"])
+    assert int(ds["indices"].astype(np.int64).sum()) == int(g["indices_sum"])
+    assert int(ds["train_set"].astype(np.int64).sum()) == int(g["train_sum"])
+    return g, ds
+
+
+def policy_weights(ds, policy):
+    """create_alias_table.cc:75-92 / create_prob_prefix_table.cc:73-90 (src = the neighbour, indices[off+i])."""
+    V = len(ds["indptr"]) - 1
+    outdeg = np.bincount(ds["indices"], minlength=V)
+    if policy == "kInverseSrcDegreeRand":
+        return (1.0 / outdeg[ds["indices"]].astype(np.float64)).astype(np.float32)     # `return 1.0 / src_out_deg;` -> float
+    return np.where(outdeg[ds["indices"]] < 10, 100.0, 1.0).astype(np.float32)         # kSrcSuffix
+
+
+@pytest.mark.parametrize("policy", ["kInverseSrcDegreeRand", "kSrcSuffix"])
+def test_weight_tables_match_reference_tools(oracle, tools_golden, policy):
+    g, ds = tools_golden
+    w = policy_weights(ds, policy)
+    prob, alias = oracle.build_alias_table(ds["indptr"], ds["indices"], w)
+    assert np.array_equal(prob.view(np.uint32), g["prob_" + policy].view(np.uint32))      # bit-exact fp32
+    assert np.array_equal(alias, g["alias_" + policy])
+    prefix = oracle.build_prefix_table(ds["indptr"], w)
+    assert np.array_equal(prefix.view(np.uint32), g["prefix_" + policy].view(np.uint32))
+    # the quirk the restatement keeps: entries whose probability ends at exactly 1 keep a zero alias
+    assert (alias[prob == 1.0] == 0).all() and (prob == 1.0).any()
+
+
+def test_cache_rankings_match_reference_tools(oracle, tools_golden):
+    g, ds = tools_golden
+    assert np.array_equal(oracle.rank_by_degree(ds["indptr"], ds["indices"]), g["cache_by_degree"])
+    assert np.array_equal(oracle.rank_by_heuristic(ds["indptr"], ds["indices"], ds["train_set"]),
+                          g["cache_by_heuristic"])
+    assert sorted(g["cache_by_heuristic"].tolist()) == list(range(len(ds["indptr"]) - 1))

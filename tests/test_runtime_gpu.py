@@ -116,7 +116,7 @@ def test_single_process_engine_matches_oracle(tmp_path, oracle, dataset, sample_
         assert float(data["miss/%d" % k0]) == data["b/%d/feat" % k0].nbytes
 
 
-@pytest.mark.parametrize("policy", ["degree", "random"])
+@pytest.mark.parametrize("policy", ["degree", "random", "heuristic"])
 def test_cache_policy_ranked_on_gpu_when_file_absent(tmp_path, oracle, dataset, policy):
     """cache_by_degree / cache_by_random without the offline tool's cache_by_*.bin (engine.cc:216-256 loads it):
     the ranking is computed on the sampler GPU; batches stay bit-exact and the degree policy's miss bytes are
@@ -130,10 +130,14 @@ def test_cache_policy_ranked_on_gpu_when_file_absent(tmp_path, oracle, dataset, 
     check_batches(oracle, dataset, cfg, data, int(data["num_step"]))
     V, D = dataset["feat"].shape
     ncache = int(V * 0.3)
-    if policy == "degree":
-        deg = np.bincount(dataset["indices"], minlength=V).astype(np.uint32)
+    if policy in ("degree", "heuristic"):
+        if policy == "degree":
+            deg = np.bincount(dataset["indices"], minlength=V).astype(np.uint32)
+            rank = oracle.presc_rank(deg)
+        else:   # toolkit/cache/cache_by_heuristic.cc:28-91 (restatement pinned to the tool's own output on CPU)
+            rank = oracle.rank_by_heuristic(dataset["indptr"], dataset["indices"], dataset["train_set"])
         cached = np.zeros(V, bool)
-        cached[oracle.presc_rank(deg)[:ncache]] = True
+        cached[rank[:ncache]] = True
         for k in data["keys"]:
             nodes = data["b/%d/input_nodes" % int(k)].view(np.uint32)
             assert float(data["miss/%d" % int(k)]) == float((~cached[nodes]).sum() * D * 4)
