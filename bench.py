@@ -217,6 +217,12 @@ def ncu_traffic():
         return None
 
 
+def workload_name(args):
+    """config.workload, identical for both arms (--impl ours / reference)."""
+    return "GraphSAGE [25,10] batch 8000 khop2, %s-shaped synthetic power-law graph, PreSC cache %.0f%%" \
+        % (args.workload, args.cache_pct * 100)
+
+
 def peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -241,11 +247,14 @@ def build_workload(args, device):
     rows = min(V, 1 << args.empty_feat)
     gh = torch.Generator()
     gh.manual_seed(SEED + 1)
-    host_feat = (torch.rand((rows, D), generator=gh, dtype=torch.float32) * 2 - 1).pin_memory()
+    host_feat = torch.rand((rows, D), generator=gh, dtype=torch.float32) * 2 - 1
+    if torch.cuda.is_available():      # the reference arm also runs on a box without a GPU
+        host_feat = host_feat.pin_memory()
     mask = rows - 1 if rows < V else 0xFFFFFFFFFFFFFFFF
     if rows < V:
         assert rows & (rows - 1) == 0
-    torch.cuda.synchronize()
+    if torch.cuda.is_available():
+        torch.cuda.synchronize()
     return dict(V=V, E=E, D=D, C=C, T=T, indptr=indptr, indices=indices, label=label, train=train,
                 host_feat=host_feat, feat_mask=mask, gen_s=time.time() - t0)
 
@@ -472,8 +481,7 @@ def run_ours(args):
         "metric": METRIC, "value": edges_all / (ms_total * 1e-3), "unit": UNIT, "n_gpus": world,
         "steps": Ksteps, "warmup": W, "ms_per_step": ms_total / Ksteps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "u32 ids / f32 rows (byte copy)", "data": "synthetic",
-        "config": {"workload": "GraphSAGE [25,10] batch 8000 khop2, %s-shaped synthetic power-law graph, PreSC cache %.0f%%"
-                               % (args.workload, args.cache_pct * 100),
+        "config": {"workload": workload_name(args),
                    "batches_in_flight": len(hp.slots),
                    "num_node": V, "num_edge": wl["E"], "feat_dim": D, "cache_percentage": args.cache_pct,
                    "e2e_cache_percentage": E2E_CACHE_PCT,
@@ -675,8 +683,9 @@ def run_reference(args):
            "n_gpus": int(os.environ.get("WORLD_SIZE", "1")), "steps": cb["steps"], "warmup": 1,
            "ms_per_step": cb["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
            "dtype": "u32 ids / f32 rows (byte copy)", "data": "synthetic",
-           "config": {"workload": "GraphSAGE [25,10] batch 8000 khop2, %s-shaped synthetic power-law graph, CPU sampler+extractor"
-                                  % args.workload},
+           "config": {"workload": workload_name(args), "num_node": wl["V"], "num_edge": wl["E"], "feat_dim": wl["D"],
+                      "reference_path": "CPUSampleKHop2 + CPUHashTable2 + CPUExtract on the host cores: every feature row "
+                                        "is read from host memory (no GPU, no cache)"},
            "cpu_baseline": cb,
            "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(out))
