@@ -209,6 +209,11 @@ class Sampler {
   bool Done(const TaskPtr &task) { return cudaEventQuery(slots_[task->slot].done) == cudaSuccess; }
   void SyncSlot(const TaskPtr &task) { CUDA_CALL(cudaStreamSynchronize(slots_[task->slot].stream)); }
   void ResetShuffler() { cur_epoch_ = 0; cur_step_ = 0; shuffled_epoch_ = (uint64_t)-1; }
+  // PreSC draws its neighbours from its own Philox stream.  The reference pre-samples with the live cuRAND states
+  // and then rewinds only the shuffler (pre_sampler.cc:101-103), so its training epochs never repeat the
+  // pre-sampling draws; with a counter-based RNG keyed by (seed, batch key) they would be repeated exactly and
+  // epoch 0 would see an optimistic cache hit rate (every node it touches was counted).
+  void SetRngSalt(uint64_t salt) { rng_salt_ = salt; }
   size_t NumStep() const { return num_step_; }
   size_t NumLocalStep() const { return local_steps_; }
   size_t NumSlots() const { return slots_.size(); }
@@ -233,6 +238,7 @@ class Sampler {
   TensorPtr train_dev_, perm_dev_, shuffle_ws_;
   size_t num_train_, num_step_, local_steps_, step_begin_;
   uint64_t cur_epoch_ = 0, cur_step_ = 0, shuffled_epoch_ = (uint64_t)-1, num_epoch_;
+  uint64_t rng_salt_ = 0;
   // hash table + scratch sized from PredictNumNodes, one set per slot
   size_t max_nodes_, ht_cap_;
   std::vector<size_t> in_max_, edge_max_;
@@ -406,7 +412,7 @@ void Sampler::Enqueue(const TaskPtr &task) {
   pl.walk_len = (uint32_t)rc_.random_walk_length;
   pl.num_walk = (uint32_t)rc_.num_random_walk;
   pl.restart_prob = rc_.random_walk_restart_prob;
-  pl.seed = rc_.seed;
+  pl.seed = rc_.seed ^ rng_salt_;
   pl.table = sl.table->data;
   pl.capacity = ht_cap_;
   pl.num_items = num_items;
@@ -916,6 +922,7 @@ void Engine::DoPreSample() {
   // a temporary sampler view limited to presample_epoch epochs: reuse Next() by bounding the loop
   const size_t total = (size_t)std::max(1, rc.presample_epoch) * s->NumLocalStep();
   CUDA_CALL(cudaStreamSynchronize(s->stream()));  // freq is zeroed before any slot stream adds to it
+  s->SetRngSalt(0x5052455343000000ull);  // "PRESC": not the stream of the training epochs (see SetRngSalt)
   std::deque<TaskPtr> hold;  // a batch's block may only return to the pool once its slot has drained
   for (size_t i = 0; i < total; ++i) {
     if (hold.size() == s->NumSlots()) {
@@ -930,6 +937,7 @@ void Engine::DoPreSample() {
   }
   s->SyncAll();
   hold.clear();
+  s->SetRngSalt(0);
   Profiler::Get().LogInit(kLogInitL3PresampleSample, ts.Passed());
   Timer tr;
   auto rank = Tensor::Device(kI32, {V}, s->device(), s->stream(), "presc_rank");
