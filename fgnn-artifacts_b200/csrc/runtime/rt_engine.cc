@@ -60,7 +60,7 @@ TaskPtr TaskPool::Get(std::atomic<bool> *stop) {
 // [input_nodes][output_nodes] and per layer {num_src,num_dst,num_edge,row,col[,data]}.
 // =============================================================================================
 struct SlotHeader {
-  std::atomic<uint32_t> ready;
+  std::atomic<uint32_t> ready;  // the slot's sequence word (rt_ring.h)
   uint32_t num_layer, have_data;
   uint64_t key;
   uint64_t input_size, output_size;
@@ -239,6 +239,7 @@ class Sampler {
   size_t num_train_, num_step_, local_steps_, step_begin_;
   uint64_t cur_epoch_ = 0, cur_step_ = 0, shuffled_epoch_ = (uint64_t)-1, num_epoch_;
   uint64_t rng_salt_ = 0;
+  std::vector<uint8_t> sanity_map_;  // SAMGRAPH_SANITY_CHECK: train nodes already handed out this epoch
   // hash table + scratch sized from PredictNumNodes, one set per slot
   size_t max_nodes_, ht_cap_;
   std::vector<size_t> in_max_, edge_max_;
@@ -349,6 +350,7 @@ void Sampler::Reshuffle(uint64_t epoch) {
   CUDA_CALL(cudaEventRecord(shuffled_, stream_));
   for (auto &sl : slots_) CUDA_CALL(cudaStreamWaitEvent(sl.stream, shuffled_, 0));
   shuffled_epoch_ = epoch;
+  if (rc_.option_sanity_check) sanity_map_.assign(ds_->num_node, 0);  // one epoch = every train node at most once
 }
 
 TaskPtr Sampler::Next() {
@@ -373,6 +375,15 @@ TaskPtr Sampler::Next() {
   task->output_nodes = Tensor::View(blk->seeds, kI32, {n}, Context(kGPU, dev_), task->block, "output_nodes");
   CUDA_CALL(cudaMemcpyAsync(blk->seeds, (const IdType *)perm_dev_->data + off, n * sizeof(IdType),
                             cudaMemcpyDeviceToDevice, st));
+  if (rc_.option_sanity_check) {  // cuda_shuffler.cc:144-151 (debug switch: one small D2H copy + host scan per batch)
+    std::vector<IdType> h(n);
+    CUDA_CALL(cudaMemcpyAsync(h.data(), blk->seeds, n * sizeof(IdType), cudaMemcpyDeviceToHost, st));
+    CUDA_CALL(cudaStreamSynchronize(st));
+    size_t bad = 0;
+    const int rc = fgnn_rt_sanity_check_batch(sanity_map_.data(), ds_->num_node, h.data(), n, &bad);
+    FCHECK(rc == 0) << (rc == 3 ? "duplicate batch input" : rc == 1 ? "empty key in batch input" : "batch input out of range")
+                    << ": seed " << (bad < n ? h[bad] : 0) << " at position " << bad << " of batch " << task->key;
+  }
   ++cur_step_;
   return task;
 }
@@ -852,7 +863,7 @@ void Engine::CreateSharedState() {  // dist_engine.cc:115-153 + memory_queue.cc:
   ring_->devq_trainers = (uint32_t)std::min<size_t>(rc.num_train_worker, 16);
   if (rc.num_train_worker > 16) ring_->devq_enabled = 0;
   for (int t = 0; t < 16; ++t) ring_->devq_ready[t] = 0;
-  for (uint32_t i = 0; i < nslots; ++i) reinterpret_cast<SlotHeader *>(ring_->slot(i))->ready = 0;
+  for (uint32_t i = 0; i < nslots; ++i) RingInitSlot(&reinterpret_cast<SlotHeader *>(ring_->slot(i))->ready, i);
 }
 
 void Engine::Init() {
@@ -1147,7 +1158,7 @@ void Engine::SendTask(const TaskPtr &t) {
     put(t->graphs[i].data);
   }
   CUDA_CALL(cudaStreamSynchronize(st));
-  RingEndWrite(&ring_->ctl, &h->ready);
+  RingEndWrite(&ring_->ctl, &h->ready, idx);
   (void)sent_bytes;
   Profiler::Get().LogStep(t->key, kLogL1SendTime, ts.Passed());
   Profiler::Get().LogEpochAdd(t->key, kLogEpochSampleSendTime, ts.Passed());
@@ -1187,7 +1198,7 @@ TaskPtr Engine::RecvTask(bool block) {
     if (h->have_data) g.data = get(g.num_edge, "train_graph.data");
   }
   CUDA_CALL(cudaStreamSynchronize(st));
-  RingEndRead(&ring_->ctl, &h->ready);
+  RingEndRead(&ring_->ctl, &h->ready, idx);
   Profiler::Get().LogStep(task->key, kLogL1RecvTime, tr.Passed());
   return task;
 }

@@ -17,7 +17,10 @@ extern "C" long fgnn_rt_ring_selftest(uint32_t num_slots, uint32_t slot_words, u
   RingCtl ctl;
   RingInit(&ctl, num_slots, /*process_shared=*/false);
   std::vector<Slot> slots(num_slots);
-  for (auto &s : slots) s.words.assign(slot_words, 0xFFFFFFFFu);
+  for (uint32_t i = 0; i < num_slots; ++i) {
+    slots[i].words.assign(slot_words, 0xFFFFFFFFu);
+    RingInitSlot(&slots[i].ready, i);
+  }
   auto ready_of = [&](uint64_t ticket) { return &slots[ticket % num_slots].ready; };
 
   std::atomic<bool> stop{false};
@@ -41,11 +44,12 @@ extern "C" long fgnn_rt_ring_selftest(uint32_t num_slots, uint32_t slot_words, u
         uint64_t ticket;
         if (!RingBeginWrite(&ctl, ready_of, &stop, &ticket, unsafe_no_slot_wait == 0)) return;
         Slot &s = slots[ticket % num_slots];
+        if ((ticket % 3) == p % 3) delay(ticket * 17 + p + 1000);  // slow writers: records complete out of order
         for (uint32_t w = 0; w < slot_words; ++w) {  // a slow, word-by-word write like a DMA in flight
           s.words[w] = (uint32_t)seq;
           if ((w & 63u) == 63u) std::this_thread::yield();
         }
-        RingEndWrite(&ctl, &s.ready);
+        RingEndWrite(&ctl, &s.ready, ticket);
       }
     });
   for (uint32_t c = 0; c < consumers; ++c)
@@ -65,7 +69,7 @@ extern "C" long fgnn_rt_ring_selftest(uint32_t num_slots, uint32_t slot_words, u
         for (uint32_t w = 0; w < slot_words; ++w) ok &= (s.words[w] == seq);
         if (!ok) damaged.fetch_add(1);
         else seen[seq].fetch_add(1);
-        RingEndRead(&ctl, &s.ready);
+        RingEndRead(&ctl, &s.ready, ticket);
         consumed.fetch_add(1);
       }
     });
@@ -88,4 +92,21 @@ extern "C" long fgnn_rt_ring_selftest(uint32_t num_slots, uint32_t slot_words, u
   long bad = (long)damaged.load();
   for (uint64_t i = 0; i < items; ++i) bad += (seen[i].load() != 1);
   return bad;
+}
+
+extern "C" int fgnn_rt_sanity_check_batch(uint8_t *epoch_map, size_t num_nodes, const uint32_t *seeds, size_t n,
+                                          size_t *bad_index) {
+  for (size_t i = 0; i < n; ++i) {
+    const uint32_t v = seeds[i];
+    int rc = 0;
+    if (v == 0xFFFFFFFFu) rc = 1;            // Constant::kEmptyKey (list_sanity_check)
+    else if (v >= num_nodes) rc = 2;
+    else if (epoch_map[v]) rc = 3;           // batch_sanity_check: map[input[index]] must still be 0
+    if (rc) {
+      if (bad_index) *bad_index = i;
+      return rc;
+    }
+    epoch_map[v] = 1;
+  }
+  return 0;
 }

@@ -1,11 +1,14 @@
 // Ticket protocol of the arch5 sampler -> trainer queue (reference: MemoryQueue, memory_queue.cc:51-138 and
 // memory_queue.h:46-113: a bounded ring of fixed-size slots in shared memory, semaphores for the fill level).
-// Several samplers produce and several trainers consume, and trainers release their slots OUT OF ORDER (a slow
-// trainer keeps its slot while a fast one returns the next), so the fill-level semaphore alone does not say that
-// the slot a new ticket maps to (ticket % num_slots) is free: every slot carries a `ready` word
-//     0 = free        (set by the consumer after it has copied the record out)
-//     1 = published   (set by the producer after the record is complete)
-// and both sides wait on the word of THEIR slot after taking a ticket.  Works across processes (MAP_SHARED,
+// Several samplers produce and several trainers consume; writers finish out of order (a slow sampler is still
+// copying ticket t while ticket t+1 is already published) and readers release out of order (a slow trainer keeps
+// its slot while a fast one returns the next).  The fill-level semaphores therefore only provide back-pressure;
+// what makes a slot safe to touch is its sequence word (the bounded MPMC queue of D. Vyukov):
+//     seq == t          slot is free for the writer holding ticket t        (initially seq = slot index)
+//     seq == t + 1      ticket t's record is complete, its reader may copy it out
+//     seq == t + N      the reader is done, the writer of ticket t + N may start   (N = num_slots)
+// A plain free/published flag is NOT enough: "free" would also be what the writer of ticket t + N sees while the
+// writer of ticket t has claimed the slot but not published yet.  Works across processes (MAP_SHARED,
 // process-shared mutex/semaphores) and across threads (tests/test_ring_cpu.py drives fgnn_rt_ring_selftest).
 #pragma once
 #include <pthread.h>
@@ -40,10 +43,13 @@ inline void RingInit(RingCtl *c, uint32_t num_slots, bool process_shared) {
 
 inline void RingPause() { std::this_thread::sleep_for(std::chrono::microseconds(1)); }
 
-// Producer: take the next ticket and wait until its slot has been released.  `ready_of(ticket)` returns the
-// slot's ready word.  Returns false when `stop` was raised while waiting (nothing may be written then).
-template <typename ReadyOf>
-inline bool RingBeginWrite(RingCtl *c, ReadyOf ready_of, const std::atomic<bool> *stop, uint64_t *ticket,
+inline void RingInitSlot(std::atomic<uint32_t> *seq, uint32_t slot_index) { seq->store(slot_index); }
+
+// Producer: take the next ticket and wait until its slot has been released by the reader of ticket - num_slots.
+// `seq_of(ticket)` returns the slot's sequence word.  Returns false when `stop` was raised while waiting (nothing
+// may be written then).
+template <typename SeqOf>
+inline bool RingBeginWrite(RingCtl *c, SeqOf seq_of, const std::atomic<bool> *stop, uint64_t *ticket,
                            bool wait_for_slot = true /* false only in the self-test's negative control */) {
   while (sem_trywait(&c->free_slots) != 0) {
     if (stop && stop->load(std::memory_order_relaxed)) return false;
@@ -52,22 +58,22 @@ inline bool RingBeginWrite(RingCtl *c, ReadyOf ready_of, const std::atomic<bool>
   pthread_mutex_lock(&c->mu);
   *ticket = c->tail++;
   pthread_mutex_unlock(&c->mu);
-  std::atomic<uint32_t> *ready = ready_of(*ticket);
-  while (wait_for_slot && ready->load(std::memory_order_acquire) != 0) {  // its previous reader is still copying it out
+  std::atomic<uint32_t> *seq = seq_of(*ticket);
+  while (wait_for_slot && seq->load(std::memory_order_acquire) != (uint32_t)*ticket) {
     if (stop && stop->load(std::memory_order_relaxed)) return false;
     RingPause();
   }
   return true;
 }
-inline void RingEndWrite(RingCtl *c, std::atomic<uint32_t> *ready) {
-  ready->store(1, std::memory_order_release);
+inline void RingEndWrite(RingCtl *c, std::atomic<uint32_t> *seq, uint64_t ticket) {
+  seq->store((uint32_t)(ticket + 1), std::memory_order_release);
   sem_post(&c->used_slots);
 }
 
 // Consumer: take the next ticket (optionally without blocking when the ring is empty) and wait until its record
 // has been published — with several producers a later ticket can be complete before an earlier one.
-template <typename ReadyOf>
-inline bool RingBeginRead(RingCtl *c, ReadyOf ready_of, const std::atomic<bool> *stop, bool block, uint64_t *ticket) {
+template <typename SeqOf>
+inline bool RingBeginRead(RingCtl *c, SeqOf seq_of, const std::atomic<bool> *stop, bool block, uint64_t *ticket) {
   while (sem_trywait(&c->used_slots) != 0) {
     if (!block || (stop && stop->load(std::memory_order_relaxed))) return false;
     RingPause();
@@ -75,20 +81,29 @@ inline bool RingBeginRead(RingCtl *c, ReadyOf ready_of, const std::atomic<bool> 
   pthread_mutex_lock(&c->mu);
   *ticket = c->head++;
   pthread_mutex_unlock(&c->mu);
-  std::atomic<uint32_t> *ready = ready_of(*ticket);
-  while (ready->load(std::memory_order_acquire) == 0) {
+  std::atomic<uint32_t> *seq = seq_of(*ticket);
+  while (seq->load(std::memory_order_acquire) != (uint32_t)(*ticket + 1)) {
     if (stop && stop->load(std::memory_order_relaxed)) return false;
     RingPause();
   }
   return true;
 }
-inline void RingEndRead(RingCtl *c, std::atomic<uint32_t> *ready) {
-  ready->store(0, std::memory_order_release);
+inline void RingEndRead(RingCtl *c, std::atomic<uint32_t> *seq, uint64_t ticket) {
+  seq->store((uint32_t)(ticket + c->num_slots), std::memory_order_release);
   sem_post(&c->free_slots);
 }
 
 }  // namespace rt
 }  // namespace fgnn
+
+// SAMGRAPH_SANITY_CHECK=1 (reference: cuda_shuffler.cc:144-151 -> GPUSanityCheckList / GPUBatchSanityCheck,
+// cuda_sanity_check.cu:29-59): every mini-batch's seeds must be valid ids and no training node may be handed out
+// twice within an epoch.  `epoch_map` has one byte per vertex, cleared by the caller at every epoch start.
+// Returns 0 = ok, 1 = an id equals the empty key, 2 = id out of range, 3 = "duplicate batch input"; *bad_index
+// (optional) receives the position of the offending seed.  Host function: the engine copies the <= batch_size
+// seeds back only when the check is switched on.
+extern "C" int fgnn_rt_sanity_check_batch(uint8_t *epoch_map, size_t num_nodes, const uint32_t *seeds, size_t n,
+                                          size_t *bad_index);
 
 // Threaded stress test of the protocol above (test hook, CPU only): `producers` threads publish `items` records
 // in total into a ring of `num_slots` slots of `slot_words` 32-bit words, `consumers` threads take them out,
@@ -96,8 +111,8 @@ inline void RingEndRead(RingCtl *c, std::atomic<uint32_t> *ready) {
 // of order.  Every record carries its sequence number in every word.  Returns 0 when every record arrived exactly
 // once and intact, a positive count of damaged / duplicated / missing records otherwise, -1 on timeout
 // (`timeout_ms`): the consumers or producers stopped making progress.  `unsafe_no_slot_wait` != 0 is the negative
-// control: producers rely on the fill-level semaphore alone (the round-1 bug) — records get overwritten while a
-// slow consumer still holds them, or a slot's ready word is cleared after its next record was published.
+// control: producers rely on the fill-level semaphore alone — records get overwritten while a slow consumer still
+// holds them, and the sequence words go out of step (dead-lock).
 extern "C" long fgnn_rt_ring_selftest(uint32_t num_slots, uint32_t slot_words, uint32_t producers,
                                       uint32_t consumers, uint64_t items, uint32_t max_delay_us,
                                       uint32_t timeout_ms, int unsafe_no_slot_wait);

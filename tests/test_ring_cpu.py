@@ -44,3 +44,29 @@ def test_negative_control_fill_level_alone_is_not_enough(selftest):
     a single-consumer ring) out-of-order releases corrupt records or dead-lock; the stress test must see it."""
     outcomes = [selftest(ns, words, P, C, items, delay, 3000, 1) for (ns, words, P, C, items, delay) in CASES[:3]]
     assert any(o != 0 for o in outcomes), outcomes
+
+
+def test_sanity_check_batch_flags_what_the_reference_asserts():
+    """SAMGRAPH_SANITY_CHECK (cuda_shuffler.cc:144-151, cuda_sanity_check.cu:29-59): empty keys, out-of-range ids and
+    a train node handed out twice within one epoch ("duplicate batch input")."""
+    import numpy as np
+    lib = ctypes.CDLL(LIB)
+    f = lib.fgnn_rt_sanity_check_batch
+    f.argtypes = [ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p, ctypes.c_size_t, ctypes.POINTER(ctypes.c_size_t)]
+    f.restype = ctypes.c_int
+    V = 1000
+    emap = np.zeros(V, np.uint8)
+    bad = ctypes.c_size_t(0)
+
+    def check(ids):
+        a = np.ascontiguousarray(ids, np.uint32)
+        return f(emap.ctypes.data, V, a.ctypes.data, len(a), ctypes.byref(bad))
+
+    perm = np.random.default_rng(1).permutation(V).astype(np.uint32)
+    assert check(perm[:400]) == 0 and check(perm[400:800]) == 0          # two batches of one epoch
+    assert int(emap.sum()) == 800
+    assert check(perm[790:810]) == 3 and bad.value == 0                   # already handed out this epoch
+    assert check([perm[900], perm[901], perm[900]]) == 3 and bad.value == 2
+    assert check([0xFFFFFFFF]) == 1 and check([V]) == 2
+    emap[:] = 0                                                           # next epoch
+    assert check(perm) == 0 and check([]) == 0
