@@ -30,6 +30,7 @@ for _p in (ROOT, PKG):
 
 METRIC = "sampled edges/s (sample + unique/remap + cache-aware extract per mini-batch)"
 UNIT = "edges/s"
+DTYPE = "u32"          # ids, offsets and hashes are uint32 arithmetic; fp32 feature rows are moved as bytes
 FANOUTS = [25, 10]
 BATCH = 8000
 
@@ -480,8 +481,9 @@ def run_ours(args):
     out = {
         "metric": METRIC, "value": edges_all / (ms_total * 1e-3), "unit": UNIT, "n_gpus": world,
         "steps": Ksteps, "warmup": W, "ms_per_step": ms_total / Ksteps, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "u32 ids / f32 rows (byte copy)", "data": "synthetic",
+        "scaling": "weak", "vs_baseline": None, "dtype": DTYPE, "data": "synthetic",
         "config": {"workload": workload_name(args),
+                   "dtype_note": "u32 ids / hashes / counts; f32 feature rows and i64 labels are byte copies",
                    "batches_in_flight": len(hp.slots),
                    "num_node": V, "num_edge": wl["E"], "feat_dim": D, "cache_percentage": args.cache_pct,
                    "e2e_cache_percentage": E2E_CACHE_PCT,
@@ -682,7 +684,7 @@ def run_reference(args):
     out = {"impl": "reference", "metric": METRIC, "value": cb["value"], "unit": UNIT,
            "n_gpus": int(os.environ.get("WORLD_SIZE", "1")), "steps": cb["steps"], "warmup": 1,
            "ms_per_step": cb["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-           "dtype": "u32 ids / f32 rows (byte copy)", "data": "synthetic",
+           "dtype": DTYPE, "data": "synthetic",
            "config": {"workload": workload_name(args), "num_node": wl["V"], "num_edge": wl["E"], "feat_dim": wl["D"],
                       "reference_path": "CPUSampleKHop2 + CPUHashTable2 + CPUExtract on the host cores: every feature row "
                                         "is read from host memory (no GPU, no cache)"},
