@@ -107,3 +107,26 @@ def test_step_split_matches_dist_shuffler(built):
                 assert c.value == (num_step // S if w < S - 1 else num_step - (num_step // S) * w)
                 covered += list(range(b.value, b.value + c.value))
             assert covered == list(range(num_step))
+
+
+def test_every_sam_name_the_reference_scripts_use_exists(built):
+    """tests/golden/sam_api_used.json lists every `sam.<name>` of example/samgraph/**/*.py (generated by
+    tests/golden/make_api_fixture.py).  Every name the reference's own package defines must exist here with the same
+    kind (callable vs constant vs dict); the three names its stale train_gat.py uses without the package defining
+    them (simple_hashtable, parallel_hashtable, report) are absent on both sides."""
+    import json
+    used = json.load(open(os.path.join(ROOT, "tests", "golden", "sam_api_used.json")))
+    import samgraph.torch as sam
+    assert len(used) >= 70
+    for name, info in used.items():
+        if not info["defined_in_reference"]:
+            assert not hasattr(sam, name), name
+            continue
+        assert hasattr(sam, name), "samgraph.torch lacks %s (used by %s)" % (name, info["scripts"][:2])
+        obj = getattr(sam, name)
+        if name.startswith(("kLog", "KLog", "kL", "kArch", "kKHop", "kCache", "kWeighted", "kRandom", "kDynamic")):
+            assert isinstance(obj, int), name
+        elif name in ("sample_types", "builtin_archs", "cache_policies"):
+            assert isinstance(obj, dict) and obj, name
+        else:
+            assert callable(obj), name
