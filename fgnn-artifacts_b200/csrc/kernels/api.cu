@@ -2,10 +2,38 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <mutex>
+#include <vector>
+
 #include "common.cuh"
 
 namespace fgnn {
 unsigned long long g_launch_count = 0;
+
+// ---- launch event trace (see common.cuh) ----
+bool g_trace_on = false;
+namespace {
+struct TraceRec {
+  cudaEvent_t ev;
+  int label;
+  cudaStream_t stream;
+};
+std::mutex g_trace_mu;
+std::vector<TraceRec> g_trace;
+cudaEvent_t g_trace_base = nullptr;
+size_t g_trace_cap = 0;
+}  // namespace
+void trace_mark_slow(cudaStream_t st, int label) {
+  std::lock_guard<std::mutex> lk(g_trace_mu);
+  if (!g_trace_on || g_trace.size() >= g_trace_cap) return;
+  TraceRec r{nullptr, label, st};
+  if (cudaEventCreate(&r.ev) != cudaSuccess) return;
+  if (cudaEventRecord(r.ev, st) != cudaSuccess) {
+    cudaEventDestroy(r.ev);
+    return;
+  }
+  g_trace.push_back(r);
+}
 
 int sm_count() {
   static int cached[64] = {0};
@@ -30,6 +58,49 @@ int grid_share_div() {
   return d;
 }
 }  // namespace fgnn
+
+extern "C" int fgnn_k_trace_enable(int on, size_t max_records) {
+  std::lock_guard<std::mutex> lk(fgnn::g_trace_mu);
+  for (auto &r : fgnn::g_trace) cudaEventDestroy(r.ev);
+  fgnn::g_trace.clear();
+  if (fgnn::g_trace_base) {
+    cudaEventDestroy(fgnn::g_trace_base);
+    fgnn::g_trace_base = nullptr;
+  }
+  fgnn::g_trace_on = false;
+  if (!on) return 0;
+  cudaError_t e = cudaEventCreate(&fgnn::g_trace_base);
+  if (e != cudaSuccess) return (int)e;
+  e = cudaEventRecord(fgnn::g_trace_base, (cudaStream_t)0);  // time zero: everything enqueued so far has to drain first
+  if (e != cudaSuccess) return (int)e;
+  fgnn::g_trace_cap = max_records ? max_records : 4096;
+  fgnn::g_trace.reserve(fgnn::g_trace_cap);
+  fgnn::g_trace_on = true;
+  return 0;
+}
+
+extern "C" long fgnn_k_trace_dump(size_t max_records, int *labels, uint64_t *streams, float *ms) {
+  std::lock_guard<std::mutex> lk(fgnn::g_trace_mu);
+  fgnn::g_trace_on = false;
+  if (!fgnn::g_trace_base) return 0;
+  size_t n = 0;
+  for (auto &r : fgnn::g_trace) {
+    float t = -1.0f;
+    if (cudaEventSynchronize(r.ev) == cudaSuccess) cudaEventElapsedTime(&t, fgnn::g_trace_base, r.ev);
+    if (n < max_records && labels && streams && ms) {
+      labels[n] = r.label;
+      streams[n] = (uint64_t)(uintptr_t)r.stream;
+      ms[n] = t;
+      ++n;
+    }
+    cudaEventDestroy(r.ev);
+  }
+  fgnn::g_trace.clear();
+  cudaEventDestroy(fgnn::g_trace_base);
+  fgnn::g_trace_base = nullptr;
+  cudaGetLastError();
+  return (long)n;
+}
 
 extern "C" const char *fgnn_k_version(void) { return "fgnn-b200 kernels r1 (sm_100a)"; }
 

@@ -37,11 +37,14 @@ extern "C" int fgnn_k_sample_batch(const fgnn_sample_plan *pl, const fgnn_sample
 
   // Reset (cuda_loops.cc:63) + FillWithUnique of the seeds (:67-69); the seed count doubles as the
   // input count of the first sampled layer
+  trace_mark(st, FGNN_TRACE_BATCH_BEGIN);
   cudaError_t e = cudaMemsetAsync(pl->table, 0xFF, fgnn_k_ht_bytes(pl->capacity), st);
   if (e != cudaSuccess) return (int)e;
+  trace_mark(st, FGNN_TRACE_TABLE_RESET);
   int rc = ht_fill_unique_first_launch(pl->table, pl->capacity, seeds, n_seeds_max, d_n_seeds, out->n2o,
                                        pl->num_items, counts + 3 * (L - 1), st);
   if (rc) return rc;
+  trace_mark(st, FGNN_TRACE_FILL_SEEDS);
 
   for (int i = (int)L - 1; i >= 0; --i) {  // cuda_loops.cc:87
     uint32_t *n_in = counts + 3 * i, *n_edge = counts + 3 * i + 1, *n_src = counts + 3 * i + 2;
@@ -54,11 +57,14 @@ extern "C" int fgnn_k_sample_batch(const fgnn_sample_plan *pl, const fgnn_sample
     if (pl->sample_type == 5 && (fuse & 4)) {
       rc = sample_khop2_pad_launch(pl->indptr, pl->indices, out->n2o, nmax, n_in, f, rng, dst, st);
       if (rc) return rc;
+      trace_mark(st, FGNN_TRACE_LAYER(i) + FGNN_TRACE_SAMPLE);
       rc = ht_insert_launch(pl->table, pl->capacity, dst, emax, n_in, pl->pos[i], st, f);
       if (rc) return rc;
+      trace_mark(st, FGNN_TRACE_LAYER(i) + FGNN_TRACE_INSERT);
       rc = ht_compact_pad_launch(pl->table, dst, nmax, n_in, f, pl->pos[i], out->n2o, pl->num_items, out->row[i],
                                  col, n_edge, n_src, n_in_next, pl->chain_ws, st);
       if (rc) return rc;
+      trace_mark(st, FGNN_TRACE_LAYER(i) + FGNN_TRACE_COMPACT);
       continue;
     }
     switch (pl->sample_type) {  // cuda_loops.cc:118-161
@@ -93,17 +99,21 @@ extern "C" int fgnn_k_sample_batch(const fgnn_sample_plan *pl, const fgnn_sample
         return FGNN_ERR_BAD_ARG;
     }
     if (rc) return rc;
+    trace_mark(st, FGNN_TRACE_LAYER(i) + FGNN_TRACE_SAMPLE);
     // populate the hash table with the sampled neighbours and remap them (:176-205)
     if (!inserted) {
       rc = ht_insert_launch(pl->table, pl->capacity, dst, emax, n_edge, pl->pos[i], st);
       if (rc) return rc;
+      trace_mark(st, FGNN_TRACE_LAYER(i) + FGNN_TRACE_INSERT);
     }
     rc = ht_compact_launch(pl->table, pl->capacity, dst, emax, n_edge, pl->pos[i], out->n2o, pl->num_items,
                            (fuse & 2) ? out->row[i] : nullptr, n_src, n_in_next, pl->chain_ws, st);
     if (rc) return rc;
+    trace_mark(st, FGNN_TRACE_LAYER(i) + FGNN_TRACE_COMPACT);
     if (!(fuse & 2)) {
       rc = fgnn_k_ht_map(pl->table, pl->capacity, nullptr, pl->pos[i], emax, n_edge, out->row[i], stream);
       if (rc) return rc;
+      trace_mark(st, FGNN_TRACE_LAYER(i) + FGNN_TRACE_MAP);
     }
   }
   return 0;

@@ -23,6 +23,16 @@ extern unsigned long long g_launch_count;  // api.cu
 int sm_count();                            // api.cu (cached per device)
 inline void note_launch(int n = 1) { g_launch_count += (unsigned long long)n; }
 
+// Event trace of the launches (profiling aid, off by default; api.cu).  With fgnn_k_trace_enable(1) every C-ABI
+// entry that takes part in a mini-batch records a CUDA event after each of its launches; fgnn_k_trace_dump turns
+// them into (label, stream, milliseconds since enable) so that the timeline of an OVERLAPPED loop — which kernel
+// ran when on which stream — can be read without nsys (not in the image).  Labels: FGNN_TRACE_* in the header.
+extern bool g_trace_on;
+void trace_mark_slow(cudaStream_t st, int label);
+inline void trace_mark(cudaStream_t st, int label) {
+  if (g_trace_on) trace_mark_slow(st, label);
+}
+
 inline int check_last() {
   cudaError_t e = cudaGetLastError();
   return (int)e;

@@ -787,11 +787,11 @@ int launch_bulk_dyn_s(int stages, char *out, const uint32_t *nodes, uint32_t n_m
 }  // namespace
 }  // namespace fgnn
 
-extern "C" int fgnn_k_gather_cached(void *out, const uint32_t *nodes, uint32_t n_max,
-                                    const uint32_t *d_n, const uint32_t *table,
-                                    const void *const *shards, uint32_t num_shards,
-                                    const void *miss_src, uint64_t miss_mask, size_t row_bytes,
-                                    unsigned long long *d_stats, fgnn_stream_t stream) {
+static int gather_cached_impl(void *out, const uint32_t *nodes, uint32_t n_max,
+                              const uint32_t *d_n, const uint32_t *table,
+                              const void *const *shards, uint32_t num_shards,
+                              const void *miss_src, uint64_t miss_mask, size_t row_bytes,
+                              unsigned long long *d_stats, fgnn_stream_t stream) {
   if (n_max == 0 || row_bytes == 0) return 0;
   if (!out || !nodes || !table || !shards || num_shards == 0 || !miss_src) return FGNN_ERR_BAD_ARG;
   cudaStream_t st = (cudaStream_t)stream;
@@ -864,4 +864,16 @@ extern "C" int fgnn_k_gather_cached(void *out, const uint32_t *nodes, uint32_t n
 #undef FGNN_GC
   note_launch();
   return check_last();
+}
+
+extern "C" int fgnn_k_gather_cached(void *out, const uint32_t *nodes, uint32_t n_max,
+                                    const uint32_t *d_n, const uint32_t *table,
+                                    const void *const *shards, uint32_t num_shards,
+                                    const void *miss_src, uint64_t miss_mask, size_t row_bytes,
+                                    unsigned long long *d_stats, fgnn_stream_t stream) {
+  trace_mark((cudaStream_t)stream, FGNN_TRACE_GATHER_BEGIN);
+  const int rc = gather_cached_impl(out, nodes, n_max, d_n, table, shards, num_shards, miss_src, miss_mask,
+                                    row_bytes, d_stats, stream);
+  trace_mark((cudaStream_t)stream, FGNN_TRACE_GATHER_END);
+  return rc;
 }

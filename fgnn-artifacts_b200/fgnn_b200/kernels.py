@@ -80,6 +80,7 @@ _SIGS = {
     "fgnn_k_rank_random": [_sz, _u64, _vp, _vp, _sz, _vp],
     "fgnn_k_row_len_sum": [_vp, _vp, _sz, _vp, _vp],
     "fgnn_k_rank_by_heuristic": [_vp, _vp, _sz, _sz, _vp, _sz, _sz, _vp, _vp, _sz, _vp],
+    "fgnn_k_trace_enable": [C.c_int, _sz],
     "fgnn_k_coo_to_csc": [_vp, _vp, _u32, _vp, _u32, C.c_int, _vp, _vp, _vp, _vp, _sz, _vp],
     "fgnn_k_shard_alloc": [C.POINTER(_vp), _sz],
     "fgnn_k_shard_free": [_vp],
@@ -105,7 +106,8 @@ _lib = None
 
 
 def exported_symbols():
-    return list(_SIGS) + list(_SIZE_FNS) + ["fgnn_k_version", "fgnn_k_error_string", "fgnn_k_launch_count"]
+    return list(_SIGS) + list(_SIZE_FNS) + ["fgnn_k_version", "fgnn_k_error_string", "fgnn_k_launch_count",
+                                            "fgnn_k_trace_dump"]
 
 
 def load(path=None):
@@ -129,6 +131,8 @@ def load(path=None):
     lib.fgnn_k_error_string.restype = C.c_char_p
     lib.fgnn_k_error_string.argtypes = [C.c_int]
     lib.fgnn_k_launch_count.restype = _u64
+    lib.fgnn_k_trace_dump.restype = C.c_long
+    lib.fgnn_k_trace_dump.argtypes = [_sz, _vp, _vp, _vp]
     _lib = lib
     return lib
 
@@ -329,6 +333,29 @@ def rank_by_heuristic(indptr, indices, num_nodes, num_edges, train_set, num_trai
                                            num_train, n_nbr, _ptr(rank), _ptr(ws), ws.numel(), _stream()),
            "rank_by_heuristic")
     return n_nbr
+
+
+TRACE_LABELS = {0: "batch_begin", 1: "table_reset", 2: "fill_seeds", 900: "gather_begin", 901: "gather_end"}
+TRACE_LAYER_OPS = {1: "sample", 2: "insert", 3: "compact", 4: "map"}
+
+
+def trace_enable(on=True, max_records=8192):
+    """Record a CUDA event after every launch of fgnn_k_sample_batch / fgnn_k_gather_cached (profiling aid)."""
+    _check(load().fgnn_k_trace_enable(int(bool(on)), max_records), "trace_enable")
+
+
+def trace_dump(max_records=8192):
+    """-> [(name, stream handle, ms since trace_enable)] in enqueue order; a record marks the END of the launch."""
+    labels = (C.c_int * max_records)()
+    streams = (C.c_uint64 * max_records)()
+    ms = (C.c_float * max_records)()
+    n = int(load().fgnn_k_trace_dump(max_records, labels, streams, ms))
+    out = []
+    for i in range(n):
+        lab = labels[i]
+        name = TRACE_LABELS.get(lab) or "L%d_%s" % (lab // 100 - 1, TRACE_LAYER_OPS.get(lab % 100, "?"))
+        out.append((name, int(streams[i]), float(ms[i])))
+    return out
 
 
 def coo_to_csc(row, col, e_max, d_e, num_dst, col_sorted, indptr, indices=None, edge_ids=None, workspace=None):

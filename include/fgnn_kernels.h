@@ -326,6 +326,27 @@ int fgnn_k_rank_by_heuristic(const uint32_t *indptr, const uint32_t *indices, si
                              size_t num_neighbours, uint32_t *ranking_nodes, void *workspace,
                              size_t workspace_bytes, fgnn_stream_t stream);
 
+/* ---- launch event trace (profiling aid, off by default) --------------------------------------- */
+/* fgnn_k_trace_enable(1, max_records): from now on fgnn_k_sample_batch and fgnn_k_gather_cached record a CUDA
+ * event after each of their launches (time zero = an event on the legacy default stream at enable time).
+ * fgnn_k_trace_dump waits for the recorded events, writes (label, stream handle, milliseconds since time zero)
+ * for up to max_records of them, switches the trace off and returns the number written.  A record marks the END
+ * of the named launch on its stream; the launch began at the previous record of the same stream (or later, when
+ * the GPU was busy elsewhere).  Not thread-safe against concurrent launches from several host threads beyond a
+ * mutex around the record list. */
+#define FGNN_TRACE_BATCH_BEGIN 0
+#define FGNN_TRACE_TABLE_RESET 1
+#define FGNN_TRACE_FILL_SEEDS 2
+#define FGNN_TRACE_LAYER(i) (100 * ((i) + 1))
+#define FGNN_TRACE_SAMPLE 1
+#define FGNN_TRACE_INSERT 2
+#define FGNN_TRACE_COMPACT 3
+#define FGNN_TRACE_MAP 4
+#define FGNN_TRACE_GATHER_BEGIN 900
+#define FGNN_TRACE_GATHER_END 901
+int fgnn_k_trace_enable(int on, size_t max_records);
+long fgnn_k_trace_dump(size_t max_records, int *labels, uint64_t *streams, float *ms);
+
 /* ---- block hand-off in CSC form ------------------------------------------ */
 /* (row, col) COO of one sampled layer -> the three arrays of the reference's DGL patch
  * `create_unitgraph_from_csc` (3rdparty/dgl.patch:30-57), replacing DGL's own COO->CSC conversion of the

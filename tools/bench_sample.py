@@ -22,7 +22,7 @@ def main():
     ap.add_argument("--workload", default="papers100M")
     ap.add_argument("--empty-feat", type=int, default=22)
     ap.add_argument("--cache-pct", type=float, default=0.3)
-    ap.add_argument("--sweep", default="fuse", choices=["fuse", "overlap", "profile", "diag"],
+    ap.add_argument("--sweep", default="fuse", choices=["fuse", "overlap", "profile", "diag", "timeline"],
                     help="fuse: kernel-fusion variants; overlap: how the sampling slots and the gather share the GPU\n                    (FGNN_GRID_DIV, gather implementation / CTA shape)")
     a = ap.parse_args()
     import torch
@@ -101,6 +101,33 @@ def main():
         us = run(1, False, a.steps)
         torch.cuda.profiler.stop()
         print("PROFILE_JSON " + json.dumps({"sample_only_us_slots1": round(us, 1)}))
+        return
+    if a.sweep == "timeline":
+        # who runs when in the overlapped loop: CUDA events after every launch (fgnn_k_trace_*), 4 slots + gather
+        out = {}
+        for tag, slots, with_gather in (("sample_only_1slot", 1, False), ("sample_only_4slots", 4, False),
+                                        ("with_gather_4slots", 4, True)):
+            run(slots, with_gather, 12)
+            torch.cuda.synchronize()
+            K.trace_enable(True, 4096)
+            run(slots, with_gather, 12)
+            recs = K.trace_dump(4096)
+            # per stream: duration of every launch = its end mark minus the previous mark on that stream
+            by_stream, rows = {}, []
+            for name, st, t in recs:
+                prev = by_stream.get(st)
+                by_stream[st] = t
+                if name in ("batch_begin", "gather_begin") or prev is None:
+                    continue
+                rows.append((round(prev * 1e3, 1), round(t * 1e3, 1), name, st))
+            rows.sort()
+            sids = {s: i for i, s in enumerate(sorted({r[3] for r in rows}))}
+            agg = {}
+            for b, e, name, st in rows:
+                agg.setdefault(name, []).append(e - b)
+            out[tag] = {"per_kernel_us_mean": {k: round(sum(v) / len(v), 1) for k, v in sorted(agg.items())},
+                        "first_200_intervals_us": [[b, e, name, sids[st]] for b, e, name, st in rows[:200]]}
+        print("TIMELINE_JSON " + json.dumps(out))
         return
     os.environ["FGNN_TUNING_DYNAMIC"] = "1"
     if a.sweep == "diag":
