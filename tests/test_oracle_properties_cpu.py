@@ -123,3 +123,54 @@ def test_khop1_is_sorted_by_seed_id_with_adjacent_dedup(oracle, data, fanout):
         assert all(a != b for a, b in zip(mine[:-1], mine[1:]))      # no adjacent duplicates survive
         assert set(mine.tolist()) <= set(indices[indptr[s]:indptr[s + 1]].tolist())
     assert set(src.tolist()) == {int(s) for s in seeds if deg[s] > 0}
+
+
+@settings(**SET)
+@given(data=st.data(), K=st.integers(1, 4), per_node=st.integers(1, 8))
+def test_topk_model(oracle, data, K, per_node):
+    """cuda_frequency_hashmap.cu:361-401,502-504,585-676: per start node, multiplicities of the visited ids, top K by
+    count, ties in first-occurrence order, dead records (EMPTY start) ignored."""
+    n = data.draw(st.integers(0, 5))
+    inp = np.arange(100, 100 + n, dtype=np.uint32)
+    E = 0xFFFFFFFF
+    ts, td, exp = [], [], []
+    for node in inp:
+        visits = data.draw(st.lists(st.one_of(st.none(), st.integers(0, 5)), min_size=per_node, max_size=per_node))
+        first, count = {}, {}
+        for p, v in enumerate(visits):
+            ts.append(E if v is None else int(node))
+            td.append(0 if v is None else v)
+            if v is not None:
+                first.setdefault(v, p)
+                count[v] = count.get(v, 0) + 1
+        for v in sorted(count, key=lambda v: (-count[v], first[v]))[:K]:
+            exp.append((int(node), v, count[v]))
+    s, d, c = oracle.topk(np.array(ts, np.uint32), np.array(td, np.uint32), inp, per_node, K)
+    assert list(zip(s.tolist(), d.tolist(), c.tolist())) == exp
+
+
+@settings(**SET)
+@given(data=st.data(), walk_len=st.integers(1, 4), num_walk=st.integers(1, 3), p=st.sampled_from([0.0, 0.3, 1.0]))
+def test_random_walk_follows_edges_and_stays_dead(oracle, data, walk_len, num_walk, p):
+    """cuda_sampling_random_walk.cu:43-109: layout [node][step][walk]; step 0 leaves from the start node, every later
+    step from the previous step's node; a walk that died (restart or dead end) stays dead; records carry the START
+    node as src."""
+    V, indptr, indices = random_csr(data.draw)
+    starts = np.array(data.draw(st.lists(st.integers(0, V - 1), max_size=5)), np.uint32)
+    ts, td = oracle.random_walk(indptr, indices, starts, walk_len, p, num_walk, 3, 9, 2)
+    E = 0xFFFFFFFF
+    ts = ts.reshape(len(starts), walk_len, num_walk)
+    td = td.reshape(len(starts), walk_len, num_walk)
+    for n, s0 in enumerate(starts):
+        for w in range(num_walk):
+            cur, alive = int(s0), True
+            for s in range(walk_len):
+                if ts[n, s, w] == E:
+                    alive = False
+                    continue
+                assert alive, "a dead walk came back to life"
+                assert ts[n, s, w] == s0
+                assert td[n, s, w] in indices[indptr[cur]:indptr[cur + 1]]
+                cur = int(td[n, s, w])
+            if p == 1.0 and walk_len > 1:
+                assert (ts[n, 1:, w] == E).all()
