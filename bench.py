@@ -441,6 +441,36 @@ def run_ours(args):
     ga1.record()
     torch.cuda.synchronize()
     gather_alone_ms = ga0.elapsed_time(ga1) / 20
+    # serialised shares (one batch at a time on ONE stream: sample chain -> gather -> labels), the quantity an ncu
+    # launch list of this command shows (its replay serialises the kernels); never used for `value`
+    serial = None
+    try:
+        n_ser = 40
+        evs = [[torch.cuda.Event(enable_timing=True) for _ in range(4)] for _ in range(n_ser)]
+        for k in range(n_ser + 3):
+            sd, n = seeds_of(k)
+            e = evs[k - 3] if k >= 3 else None
+            if e:
+                e[0].record()
+            hp.sample(sd, n, 5_000_000 + k, slot=0)
+            if e:
+                e[1].record()
+            hp.gather(0)
+            if e:
+                e[2].record()
+            hp.gather_labels(sd, n)
+            if e:
+                e[3].record()
+        torch.cuda.synchronize()
+        s_ms = sum(e[0].elapsed_time(e[1]) for e in evs) / n_ser
+        g_ms = sum(e[1].elapsed_time(e[2]) for e in evs) / n_ser
+        l_ms = sum(e[2].elapsed_time(e[3]) for e in evs) / n_ser
+        serial = {"sample_chain_ms": s_ms, "gather_ms": g_ms, "labels_ms": l_ms,
+                  "gather_share": round(g_ms / (s_ms + g_ms + l_ms), 3),
+                  "note": "one batch at a time on one stream; compare THIS share with the ncu launch list "
+                          "(profiles/*_launches_timed_region.txt), whose replay serialises the kernels"}
+    except Exception as ex:      # diagnostic only: never fail the bench line for it
+        serial = {"error": repr(ex)[:200]}
     ms_total, edges_all = aggregate(ms_total, edges, dev)
 
     # ---- N > 1: the same workload with the cache striped over the ranks' GPUs (north_star):
@@ -471,6 +501,9 @@ def run_ours(args):
                 "traffic": (ncu_traffic() or {}).get("dram_bytes_per_launch"), "traffic_capture": ncu_traffic(),
                 "bytes_per_launch": alg_bytes // max(1, Ksteps), "avg_launch_ms": gather_ms / max(1, Ksteps),
                 "share_of_step": round(gather_ms / ms_total, 3),
+                "share_note": "gather stream time / wall time of the OVERLAPPED loop (sampling of later batches runs "
+                              "next to it, so the per-stream times add up to more than the wall time)",
+                "serialised": serial,
                 "timing": "CUDA events on the extraction stream around every gather launch of the timed region; "
                           "%d sampling slots run concurrently on other streams and share HBM with it" % len(hp.slots),
                 "alone": {"avg_launch_ms": gather_alone_ms, "bytes_per_launch": n_alone * (4 + 2 * row_bytes),
