@@ -30,6 +30,7 @@ for _p in (ROOT, PKG):
 
 METRIC = "sampled edges/s (sample + unique/remap + cache-aware extract per mini-batch)"
 UNIT = "edges/s"
+SEED_WEIGHTS = 0x46474E50
 DTYPE = "u32"          # ids, offsets and hashes are uint32 arithmetic; fp32 feature rows are moved as bytes
 FANOUTS = [25, 10]
 BATCH = 8000
@@ -48,6 +49,14 @@ def parse():
                     help="host feature table has 2^k rows, indices masked (SAMGRAPH_EMPTY_FEAT semantics)")
     ap.add_argument("--slots", type=int, default=int(os.environ.get("FGNN_BENCH_SLOTS", "4")),
                     help="mini-batches in flight on separate streams (device-resident leg)")
+    ap.add_argument("--sample-type", default=os.environ.get("FGNN_BENCH_SAMPLE_TYPE", "khop2"),
+                    choices=["khop2", "khop0", "khop1", "weighted_khop", "weighted_khop_prefix",
+                             "weighted_khop_hash_dedup", "random_walk"],
+                    help="sampler of the device-resident leg (BASELINE configs #3-#5); anything but the default khop2 "
+                         "skips the e2e and CPU-baseline legs, which are defined for the headline configuration only")
+    ap.add_argument("--fanout", default=os.environ.get("FGNN_BENCH_FANOUT", "25,10"),
+                    help="samgraph fanout list (sampled last to first), e.g. 5,10,15 for GCN; random_walk ignores it "
+                         "(3 layers x top-5 of 4 walks of length 3, restart 0.5: train_pinsage.py:122-126)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cache25", action="store_true", help="skip the extra 25 %% cache leg (profiling runs)")
@@ -218,10 +227,27 @@ def ncu_traffic():
         return None
 
 
+RW = dict(random_walk_length=3, random_walk_restart_prob=0.5, num_random_walk=4, num_neighbor=5, num_layer=3)
+
+
+def fanouts_of(args):
+    """Per-layer fanout of the device-resident leg; the default is FANOUTS (GraphSAGE [25,10])."""
+    if getattr(args, "sample_type", "khop2") == "random_walk":
+        return [RW["num_neighbor"]] * RW["num_layer"]
+    return [int(x) for x in str(getattr(args, "fanout", "25,10")).split(",") if x]
+
+
+def is_headline(args):
+    return getattr(args, "sample_type", "khop2") == "khop2" and fanouts_of(args) == FANOUTS
+
+
 def workload_name(args):
     """config.workload, identical for both arms (--impl ours / reference)."""
-    return "GraphSAGE [25,10] batch 8000 khop2, %s-shaped synthetic power-law graph, PreSC cache %.0f%%" \
-        % (args.workload, args.cache_pct * 100)
+    if is_headline(args):
+        return "GraphSAGE [25,10] batch 8000 khop2, %s-shaped synthetic power-law graph, PreSC cache %.0f%%" \
+            % (args.workload, args.cache_pct * 100)
+    return "fanout %s batch 8000 %s, %s-shaped synthetic power-law graph, PreSC cache %.0f%%" \
+        % (fanouts_of(args), args.sample_type, args.workload, args.cache_pct * 100)
 
 
 def peaks():
@@ -278,8 +304,26 @@ def run_ours(args):
     wl = build_workload(args, dev)
     V, D = wl["V"], wl["D"]
     row_bytes = D * 4
-    hp = HotPath(wl["indptr"], wl["indices"], V, FANOUTS, BATCH, "khop2", seed=0x5EED0000 + rank, device=dev,
-                 num_slots=args.slots)
+    fanouts = fanouts_of(args)
+    tables = {}
+    if args.sample_type.startswith("weighted"):
+        # kDefault weights of the reference's tools (integers 1..10, create_alias_table.cc:113), tables built on the GPU
+        E = wl["E"]
+        gw = torch.Generator(device=dev)
+        gw.manual_seed(SEED_WEIGHTS)
+        weights = torch.randint(1, 11, (E,), generator=gw, device=dev, dtype=torch.int32).to(torch.float32)
+        if args.sample_type == "weighted_khop_prefix":
+            tables["prefix_table"] = torch.empty(E, dtype=torch.float32, device=dev)
+            K.build_prefix_table(wl["indptr"], V, weights, tables["prefix_table"])
+        else:
+            tables["prob_table"] = torch.empty(E, dtype=torch.float32, device=dev)
+            tables["alias_table"] = torch.empty(E, dtype=torch.int32, device=dev)
+            K.build_alias_table(wl["indptr"], wl["indices"], V, E, weights, tables["prob_table"], tables["alias_table"])
+        torch.cuda.synchronize()
+        del weights
+        torch.cuda.empty_cache()
+    hp = HotPath(wl["indptr"], wl["indices"], V, fanouts, BATCH, args.sample_type, seed=0x5EED0000 + rank, device=dev,
+                 num_slots=args.slots, rw=RW if args.sample_type == "random_walk" else None, **tables)
     steps_per_epoch = (wl["T"] + BATCH - 1) // BATCH
     # DistShuffler split (dist_shuffler.cc:60-83): rank r owns a contiguous range of the epoch's steps
     g = torch.Generator(device=dev)
@@ -551,6 +595,9 @@ def run_ours(args):
             "extract_GBps": r25["n_in_total"] * row_bytes / (r25["gather_ms"] * 1e-3) / 1e9}
 
     # ---- e2e through the host runtime (samgraph_* C-ABI) with host buffers ------------------
+    if not is_headline(args):
+        args.no_e2e = args.no_cpu_baseline = True      # those legs are defined for the headline configuration
+        out["config"]["note"] = "non-headline sampler / fanout: device-resident leg only"
     if not args.no_e2e:
         # release the device-resident leg's buffers first: the engine child builds its own cache
         hp.cache = hp.feat_out = hp.cache_table = None

@@ -27,3 +27,7 @@ timeout 600 ncu --set full --clock-control none --import-source on --profile-fro
 python tools/ncu_summary.py rep gpurun_out/r2a_sampling.ncu-rep > gpurun_out/r2a_sampling_kernels.txt 2>&1
 cut -c1-330 gpurun_out/r2a_sampling_kernels.txt
 ls -la gpurun_out | head -20
+# other BASELINE configs through the same device-resident leg (first runs ever: check before trusting)
+#   python bench.py --workload twitter --sample-type random_walk --no-cache25            # config #3 PinSAGE
+#   python bench.py --workload uk-2006-05 --fanout 5,10,15 --no-cache25                  # config #4 GCN
+#   python bench.py --sample-type weighted_khop --no-cache25                             # config #5 weighted GraphSAGE
