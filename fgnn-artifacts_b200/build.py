@@ -81,7 +81,7 @@ def build(force=False, verbose=True):
         ext = os.path.join(HERE, "samgraph", "torch", "c_lib.so")
         if force or _newer(ext, kobjs + robjs):
             subprocess.check_call([NVCC] + ARCH + ["-shared", "-cudart", "static", "-ccbin", HOST_CXX,
-                                                   "-Xlinker", "--version-script=" + os.path.join(CSRC, "samgraph.lds"),
+                                                   "-Xlinker", "--version-script=" + os.path.join(CSRC, "c_lib_exports.map"),
                                                    "-o", ext] + kobjs + robjs + ["-lpthread", "-lrt"])
         outs.append(ext)
     if verbose:
