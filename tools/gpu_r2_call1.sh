@@ -31,3 +31,5 @@ ls -la gpurun_out | head -20
 #   python bench.py --workload twitter --sample-type random_walk --no-cache25            # config #3 PinSAGE
 #   python bench.py --workload uk-2006-05 --fanout 5,10,15 --no-cache25                  # config #4 GCN
 #   python bench.py --sample-type weighted_khop --no-cache25                             # config #5 weighted GraphSAGE
+# the DGL-free training example (first GPU run): generated ci-1m dataset, 3 epochs
+#   PYTHONPATH=fgnn-artifacts_b200 timeout 300 python examples/train_graphsage_csc.py --synthetic ci-1m --num-epoch 3 --cache-percentage 0.25
