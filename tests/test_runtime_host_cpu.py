@@ -146,3 +146,29 @@ def test_violated_checks_abort_like_the_reference(tmp_path, dataset, case, needl
     assert r.returncode != 0 and out is None
     assert r.returncode in (-6, 134), "expected SIGABRT, got %d\n%s" % (r.returncode, r.stderr[-1500:])
     assert needle.lower() in (r.stderr + r.stdout).lower(), r.stderr[-1500:]
+
+
+def test_tensor_getters_without_a_batch_raise_instead_of_aborting(tmp_path, dataset):
+    """The DLPack getters of samgraph.torch.c_lib (adapter.cc:48-192 equivalents): before any get_next_batch there
+    is no current batch — a Python exception, the process stays alive."""
+    r, out = run(tmp_path, config(dataset["path"]), """
+        sam.config(cfg)
+        sam.data_init()
+        errs = {}
+        for name, args in (("get_graph_feat", (0,)), ("get_graph_label", (0,)), ("get_graph_row", (0, 0)),
+                           ("get_graph_col", (0, 1)), ("get_graph_data", (0, 0)), ("get_graph_csc", (0, 0)),
+                           ("get_graph_input_nodes", (0,)), ("get_graph_output_nodes", (0,))):
+            try:
+                getattr(sam, name)(*args)
+                errs[name] = "no error"
+            except RuntimeError as e:
+                errs[name] = "RuntimeError: " + str(e)
+        out.update(errs)
+        out["alive"] = True
+        sam.shutdown()
+    """)
+    assert r.returncode == 0, r.stderr[-2000:]
+    assert out.pop("alive") is True
+    assert len(out) == 8
+    for name, msg in out.items():
+        assert msg.startswith("RuntimeError: samgraph: no current batch"), (name, msg)
