@@ -1,7 +1,13 @@
 // fgnn_rt_ring_selftest: threaded stress test of the arch5 queue's ticket protocol (rt_ring.h).
 #include "rt_ring.h"
 
+#include <signal.h>
+#include <sys/mman.h>
+#include <sys/wait.h>
+#include <unistd.h>
+
 #include <memory>
+#include <new>
 #include <vector>
 
 using namespace fgnn::rt;
@@ -109,4 +115,111 @@ extern "C" int fgnn_rt_sanity_check_batch(uint8_t *epoch_map, size_t num_nodes, 
     epoch_map[v] = 1;
   }
   return 0;
+}
+
+namespace {
+struct ProcShared {
+  RingCtl ctl;
+  std::atomic<uint64_t> next_item, consumed, damaged;
+};
+inline void proc_delay(uint64_t x, uint32_t max_delay_us) {
+  if (!max_delay_us) return;
+  x = (x + 0x9E3779B97F4A7C15ull) * 0xBF58476D1CE4E5B9ull;
+  x ^= x >> 29;
+  const uint32_t us = (uint32_t)(x % (max_delay_us + 1));
+  if (us) usleep(us);
+}
+}  // namespace
+
+extern "C" long fgnn_rt_ring_selftest_procs(uint32_t num_slots, uint32_t slot_words, uint32_t producers,
+                                            uint32_t consumers, uint64_t items, uint32_t max_delay_us,
+                                            uint32_t timeout_ms) {
+  if (!num_slots || !slot_words || !producers || !consumers) return -2;
+  // layout: ProcShared | seq[num_slots] | seen[items] | words[num_slots][slot_words]
+  const size_t off_seq = (sizeof(ProcShared) + 63) & ~(size_t)63;
+  const size_t off_seen = off_seq + (((size_t)num_slots * sizeof(std::atomic<uint32_t>) + 63) & ~(size_t)63);
+  const size_t off_words = off_seen + (((size_t)(items ? items : 1) * sizeof(std::atomic<uint32_t>) + 63) & ~(size_t)63);
+  const size_t bytes = off_words + (size_t)num_slots * slot_words * sizeof(uint32_t);
+  char *base = (char *)mmap(nullptr, bytes, PROT_READ | PROT_WRITE, MAP_SHARED | MAP_ANONYMOUS, -1, 0);
+  if (base == MAP_FAILED) return -3;
+  ProcShared *sh = new (base) ProcShared();
+  auto *seq = reinterpret_cast<std::atomic<uint32_t> *>(base + off_seq);
+  auto *seen = reinterpret_cast<std::atomic<uint32_t> *>(base + off_seen);
+  auto *words = reinterpret_cast<volatile uint32_t *>(base + off_words);
+  RingInit(&sh->ctl, num_slots, /*process_shared=*/true);
+  for (uint32_t i = 0; i < num_slots; ++i) RingInitSlot(new (&seq[i]) std::atomic<uint32_t>(0), i);
+  for (uint64_t i = 0; i < items; ++i) new (&seen[i]) std::atomic<uint32_t>(0);
+  sh->next_item = 0;
+  sh->consumed = 0;
+  sh->damaged = 0;
+  auto seq_of = [&](uint64_t ticket) { return &seq[ticket % num_slots]; };
+
+  std::vector<pid_t> kids;
+  bool fork_failed = false;
+  for (uint32_t k = 0; k < producers + consumers && !fork_failed; ++k) {
+    const pid_t pid = fork();
+    if (pid < 0) { fork_failed = true; break; }
+    if (pid == 0) {  // child: no allocation, no stdio — only the ring
+      if (k < producers) {
+        const uint32_t p = k;
+        for (;;) {
+          const uint64_t item = sh->next_item.fetch_add(1);
+          if (item >= items) _exit(0);
+          uint64_t ticket;
+          if (!RingBeginWrite(&sh->ctl, seq_of, nullptr, &ticket)) _exit(0);
+          volatile uint32_t *w = words + (size_t)(ticket % num_slots) * slot_words;
+          if ((ticket % 3) == p % 3) proc_delay(ticket * 17 + p + 1000, max_delay_us);
+          for (uint32_t i = 0; i < slot_words; ++i) w[i] = (uint32_t)item;
+          RingEndWrite(&sh->ctl, seq_of(ticket), ticket);
+        }
+      } else {
+        const uint32_t c = k - producers;
+        for (;;) {
+          if (sh->consumed.load() >= items) _exit(0);
+          uint64_t ticket;
+          if (!RingBeginRead(&sh->ctl, seq_of, nullptr, /*block=*/false, &ticket)) {
+            usleep(1);
+            continue;
+          }
+          volatile uint32_t *w = words + (size_t)(ticket % num_slots) * slot_words;
+          const uint32_t item = w[0];
+          proc_delay(ticket * 131 + c, max_delay_us);
+          bool ok = item < items;
+          for (uint32_t i = 0; i < slot_words; ++i) ok &= (w[i] == item);
+          if (!ok) sh->damaged.fetch_add(1);
+          else seen[item].fetch_add(1);
+          RingEndRead(&sh->ctl, seq_of(ticket), ticket);
+          sh->consumed.fetch_add(1);
+        }
+      }
+    }
+    kids.push_back(pid);
+  }
+  const auto t0 = std::chrono::steady_clock::now();
+  bool timed_out = false;
+  while (!fork_failed && sh->consumed.load() < items) {
+    usleep(1000);
+    if (std::chrono::steady_clock::now() - t0 > std::chrono::milliseconds(timeout_ms)) {
+      timed_out = true;
+      break;
+    }
+  }
+  if (timed_out || fork_failed)
+    for (pid_t pid : kids) kill(pid, SIGKILL);
+  else
+    usleep(20000);  // consumers notice consumed >= items; producers are blocked on a full-ring wait or gone
+  for (pid_t pid : kids) {
+    if (!(timed_out || fork_failed)) kill(pid, SIGKILL);  // producers waiting for a ticket nobody will free
+    int st = 0;
+    waitpid(pid, &st, 0);
+  }
+  long result;
+  if (fork_failed) result = -3;
+  else if (timed_out) result = -1;
+  else {
+    result = (long)sh->damaged.load();
+    for (uint64_t i = 0; i < items; ++i) result += (seen[i].load() != 1);
+  }
+  munmap(base, bytes);
+  return result;
 }

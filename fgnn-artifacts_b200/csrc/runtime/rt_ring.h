@@ -116,3 +116,9 @@ extern "C" int fgnn_rt_sanity_check_batch(uint8_t *epoch_map, size_t num_nodes, 
 extern "C" long fgnn_rt_ring_selftest(uint32_t num_slots, uint32_t slot_words, uint32_t producers,
                                       uint32_t consumers, uint64_t items, uint32_t max_delay_us,
                                       uint32_t timeout_ms, int unsafe_no_slot_wait);
+// The same stress test with PROCESSES: ring, slots and counters live in one MAP_SHARED region, producers and
+// consumers are fork()ed children (the arch5 situation: process-shared mutex / semaphores, atomics in shared
+// memory).  Call it from a single-threaded process.  Same return values; -3 = fork/mmap failure.
+extern "C" long fgnn_rt_ring_selftest_procs(uint32_t num_slots, uint32_t slot_words, uint32_t producers,
+                                            uint32_t consumers, uint64_t items, uint32_t max_delay_us,
+                                            uint32_t timeout_ms);

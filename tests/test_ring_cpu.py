@@ -70,3 +70,26 @@ def test_sanity_check_batch_flags_what_the_reference_asserts():
     assert check([0xFFFFFFFF]) == 1 and check([V]) == 2
     emap[:] = 0                                                           # next epoch
     assert check(perm) == 0 and check([]) == 0
+
+
+def test_ring_protocol_across_processes():
+    """The same protocol with fork()ed producers / consumers over one MAP_SHARED region (process-shared mutex and
+    semaphores, sequence words in shared memory) — the arch5 situation.  Run from a fresh single-threaded interpreter
+    (fork in a multi-threaded pytest process would be unsafe)."""
+    import subprocess
+    import sys
+    code = (
+        "import ctypes\n"
+        "lib = ctypes.CDLL(%r)\n"
+        "f = lib.fgnn_rt_ring_selftest_procs\n"
+        "f.argtypes = [ctypes.c_uint32] * 4 + [ctypes.c_uint64, ctypes.c_uint32, ctypes.c_uint32]\n"
+        "f.restype = ctypes.c_long\n"
+        "cases = [(3, 4096, 1, 2, 400, 300), (3, 1024, 2, 2, 800, 200), (4, 256, 3, 2, 2000, 50),\n"
+        "         (16, 64, 4, 4, 5000, 20), (2, 8, 4, 4, 20000, 0), (5, 16, 2, 2, 0, 5)]\n"
+        "print([int(f(*c, 60000)) for c in cases])\n" % LIB)
+    if not os.path.exists(LIB):
+        import __graft_entry__
+        __graft_entry__.build()
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    assert r.stdout.strip() == "[0, 0, 0, 0, 0, 0]", r.stdout
