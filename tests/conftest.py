@@ -13,6 +13,7 @@ for p in (ROOT, PKG):
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
+    config.addinivalue_line("markers", "timeout(seconds): per-test limit (pytest-timeout; a no-op marker without the plugin)")
 
 
 @pytest.fixture(scope="session")

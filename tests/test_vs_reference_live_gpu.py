@@ -8,7 +8,7 @@ import pytest
 
 from test_kernels_gpu import HT, K, dev, host  # noqa: F401  (fixtures + helpers)
 
-pytestmark = pytest.mark.gpu
+pytestmark = [pytest.mark.gpu, pytest.mark.timeout(300)]   # pytest-timeout: a hang must not eat the GPU run
 torch = pytest.importorskip("torch")
 
 

@@ -8,7 +8,7 @@ device is plain torch.  (File name sorts last on purpose: these ran for the firs
 import numpy as np
 import pytest
 
-pytestmark = pytest.mark.gpu
+pytestmark = [pytest.mark.gpu, pytest.mark.timeout(420)]   # pytest-timeout: a hang must not eat the GPU run
 torch = pytest.importorskip("torch")
 
 BATCH = 8000
