@@ -47,8 +47,10 @@ def parse():
                     help="fraction of vertices whose features are cached in HBM (PreSC order); 1.0 = the whole\n                    57 GB table is HBM-resident on a 180 GB B200; the reference-like 25%% regime is always\n                    measured too and reported under extra.cache25")
     ap.add_argument("--empty-feat", type=int, default=int(os.environ.get("FGNN_BENCH_EMPTY_FEAT", "22")),
                     help="host feature table has 2^k rows, indices masked (SAMGRAPH_EMPTY_FEAT semantics)")
-    ap.add_argument("--slots", type=int, default=int(os.environ.get("FGNN_BENCH_SLOTS", "4")),
-                    help="mini-batches in flight on separate streams (device-resident leg)")
+    ap.add_argument("--super", dest="super_batch", type=int, default=int(os.environ.get("FGNN_BENCH_SUPER", "4")),
+                    help="mini-batches per super-batch: one fgnn_k_sample_batch_multi call samples them together "
+                         "(two launches per layer for all of them); two super-batches alternate, one being sampled "
+                         "while the other is extracted (device-resident leg; the engine does the same)")
     ap.add_argument("--sample-type", default=os.environ.get("FGNN_BENCH_SAMPLE_TYPE", "khop2"),
                     choices=["khop2", "khop0", "khop1", "weighted_khop", "weighted_khop_prefix",
                              "weighted_khop_hash_dedup", "random_walk"],
@@ -61,7 +63,10 @@ def parse():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cache25", action="store_true", help="skip the extra 25 %% cache leg (profiling runs)")
     ap.add_argument("--no-partition", action="store_true",
-                    help="N > 1: skip the extra leg that stripes the feature cache over the GPUs (NVLink peer loads)")
+                    help="N > 1: skip the partitioned-cache legs (value is then the replicated-cache arm)")
+    ap.add_argument("--replicate-pct", type=float, default=float(os.environ.get("FGNN_BENCH_REPLICATE_PCT", "0.25")),
+                    help="N > 1, partitioned cache: fraction of the vertices (hottest PreSC ranks) that every GPU "
+                         "keeps a copy of; the rest of the cache is striped over the GPUs and read by NVLink peer loads")
     return ap.parse_args()
 
 
@@ -250,6 +255,15 @@ def workload_name(args):
         % (fanouts_of(args), args.sample_type, args.workload, args.cache_pct * 100)
 
 
+def shared_config(args, V, E, D, host_rows):
+    """config: byte-identical in both arms (--impl ours / reference); arm-specific remarks go to `notes`."""
+    return {"workload": workload_name(args), "batch": BATCH, "fanout": fanouts_of(args),
+            "sample_type": args.sample_type, "num_node": V, "num_edge": E, "feat_dim": D,
+            "synthetic_degree_exponent": 0.5, "cache_percentage": args.cache_pct,
+            "e2e_cache_percentage": E2E_CACHE_PCT, "host_feat_rows": host_rows,
+            "l2_policy": "inputs larger than L2 (GBs of topology and cache); no flush needed"}
+
+
 def peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -323,7 +337,7 @@ def run_ours(args):
         del weights
         torch.cuda.empty_cache()
     hp = HotPath(wl["indptr"], wl["indices"], V, fanouts, BATCH, args.sample_type, seed=0x5EED0000 + rank, device=dev,
-                 num_slots=args.slots, rw=RW if args.sample_type == "random_walk" else None, **tables)
+                 num_slots=2 * args.super_batch, rw=RW if args.sample_type == "random_walk" else None, **tables)
     steps_per_epoch = (wl["T"] + BATCH - 1) // BATCH
     # DistShuffler split (dist_shuffler.cc:60-83): rank r owns a contiguous range of the epoch's steps
     g = torch.Generator(device=dev)
@@ -361,66 +375,90 @@ def run_ours(args):
     presc_s = time.time() - t0
     hp.set_labels(wl["label"])
 
-    S = len(hp.slots)
-    s_streams = [torch.cuda.Stream(device=dev) for _ in range(S)]
+    G = args.super_batch
+    S = len(hp.slots)                      # two slot groups of G mini-batches
+    s_streams = [torch.cuda.Stream(device=dev) for _ in range(2)]
     x_stream = torch.cuda.Stream(device=dev, priority=-1)
 
-    def measure(cache_pct, Ksteps, W, key0, profile=False, partition=False):
+    def measure(cache_pct, Ksteps, W, key0, profile=False, partition=False, replicate_pct=None):
         """Build the cache at `cache_pct` (replicated per GPU, or with partition=True striped over the ranks'
         GPUs and read through NVLink peer mappings), run W warm-up + Ksteps timed steps; device-timed.
-        Like the engine's pump: batch k is sampled on slot k % S (own stream, own hash table and scratch) while
-        the extraction stream gathers the features of batch k-1; a slot is resampled only after its previous
-        batch has been gathered."""
+        Like the engine's pump: G mini-batches are sampled together by ONE fgnn_k_sample_batch_multi call on the
+        slot group's stream while the extraction stream gathers the features of the previous group's batches one
+        after the other; a slot group is resampled only after its batches have been gathered."""
         t0 = time.time()
         hp.cache = None
         hp.feat_out = None
         torch.cuda.empty_cache()
         shards = None
         if partition:
-            shards = P.CacheShards(rank_nodes, int(V * cache_pct), wl["host_feat"], row_bytes, wl["feat_mask"],
-                                   rank, world, dev)
+            n_cached = int(V * cache_pct)
+            n_repl = int(V * replicate_pct) if replicate_pct else 0
+            n_repl = min(n_repl, n_cached)
+            shards = P.CacheShards(rank_nodes, n_cached, wl["host_feat"], row_bytes, wl["feat_mask"],
+                                   rank, world, dev, num_replicated=n_repl)
             hp.build_cache(rank_nodes, cache_pct, wl["host_feat"], row_bytes, wl["feat_mask"], num_shards=world,
-                           shard_id=rank, peer_ptrs=shards.ptrs, fill_local=False)
+                           shard_id=rank, peer_ptrs=shards.ptrs, fill_local=False, num_replicated=n_repl,
+                           replica_ptr=shards.replica_ptr)
         else:
             hp.build_cache(rank_nodes, cache_pct, wl["host_feat"], row_bytes, wl["feat_mask"])
         torch.cuda.synchronize()
         cache_s = time.time() - t0
         hist = torch.zeros((Ksteps, hp.L, 3), dtype=torch.int32, device=dev)
-        ev = [[torch.cuda.Event(enable_timing=True) for _ in range(5)] for _ in range(Ksteps)]
-        sampled = [torch.cuda.Event() for _ in range(S)]
-        gathered = [torch.cuda.Event() for _ in range(S)]
+        n_groups = (Ksteps + G - 1) // G
+        gev = [[torch.cuda.Event(enable_timing=True) for _ in range(2)] for _ in range(n_groups)]
+        ev = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(Ksteps)]
+        sampled = [torch.cuda.Event() for _ in range(2)]
+        gathered = [torch.cuda.Event() for _ in range(2)]
         main = torch.cuda.current_stream()
 
-        def one_step(k, key, timed):
-            sd, n = seeds_of(k)
-            slot = k % S
-            with torch.cuda.stream(s_streams[slot]):
-                s_streams[slot].wait_event(gathered[slot])     # the slot's previous batch has been extracted
+        def one_group(gi, k0, nb, key, timed):
+            """steps k0 .. k0+nb-1 (timed: index of the first one in the timed region, or None)"""
+            grp = gi % 2
+            batches = []
+            for j in range(nb):
+                sd, n = seeds_of(k0 + j)
+                batches.append((sd, n, key + j, grp * G + j))
+            with torch.cuda.stream(s_streams[grp]):
+                s_streams[grp].wait_event(gathered[grp])       # the group's previous batches have been extracted
                 if timed is not None:
-                    timed[0].record()
-                hp.sample(sd, n, key, slot=slot)
+                    gev[timed // G][0].record()
+                if nb == 1:
+                    hp.sample(*batches[0][:3], slot=batches[0][3])
+                else:
+                    hp.sample_multi(batches)
                 if timed is not None:
-                    timed[1].record()
-                sampled[slot].record()
+                    gev[timed // G][1].record()
+                sampled[grp].record()
             with torch.cuda.stream(x_stream):
-                x_stream.wait_event(sampled[slot])
-                if timed is not None:
-                    timed[2].record()
-                hp.gather(slot)
-                if timed is not None:
-                    timed[3].record()
-                hp.gather_labels(sd, n)
-                if timed is not None:
-                    hist[k - W].copy_(hp.slots[slot].counts)
-                    timed[4].record()
-                gathered[slot].record()
+                x_stream.wait_event(sampled[grp])
+                for j, (sd, n, _, slot) in enumerate(batches):
+                    e = ev[timed + j] if timed is not None else None
+                    if e:
+                        e[0].record()
+                    hp.gather(slot)
+                    if e:
+                        e[1].record()
+                    hp.gather_labels(sd, n)
+                    if e:
+                        hist[timed + j].copy_(hp.slots[slot].counts)
+                        e[2].record()
+                gathered[grp].record()
+
+        def run(first_step, nsteps, key, timed):
+            gi = 0
+            for k0 in range(0, nsteps, G):
+                nb = min(G, nsteps - k0)
+                one_group(gi, first_step + k0, nb, key + k0, k0 if timed else None)
+                gi += 1
 
         for st in s_streams + [x_stream]:
             st.wait_stream(main)
-        for w in range(W):
-            one_step(w, key0 + w, None)
+        run(0, max(W, 2 * G), key0, False)       # warm-up covers both slot groups
+        Wd = max(W, 2 * G)
         torch.cuda.synchronize()
         hp.stats.zero_()
+        hp.remote.zero_()
         torch.cuda.synchronize()
         clocks = ClockSampler(local)
         clocks.start()
@@ -437,8 +475,7 @@ def run_ours(args):
         for st in s_streams + [x_stream]:
             st.wait_stream(main)
         th0 = time.perf_counter()
-        for k in range(Ksteps):
-            one_step(W + k, key0 + W + k, ev[k])
+        run(Wd, Ksteps, key0 + Wd, True)
         host_enqueue_s = time.perf_counter() - th0
         for st in s_streams + [x_stream]:
             main.wait_stream(st)
@@ -453,12 +490,14 @@ def run_ours(args):
         h = hist.cpu().numpy().astype("int64")
         r["edges"] = int(h[:, :, 1].sum())
         r["n_in_total"] = int(h[:, 0, 2].sum())       # input_nodes of every step (num_src of layer 0)
-        r["sample_ms"] = sum(e[0].elapsed_time(e[1]) for e in ev)    # per-slot stream time of the sampling chain
-        r["gather_ms"] = sum(e[2].elapsed_time(e[3]) for e in ev)    # the gather kernel alone, on its stream
-        r["extract_ms"] = sum(e[2].elapsed_time(e[4]) for e in ev)   # gather + label gather
+        r["sample_ms"] = sum(e[0].elapsed_time(e[1]) for e in gev)   # the slot groups' stream time of the sampling chain
+        r["gather_ms"] = sum(e[0].elapsed_time(e[1]) for e in ev)    # the gather kernel alone, on its stream
+        r["extract_ms"] = sum(e[0].elapsed_time(e[2]) for e in ev)   # gather + label gather
         r["hits"], r["misses"] = [int(x) for x in hp.stats.tolist()]
+        r["remote"] = int(hp.remote.item())           # rows read from peer shards over NVLink (counted by the kernel)
         if shards is not None:
             r["shard_bytes"] = shards.nbytes
+            r["replica_bytes"] = shards.replica_bytes
             hp.cache_table = hp.shard_ptrs = None
             shards.close()
         return r
@@ -517,23 +556,49 @@ def run_ours(args):
         serial = {"error": repr(ex)[:200]}
     ms_total, edges_all = aggregate(ms_total, edges, dev)
 
-    # ---- N > 1: the same workload with the cache striped over the ranks' GPUs (north_star):
-    # every GPU keeps 1/N of the rows, (N-1)/N of the hit rows are NVLink peer loads inside the gather kernel.
-    part = None
+    # ---- N > 1: the same workload with the cache PARTITIONED over the ranks' GPUs (north_star).
+    # hybrid: every GPU keeps the hottest --replicate-pct of the vertices, the tail of the cache is striped over the
+    # GPUs and read by NVLink peer loads inside the gather kernel; striped: no replicated head (round 1's layout).
+    part = part_striped = None
     if world > 1 and not args.no_partition:
-        hp.cache = None
-        torch.cuda.empty_cache()
-        kp = min(Ksteps, 2 * steps_per_epoch)
-        rp = measure(args.cache_pct, kp, W, 3_000_000, partition=True)
-        p_ms, p_edges = aggregate(rp["ms_total"], rp["edges"], dev)
-        remote = rp["hits"] * (world - 1) / world * row_bytes       # slots are striped slot % N: uniform
-        part = {"note": "cache striped over the %d GPUs (slot %% N), remote rows read by NVLink peer loads inside "
-                        "fgnn_k_gather_cached; population = PreSC ranking broadcast + each rank fills its stripe" % world,
-                "edges_per_s": p_edges / (p_ms * 1e-3), "ms_per_step": p_ms / kp, "steps": kp,
-                "gather_ms_per_step": rp["gather_ms"] / kp, "shard_GB_per_gpu": rp["shard_bytes"] / 1e9,
-                "nvlink_peer_GBps_per_gpu": remote / (rp["gather_ms"] * 1e-3) / 1e9 if rp["gather_ms"] else None,
-                "nvlink_peak_GBps": 900.0, "cache_hit_rate": rp["hits"] / max(1, rp["hits"] + rp["misses"]),
-                "extract_GBps_per_gpu": rp["n_in_total"] * row_bytes / (rp["gather_ms"] * 1e-3) / 1e9}
+        def part_leg(replicate_pct, key0):
+            hp.cache = None
+            torch.cuda.empty_cache()
+            kp = Ksteps
+            rp = measure(args.cache_pct, kp, W, key0, partition=True, replicate_pct=replicate_pct)
+            p_ms, p_edges = aggregate(rp["ms_total"], rp["edges"], dev)
+            remote = rp["remote"] * row_bytes
+            return {"edges_per_s": p_edges / (p_ms * 1e-3), "ms_per_step": p_ms / kp, "steps": kp,
+                    "replicate_pct": replicate_pct, "gather_ms_per_step": rp["gather_ms"] / kp,
+                    "shard_GB_per_gpu": rp["shard_bytes"] / 1e9, "replica_GB_per_gpu": rp["replica_bytes"] / 1e9,
+                    "remote_row_fraction": rp["remote"] / max(1, rp["hits"] + rp["misses"]),
+                    "nvlink_peer_GBps_per_gpu": remote / (rp["gather_ms"] * 1e-3) / 1e9 if rp["gather_ms"] else None,
+                    "nvlink_peak_GBps": 900.0, "cache_hit_rate": rp["hits"] / max(1, rp["hits"] + rp["misses"]),
+                    "extract_GBps_per_gpu": rp["n_in_total"] * row_bytes / (rp["gather_ms"] * 1e-3) / 1e9,
+                    "edges": p_edges, "ms_total": p_ms, "raw": rp}
+        part = part_leg(args.replicate_pct, 3_000_000)
+        part["note"] = ("cache partitioned over the %d GPUs: the hottest %.0f%% of the vertices (PreSC ranks) on every "
+                        "GPU, the rest striped (slot %% N) and read by NVLink peer loads inside fgnn_k_gather_cached_layout; "
+                        "remote rows counted by the kernel; population = PreSC ranking broadcast + each rank fills its "
+                        "own stripe and replica" % (world, args.replicate_pct * 100))
+        if args.replicate_pct > 0:
+            part_striped = part_leg(0.0, 4_000_000)
+            part_striped["note"] = "no replicated head: every cached row striped over the GPUs (round 1's layout)"
+
+    replicated = None
+    if part is not None:
+        # N > 1: the headline is the PARTITIONED arm (north_star); the replicated-cache arm moves to extra
+        replicated = {"note": "every GPU holds the whole cache (the 57 GB table fits one B200): N independent replicas, "
+                              "no NVLink traffic", "edges_per_s": edges_all / (ms_total * 1e-3),
+                      "ms_per_step": ms_total / Ksteps, "gather_ms_per_step": gather_ms / Ksteps}
+        hr = part.pop("raw")
+        ms_total, edges_all = part.pop("ms_total"), part.pop("edges")
+        edges, n_in_total = hr["edges"], hr["n_in_total"]
+        sample_ms, gather_ms, hits, misses = hr["sample_ms"], hr["gather_ms"], hr["hits"], hr["misses"]
+        launches, clk, cache_s, r = hr["launches"], hr["clk"], hr["cache_s"], hr
+        if part_striped is not None:
+            for k in ("raw", "ms_total", "edges"):
+                part_striped.pop(k)
 
     # ---- roofline of the dominant kernel: the fused cache-aware feature gather -----------
     peak, peak_kind = peaks()
@@ -549,7 +614,8 @@ def run_ours(args):
                               "next to it, so the per-stream times add up to more than the wall time)",
                 "serialised": serial,
                 "timing": "CUDA events on the extraction stream around every gather launch of the timed region; "
-                          "%d sampling slots run concurrently on other streams and share HBM with it" % len(hp.slots),
+                          "super-batches of %d mini-batches are sampled concurrently on two other streams and share "
+                          "HBM with it" % G,
                 "alone": {"avg_launch_ms": gather_alone_ms, "bytes_per_launch": n_alone * (4 + 2 * row_bytes),
                           "achieved": round(n_alone * (4 + 2 * row_bytes) / (gather_alone_ms * 1e-3) / 1e9, 1),
                           "frac": round(n_alone * (4 + 2 * row_bytes) / (gather_alone_ms * 1e-3) / 1e9 / peak, 4),
@@ -559,16 +625,12 @@ def run_ours(args):
         "metric": METRIC, "value": edges_all / (ms_total * 1e-3), "unit": UNIT, "n_gpus": world,
         "steps": Ksteps, "warmup": W, "ms_per_step": ms_total / Ksteps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": DTYPE, "data": "synthetic",
-        "config": {"workload": workload_name(args),
-                   "dtype_note": "u32 ids / hashes / counts; f32 feature rows and i64 labels are byte copies",
-                   "batches_in_flight": len(hp.slots),
-                   "num_node": V, "num_edge": wl["E"], "feat_dim": D, "cache_percentage": args.cache_pct,
-                   "e2e_cache_percentage": E2E_CACHE_PCT,
-                   "host_feat_rows": int(wl["host_feat"].shape[0]),
-                   "l2_policy": "inputs larger than L2 (6.9 GB topology, %.1f GB cache)" % (hp.num_cached * row_bytes / 1e9),
-                   "sharding": "seed mini-batches split across ranks (no data-path collective); topology replicated; "
-                               "cache replicated for `value` (the 57 GB table fits one B200), striped over the GPUs "
-                               "with NVLink peer loads in extra.partitioned_cache; PreSC ranking: NCCL all-reduce + broadcast at init"},
+        "config": shared_config(args, V, wl["E"], D, int(wl["host_feat"].shape[0])),
+        "notes": {"dtype_note": "u32 ids / hashes / counts; f32 feature rows and i64 labels are byte copies",
+                  "batches_in_flight": len(hp.slots), "super_batch": G,
+                  "cache_GB": hp.num_cached * row_bytes / 1e9,
+                  "sharding": "seed mini-batches split across ranks (no data-path collective); topology replicated; "
+                              "N = 1: whole cache in HBM; PreSC ranking: NCCL all-reduce + broadcast at init"},
         "clocks": clk, "gpu_launches": int(launches),
         "roofline": roofline,
         "extra": {"sample_only_edges_per_s": edges / (sample_ms * 1e-3) if sample_ms else None,
@@ -584,6 +646,14 @@ def run_ours(args):
     }
     if part is not None:
         out["extra"]["partitioned_cache"] = part
+        out["extra"]["replicated_cache"] = replicated
+        if part_striped is not None:
+            out["extra"]["partitioned_cache_striped"] = part_striped
+        out["notes"]["sharding"] = ("seed mini-batches split across ranks (no data-path collective); topology replicated; "
+                                     "feature cache PARTITIONED over the GPUs for `value` (hottest %.0f%% of the vertices on "
+                                     "every GPU, the rest striped and read by NVLink peer loads); PreSC ranking: NCCL "
+                                     "all-reduce + broadcast at init; extra.replicated_cache = a full replica per GPU"
+                                     % (args.replicate_pct * 100))
     if r25 is not None:
         k25 = min(Ksteps, steps_per_epoch)
         out["extra"]["cache25"] = {
@@ -597,7 +667,7 @@ def run_ours(args):
     # ---- e2e through the host runtime (samgraph_* C-ABI) with host buffers ------------------
     if not is_headline(args):
         args.no_e2e = args.no_cpu_baseline = True      # those legs are defined for the headline configuration
-        out["config"]["note"] = "non-headline sampler / fanout: device-resident leg only"
+        out["notes"]["legs"] = "non-headline sampler / fanout: device-resident leg only"
     if not args.no_e2e:
         # release the device-resident leg's buffers first: the engine child builds its own cache
         hp.cache = hp.feat_out = hp.cache_table = None
@@ -765,9 +835,9 @@ def run_reference(args):
            "n_gpus": int(os.environ.get("WORLD_SIZE", "1")), "steps": cb["steps"], "warmup": 1,
            "ms_per_step": cb["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
            "dtype": DTYPE, "data": "synthetic",
-           "config": {"workload": workload_name(args), "num_node": wl["V"], "num_edge": wl["E"], "feat_dim": wl["D"],
-                      "reference_path": "CPUSampleKHop2 + CPUHashTable2 + CPUExtract on the host cores: every feature row "
-                                        "is read from host memory (no GPU, no cache)"},
+           "config": shared_config(args, wl["V"], wl["E"], wl["D"], int(wl["host_feat"].shape[0])),
+           "notes": {"reference_path": "CPUSampleKHop2 + CPUHashTable2 + CPUExtract on the host cores: every feature row "
+                                       "is read from host memory (no GPU, no cache)"},
            "cpu_baseline": cb,
            "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(out))

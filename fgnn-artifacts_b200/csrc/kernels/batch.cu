@@ -32,8 +32,14 @@ extern "C" int fgnn_k_sample_batch(const fgnn_sample_plan *pl, const fgnn_sample
   // bit 2 = khop2 writes a padded [seed][fanout] block and ONE chained scan (in the unique/remap pass) compacts
   // the edges and numbers the new ids (3 launches per layer, one look-back chain instead of two; ncu r1_q c4/c7:
   // sampler 18+39 us -> 10+24 us per batch; on)
+  // bit 3 = the two-launch-per-layer chain of fast_chain.cu (sampler with compacted Fisher-Yates lanes that
+  // inserts its picks, register-resident compaction with a direct-sum scan, versioned table; on)
   const char *fz = getenv("FGNN_BATCH_FUSE");
-  const int fuse = fz && *fz ? atoi(fz) : 6;
+  const int fuse = fz && *fz ? atoi(fz) : 14;
+  if ((fuse & 8) && fast_chain_supported(pl)) {
+    trace_mark(st, FGNN_TRACE_BATCH_BEGIN);
+    return fast_chain_launch(&pl, &out, &seeds, &n_seeds_max, &d_n_seeds, &batch_key, 1, st);
+  }
 
   // Reset (cuda_loops.cc:63) + FillWithUnique of the seeds (:67-69); the seed count doubles as the
   // input count of the first sampled layer
@@ -117,4 +123,58 @@ extern "C" int fgnn_k_sample_batch(const fgnn_sample_plan *pl, const fgnn_sample
     }
   }
   return 0;
+}
+
+extern "C" int fgnn_k_sample_batch_multi(const fgnn_sample_plan *const *plans, const fgnn_sample_out *const *outs,
+                                         const uint32_t *const *seeds, const uint32_t *n_seeds_max,
+                                         const uint64_t *batch_keys, uint32_t num_batches,
+                                         fgnn_stream_t stream) {
+  if (!plans || !outs || !seeds || !n_seeds_max || !batch_keys) return FGNN_ERR_BAD_ARG;
+  if (num_batches == 0) return 0;
+  if (num_batches > FGNN_MAX_SUPER) return FGNN_ERR_UNSUPPORTED;
+  const char *fz = getenv("FGNN_BATCH_FUSE");
+  const int fuse = fz && *fz ? atoi(fz) : 14;
+  bool fast = (fuse & 8) != 0;
+  for (uint32_t k = 0; k < num_batches; ++k) {
+    const fgnn_sample_plan *pl = plans[k];
+    if (!pl || !outs[k] || !pl->indptr || !pl->indices || !pl->table || !pl->num_items || !pl->chain_ws ||
+        !outs[k]->n2o || !outs[k]->counts)
+      return FGNN_ERR_BAD_ARG;
+    const uint32_t L = pl->num_layers;
+    if (L == 0 || L > FGNN_MAX_LAYERS) return FGNN_ERR_UNSUPPORTED;
+    if ((pl->capacity & (pl->capacity - 1)) || pl->capacity > 0x80000000ull) return FGNN_ERR_BAD_ARG;
+    if (n_seeds_max[k] > pl->in_max[L - 1] || (n_seeds_max[k] > 0 && !seeds[k])) return FGNN_ERR_BAD_ARG;
+    // one configuration per super-batch
+    if (pl->sample_type != plans[0]->sample_type || L != plans[0]->num_layers || pl->capacity != plans[0]->capacity ||
+        pl->indptr != plans[0]->indptr || pl->indices != plans[0]->indices || pl->seed != plans[0]->seed)
+      return FGNN_ERR_BAD_ARG;
+    for (uint32_t i = 0; i < L; ++i) {
+      if (pl->fanout[i] != plans[0]->fanout[i] || pl->in_max[i] != plans[0]->in_max[i]) return FGNN_ERR_BAD_ARG;
+      if (!pl->pos[i] || !outs[k]->row[i] || !outs[k]->col[i]) return FGNN_ERR_BAD_ARG;
+    }
+    for (uint32_t j = 0; j < k; ++j)
+      if (plans[j]->table == pl->table || outs[j]->n2o == outs[k]->n2o || plans[j]->chain_ws == pl->chain_ws)
+        return FGNN_ERR_BAD_ARG;  // mini-batches of one launch run concurrently: nothing may be shared
+    if (!fast_chain_supported(pl)) fast = false;
+  }
+  if (fast) {
+    trace_mark((cudaStream_t)stream, FGNN_TRACE_BATCH_BEGIN);
+    return fast_chain_launch(plans, outs, seeds, n_seeds_max, nullptr, batch_keys, num_batches, (cudaStream_t)stream);
+  }
+  for (uint32_t k = 0; k < num_batches; ++k) {
+    const int rc = fgnn_k_sample_batch(plans[k], outs[k], seeds[k], n_seeds_max[k], nullptr, batch_keys[k], stream);
+    if (rc) return rc;
+  }
+  return 0;
+}
+
+extern "C" uint32_t fgnn_k_ht_next_version(uint32_t *state, void *table, size_t capacity, fgnn_stream_t stream) {
+  if (!state || !table) return 0;
+  uint32_t v = *state + 1;
+  if (*state == 0 || v > 126) {  // first use or wrap: no bucket may keep a tag that is about to be reused
+    cudaMemsetAsync(table, 0xFF, capacity * sizeof(Bucket), (cudaStream_t)stream);
+    v = 1;
+  }
+  *state = v;
+  return v;
 }

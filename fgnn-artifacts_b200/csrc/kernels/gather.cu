@@ -74,67 +74,7 @@ row_copy_kernel(char *__restrict__ dst, const uint32_t *__restrict__ dst_index,
   }
 }
 
-template <typename V>
-__global__ void __launch_bounds__(kBlock)
-gather_cached_kernel(char *__restrict__ out, const uint32_t *__restrict__ nodes, uint32_t n_max,
-                     const uint32_t *__restrict__ d_n, const uint32_t *__restrict__ table,
-                     const void *const *__restrict__ shards, uint32_t num_shards,
-                     const char *__restrict__ miss_src, uint64_t miss_mask, size_t row_bytes,
-                     uint32_t cpr, unsigned long long *d_stats) {
-  const uint32_t n = load_count(n_max, d_n);
-  const uint64_t total = (uint64_t)n * cpr;
-  const uint64_t stride = (uint64_t)gridDim.x * kBlock;
-  const char *shard0 = (const char *)__ldg((const unsigned long long *)shards);
-  uint32_t hits = 0, misses = 0;
-  for (uint64_t c0 = (uint64_t)blockIdx.x * kBlock + threadIdx.x; c0 < total;
-       c0 += stride * kUnroll) {
-    V v[kUnroll];
-    char *dp[kUnroll];
-#pragma unroll
-    for (int u = 0; u < kUnroll; ++u) {
-      const uint64_t c = c0 + u * stride;
-      dp[u] = nullptr;
-      if (c < total) {
-        const uint32_t row = (uint32_t)(c / cpr);
-        const uint32_t col = (uint32_t)(c - (uint64_t)row * cpr);
-        const uint32_t node = __ldg(nodes + row);
-        const uint32_t slot = __ldg(table + node);
-        const char *sp;
-        if (slot != kEmpty) {
-          if (num_shards == 1) {
-            sp = shard0 + (size_t)slot * row_bytes;
-          } else {  // striped: owner = slot mod T, local row = slot div T
-            const uint32_t owner = slot % num_shards;
-            const uint32_t lrow = slot / num_shards;
-            sp = (const char *)__ldg((const unsigned long long *)shards + owner) +
-                 (size_t)lrow * row_bytes;
-          }
-          hits += (col == 0);
-        } else {
-          sp = miss_src + ((uint64_t)node & miss_mask) * row_bytes;
-          misses += (col == 0);
-        }
-        v[u] = VecIO<V>::ld(sp + (size_t)col * sizeof(V));
-        dp[u] = out + (size_t)row * row_bytes + (size_t)col * sizeof(V);
-      }
-    }
-#pragma unroll
-    for (int u = 0; u < kUnroll; ++u)
-      if (dp[u]) VecIO<V>::st(dp[u], v[u]);
-  }
-  if (d_stats) {
-#pragma unroll
-    for (int d = 16; d > 0; d >>= 1) {
-      hits += __shfl_down_sync(0xFFFFFFFFu, hits, d);
-      misses += __shfl_down_sync(0xFFFFFFFFu, misses, d);
-    }
-    if ((threadIdx.x & 31) == 0) {
-      if (hits) atomicAdd(d_stats + 0, (unsigned long long)hits);
-      if (misses) atomicAdd(d_stats + 1, (unsigned long long)misses);
-    }
-  }
-}
-
+// (gather_cached_kernel<V>, the flat variant for rows that are not 16-byte multiples, follows RowSrc below)
 
 // ---------------------------------------------------------------------------
 // Warp-group gather (16-byte rows, production path of the LDG family).
@@ -151,6 +91,11 @@ gather_cached_kernel(char *__restrict__ out, const uint32_t *__restrict__ nodes,
 constexpr int kGroupUnroll = 8;
 constexpr uint32_t kGroupChunks = 32 * kGroupUnroll;  // chunks of one pass
 
+// Where a row lives.  Cache slot s (= position in the hotness ranking):
+//   s <  num_replicated : on THIS GPU, row s of `replica` (the hottest rows are replicated on every trainer)
+//   s >= num_replicated : striped, owner = (s - R) mod T, local row = (s - R) div T of that owner's shard
+//                         (own shard: HBM; a peer's: loads over NVLink through the IPC mapping)
+//   EMPTY               : the pinned host feature table (UVA, host link)
 struct RowSrc {
   const void *const *shards;
   const char *shard0;
@@ -158,15 +103,79 @@ struct RowSrc {
   const char *miss_src;
   uint64_t miss_mask;
   size_t row_bytes;
+  const char *replica;
+  uint32_t num_replicated, self_shard;
+  unsigned long long *d_remote;  // optional: rows read from peer shards
   __device__ __forceinline__ const char *resolve(uint32_t node, uint32_t slot) const {
     if (slot != kEmpty) {
-      if (num_shards == 1) return shard0 + (size_t)slot * row_bytes;
-      const uint32_t owner = slot % num_shards, lrow = slot / num_shards;
+      if (slot < num_replicated) return replica + (size_t)slot * row_bytes;
+      const uint32_t s = slot - num_replicated;
+      if (num_shards == 1) return shard0 + (size_t)s * row_bytes;
+      const uint32_t owner = s % num_shards, lrow = s / num_shards;
       return (const char *)__ldg((const unsigned long long *)shards + owner) + (size_t)lrow * row_bytes;
     }
     return miss_src + ((uint64_t)node & miss_mask) * row_bytes;
   }
+  __device__ __forceinline__ bool is_remote(uint32_t slot) const {
+    return slot != kEmpty && slot >= num_replicated && num_shards > 1 &&
+           (slot - num_replicated) % num_shards != self_shard;
+  }
+  // warp-reduced counters -> d_stats[0] hits, [1] misses; *d_remote rows read from peer shards
+  __device__ __forceinline__ void report(unsigned long long *d_stats, uint32_t hits, uint32_t misses,
+                                         uint32_t remote) const {
+    if (!d_stats && !d_remote) return;
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) {
+      hits += __shfl_down_sync(0xFFFFFFFFu, hits, d);
+      misses += __shfl_down_sync(0xFFFFFFFFu, misses, d);
+      remote += __shfl_down_sync(0xFFFFFFFFu, remote, d);
+    }
+    if ((threadIdx.x & 31) == 0) {
+      if (d_stats && hits) atomicAdd(d_stats + 0, (unsigned long long)hits);
+      if (d_stats && misses) atomicAdd(d_stats + 1, (unsigned long long)misses);
+      if (d_remote && remote) atomicAdd(d_remote, (unsigned long long)remote);
+    }
+  }
 };
+
+template <typename V>
+__global__ void __launch_bounds__(kBlock)
+gather_cached_kernel(char *__restrict__ out, const uint32_t *__restrict__ nodes, uint32_t n_max,
+                     const uint32_t *__restrict__ d_n, const uint32_t *__restrict__ table, RowSrc rs,
+                     uint32_t cpr, unsigned long long *d_stats) {
+  rs.shard0 = (const char *)__ldg((const unsigned long long *)rs.shards);
+  const uint32_t n = load_count(n_max, d_n);
+  const uint64_t total = (uint64_t)n * cpr;
+  const uint64_t stride = (uint64_t)gridDim.x * kBlock;
+  uint32_t hits = 0, misses = 0, remote = 0;
+  for (uint64_t c0 = (uint64_t)blockIdx.x * kBlock + threadIdx.x; c0 < total;
+       c0 += stride * kUnroll) {
+    V v[kUnroll];
+    char *dp[kUnroll];
+#pragma unroll
+    for (int u = 0; u < kUnroll; ++u) {
+      const uint64_t c = c0 + u * stride;
+      dp[u] = nullptr;
+      if (c < total) {
+        const uint32_t row = (uint32_t)(c / cpr);
+        const uint32_t col = (uint32_t)(c - (uint64_t)row * cpr);
+        const uint32_t node = __ldg(nodes + row);
+        const uint32_t slot = __ldg(table + node);
+        const char *sp = rs.resolve(node, slot);
+        if (col == 0) {
+          if (slot != kEmpty) ++hits; else ++misses;
+          if (rs.is_remote(slot)) ++remote;
+        }
+        v[u] = VecIO<V>::ld(sp + (size_t)col * sizeof(V));
+        dp[u] = out + (size_t)row * rs.row_bytes + (size_t)col * sizeof(V);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < kUnroll; ++u)
+      if (dp[u]) VecIO<V>::st(dp[u], v[u]);
+  }
+  rs.report(d_stats, hits, misses, remote);
+}
 
 __device__ __forceinline__ const char *shfl_ptr(const char *p, int src) {
   unsigned long long v = (unsigned long long)p;
@@ -196,7 +205,7 @@ gather_group_kernel(char *__restrict__ out, const uint32_t *__restrict__ nodes, 
       cmap[k] = (r << 24) | ((c - r * cpr) * 16u);
     }
   }
-  uint32_t hits = 0, misses = 0;
+  uint32_t hits = 0, misses = 0, remote = 0;
   auto load_node = [&](uint32_t gg) -> uint32_t {
     const uint64_t row = (uint64_t)gg * G + lane;
     return (gg < groups && lane < G && row < n) ? __ldg(nodes + row) : kEmpty;
@@ -210,6 +219,7 @@ gather_group_kernel(char *__restrict__ out, const uint32_t *__restrict__ nodes, 
     if (node_c != kEmpty) {
       sp = rs.resolve(node_c, slot_c);
       if (slot_c != kEmpty) ++hits; else ++misses;
+      if (rs.is_remote(slot_c)) ++remote;
     }
     // stage the next groups' index loads before streaming this one
     const uint32_t slot_n = node_n != kEmpty ? __ldg(table + node_n) : kEmpty;
@@ -247,17 +257,7 @@ gather_group_kernel(char *__restrict__ out, const uint32_t *__restrict__ nodes, 
     slot_c = slot_n;
     node_n = node_nn;
   }
-  if (d_stats) {
-#pragma unroll
-    for (int d = 16; d > 0; d >>= 1) {
-      hits += __shfl_down_sync(0xFFFFFFFFu, hits, d);
-      misses += __shfl_down_sync(0xFFFFFFFFu, misses, d);
-    }
-    if (lane == 0) {
-      if (hits) atomicAdd(d_stats + 0, (unsigned long long)hits);
-      if (misses) atomicAdd(d_stats + 1, (unsigned long long)misses);
-    }
-  }
+  rs.report(d_stats, hits, misses, remote);
 }
 
 // ---------------------------------------------------------------------------
@@ -371,7 +371,7 @@ gather_bulk_kernel(char *__restrict__ out, const uint32_t *__restrict__ nodes, u
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncwarp();
-  uint32_t hits = 0, misses = 0;
+  uint32_t hits = 0, misses = 0, remote = 0;
   auto load_node = [&](uint32_t m) -> uint32_t {  // super-group m of this warp: rows r0+32m+lane
     const uint64_t row = r0 + (uint64_t)m * 32 + lane;
     return row < r_end ? __ldg(nodes + row) : kEmpty;
@@ -383,7 +383,7 @@ gather_bulk_kernel(char *__restrict__ out, const uint32_t *__restrict__ nodes, u
   uint32_t slot_n = node_n != kEmpty ? __ldg(table + node_n) : kEmpty;
   uint32_t node_nn = load_node(2);
   const char *sp = node_i != kEmpty ? rs.resolve(node_i, slot_i) : nullptr;
-  if (node_i != kEmpty) { if (slot_i != kEmpty) ++hits; else ++misses; }
+  if (node_i != kEmpty) { if (slot_i != kEmpty) ++hits; else ++misses; if (rs.is_remote(slot_i)) ++remote; }
 
   // issue the loads of this warp's sub-group number j (all lanes call)
   auto issue = [&](uint32_t j) {
@@ -394,7 +394,7 @@ gather_bulk_kernel(char *__restrict__ out, const uint32_t *__restrict__ nodes, u
       slot_n = node_n != kEmpty ? __ldg(table + node_n) : kEmpty;
       node_nn = load_node(j / spg + 2);
       sp = node_i != kEmpty ? rs.resolve(node_i, slot_i) : nullptr;
-      if (node_i != kEmpty) { if (slot_i != kEmpty) ++hits; else ++misses; }
+      if (node_i != kEmpty) { if (slot_i != kEmpty) ++hits; else ++misses; if (rs.is_remote(slot_i)) ++remote; }
     }
     const uint32_t s = j % S;
     const uint32_t bar = smem_u32(&s_bar[warp][s]);
@@ -439,180 +439,9 @@ gather_bulk_kernel(char *__restrict__ out, const uint32_t *__restrict__ nodes, u
     }
   }
   if (lane == 0) bulk_wait_read<0>();
-  if (d_stats) {
-#pragma unroll
-    for (int d = 16; d > 0; d >>= 1) {
-      hits += __shfl_down_sync(0xFFFFFFFFu, hits, d);
-      misses += __shfl_down_sync(0xFFFFFFFFu, misses, d);
-    }
-    if (lane == 0) {
-      if (hits) atomicAdd(d_stats + 0, (unsigned long long)hits);
-      if (misses) atomicAdd(d_stats + 1, (unsigned long long)misses);
-    }
-  }
+  rs.report(d_stats, hits, misses, remote);
 }
 
-
-// ---------------------------------------------------------------------------
-// Bulk-copy gather with DYNAMIC work distribution.
-//
-// gather_bulk_kernel above cuts the rows into one static contiguous range per warp.  That is optimal when the
-// kernel owns the GPU, but in the pipelined loop the sampling kernels of the other slots hold SM resources when
-// the gather launches: some of its 148 CTAs are placed tens of microseconds late and, with a static partition,
-// the whole kernel waits for them (bench r1_p: 0.109 ms alone, 0.18 ms in the loop).  Here warps take
-// 32-row super-groups from a global ticket counter, three tickets ahead (the index pipeline needs the node ids
-// of the next two super-groups), so late CTAs simply take fewer tickets.  Everything else — per-warp
-// shared-memory ring, cp.async.bulk loads counted on mbarriers, one bulk store per stage — is unchanged.
-// `tick` = {next ticket, finished CTAs}; the last CTA to finish re-zeroes it for the next launch.
-// ---------------------------------------------------------------------------
-constexpr int kSgQueue = 16;  // >= S - 2 super-groups can lie between the issue and the store cursor
-
-template <int S, int NW>
-__global__ void __launch_bounds__(NW * 32)
-gather_bulk_dyn_kernel(char *__restrict__ out, const uint32_t *__restrict__ nodes, uint32_t n_max,
-                       const uint32_t *__restrict__ d_n, const uint32_t *__restrict__ table,
-                       RowSrc rs, uint32_t G, uint32_t stage_bytes, int mode,
-                       unsigned long long *d_stats, unsigned int *tick) {
-  rs.shard0 = (const char *)__ldg((const unsigned long long *)rs.shards);
-  const bool hint = (mode & 2) != 0;
-  const int miss_by_ldg = mode & 1;
-  const uint64_t pol = l2_evict_first_policy();
-  constexpr uint32_t A = S - 2;
-  static_assert(S - 2 <= kSgQueue, "super-group queue too short");
-  extern __shared__ __align__(128) unsigned char s_raw[];
-  __shared__ __align__(8) unsigned long long s_bar[NW][S];
-  __shared__ uint32_t s_sgbase[NW][kSgQueue];
-  const uint32_t n = load_count(n_max, d_n);
-  const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const uint32_t nsg = (n + 31u) / 32u;
-  const uint32_t row_bytes = (uint32_t)rs.row_bytes;
-  unsigned char *stage0 = s_raw + (size_t)warp * S * stage_bytes;
-  if (lane == 0) {
-#pragma unroll
-    for (int s = 0; s < S; ++s) mbar_init(smem_u32(&s_bar[warp][s]), 1);
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  }
-  __syncwarp();
-  uint32_t hits = 0, misses = 0;
-  auto take = [&]() -> uint32_t {  // row base of this warp's next super-group, kEmpty when none is left
-    uint32_t t = 0;
-    if (lane == 0) t = atomicAdd(tick, 1u);
-    t = __shfl_sync(0xFFFFFFFFu, t, 0);
-    return t < nsg ? t * 32u : kEmpty;
-  };
-  auto load_node = [&](uint32_t base) -> uint32_t {
-    return (base != kEmpty && base + lane < n) ? __ldg(nodes + base + lane) : kEmpty;
-  };
-  auto subs_of = [&](uint32_t base) -> uint32_t {
-    const uint32_t rows = n - base < 32u ? n - base : 32u;
-    return (rows + G - 1) / G;
-  };
-
-  // index pipeline: super-group being issued (i), the next one (n) and the one after (nn)
-  uint32_t base_i = take();
-  uint32_t base_n = base_i != kEmpty ? take() : kEmpty;
-  uint32_t base_nn = base_n != kEmpty ? take() : kEmpty;
-  uint32_t node_i = load_node(base_i), node_n = load_node(base_n), node_nn = load_node(base_nn);
-  uint32_t slot_i = node_i != kEmpty ? __ldg(table + node_i) : kEmpty;
-  uint32_t slot_n = node_n != kEmpty ? __ldg(table + node_n) : kEmpty;
-  const char *sp = node_i != kEmpty ? rs.resolve(node_i, slot_i) : nullptr;
-  if (node_i != kEmpty) { if (slot_i != kEmpty) ++hits; else ++misses; }
-  bool exhausted = base_i == kEmpty;
-  uint32_t subs_i = exhausted ? 0u : subs_of(base_i);
-  uint32_t q_issue = 0, sub_issue = 0, issued = 0;
-  uint32_t q_store = 0, sub_store = 0, stored = 0;
-  if (lane == 0) s_sgbase[warp][0] = base_i;
-  __syncwarp();
-
-  while (true) {
-    while (!exhausted && issued <= stored + A) {
-      // the stage about to be refilled was stored two stores ago: one younger store may still be reading
-      if (lane == 0) bulk_wait_read<1>();
-      __syncwarp();
-      const uint32_t s = issued % S;
-      const uint32_t bar = smem_u32(&s_bar[warp][s]);
-      unsigned char *st = stage0 + (size_t)s * stage_bytes;
-      const bool mine = (lane / G) == sub_issue && node_i != kEmpty;
-      const bool by_bulk = mine && (slot_i != kEmpty || !miss_by_ldg);
-      const uint32_t nbulk = __popc(__ballot_sync(0xFFFFFFFFu, by_bulk));
-      if (lane == 0) mbar_expect_tx(bar, nbulk * row_bytes);
-      __syncwarp();
-      if (by_bulk) {
-        if (hint) bulk_g2s(smem_u32(st + (size_t)(lane - sub_issue * G) * row_bytes), sp, row_bytes, bar, pol);
-        else bulk_g2s(smem_u32(st + (size_t)(lane - sub_issue * G) * row_bytes), sp, row_bytes, bar);
-      }
-      uint32_t ldg_rows = __ballot_sync(0xFFFFFFFFu, mine && !by_bulk);
-      while (ldg_rows) {  // host-resident rows: warp-wide 16-byte loads into the stage
-        const int r = __ffs(ldg_rows) - 1;
-        ldg_rows &= ldg_rows - 1;
-        const char *p = shfl_ptr(sp, r);
-        for (uint32_t c = lane * 16u; c < row_bytes; c += 32u * 16u)
-          *reinterpret_cast<uint4 *>(st + (size_t)(r - sub_issue * G) * row_bytes + c) = ld_nc_na_v4(p + c);
-      }
-      ++issued;
-      if (++sub_issue == subs_i) {  // rotate the index pipeline into the next super-group
-        base_i = base_n; node_i = node_n; slot_i = slot_n;
-        base_n = base_nn; node_n = node_nn;
-        slot_n = node_n != kEmpty ? __ldg(table + node_n) : kEmpty;
-        base_nn = base_n != kEmpty ? take() : kEmpty;
-        node_nn = load_node(base_nn);
-        sub_issue = 0;
-        ++q_issue;
-        if (base_i == kEmpty) {
-          exhausted = true;
-        } else {
-          sp = node_i != kEmpty ? rs.resolve(node_i, slot_i) : nullptr;
-          if (node_i != kEmpty) { if (slot_i != kEmpty) ++hits; else ++misses; }
-          subs_i = subs_of(base_i);
-          if (lane == 0) s_sgbase[warp][q_issue % kSgQueue] = base_i;
-          __syncwarp();
-        }
-      }
-    }
-    if (stored == issued) break;
-    const uint32_t s = stored % S;
-    mbar_wait(smem_u32(&s_bar[warp][s]), (stored / S) & 1u);
-    const uint32_t base = s_sgbase[warp][q_store % kSgQueue];
-    const uint32_t row0 = base + sub_store * G;
-    const uint32_t rows_here = n - row0 < G ? n - row0 : G;
-    fence_proxy_async();  // generic-proxy stage writes (miss rows) -> async proxy
-    __syncwarp();
-    if (lane == 0) {
-      if (hint) bulk_s2g(out + (size_t)row0 * row_bytes, smem_u32(stage0 + (size_t)s * stage_bytes), rows_here * row_bytes, pol);
-      else bulk_s2g(out + (size_t)row0 * row_bytes, smem_u32(stage0 + (size_t)s * stage_bytes), rows_here * row_bytes);
-      bulk_commit();
-    }
-    ++stored;
-    if (++sub_store == subs_of(base)) { sub_store = 0; ++q_store; }
-  }
-  if (lane == 0) bulk_wait_read<0>();
-  if (d_stats) {
-#pragma unroll
-    for (int d = 16; d > 0; d >>= 1) {
-      hits += __shfl_down_sync(0xFFFFFFFFu, hits, d);
-      misses += __shfl_down_sync(0xFFFFFFFFu, misses, d);
-    }
-    if (lane == 0) {
-      if (hits) atomicAdd(d_stats + 0, (unsigned long long)hits);
-      if (misses) atomicAdd(d_stats + 1, (unsigned long long)misses);
-    }
-  }
-  // every warp of this CTA has drawn its last ticket: the last CTA re-arms the counter
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    const unsigned int prev = atomicAdd(tick + 1, 1u);
-    if (prev == gridDim.x - 1) {
-      tick[0] = 0u;
-      __threadfence();
-      tick[1] = 0u;
-    }
-  }
-}
-
-// ticket counters of the dynamic gather: one pair per launch in flight (round robin; a pair is re-zeroed by
-// the launch that used it, and 64 gathers are never in flight at once)
-constexpr int kTickSlots = 64;
-__device__ unsigned int g_gather_tick[kTickSlots][2];
 
 inline int vec_width(size_t row_bytes, const void *a, const void *b, const void *c = nullptr) {
   const uintptr_t bits = (uintptr_t)row_bytes | (uintptr_t)a | (uintptr_t)b | (uintptr_t)c;
@@ -661,9 +490,8 @@ namespace fgnn {
 namespace {
 // A/B switches for profiling (read once): FGNN_GATHER_IMPL = flat | group | bulk
 struct GatherTuning {
-  int impl;         // 0 flat, 1 group, 2 bulk (static partition), 3 bulk with dynamic tickets
-  int stages;       // bulk: ring depth per warp
-  int warps;        // bulk: warps per CTA
+  int impl;         // 0 flat, 1 group, 2 bulk
+  int stages;       // bulk: ring depth per warp (6, or 3 for long rows)
   uint32_t stage_cap;  // bulk: max bytes per stage
   int miss_ldg;     // bulk: host-resident rows by warp loads (1) or by the bulk engine (0)
   int l2_hint;      // bulk: evict-first L2 policy on the streamed rows
@@ -681,9 +509,9 @@ GatherTuning read_tuning() {
   if (v && !strcmp(v, "flat")) g.impl = 0;
   if (v && !strcmp(v, "group")) g.impl = 1;
   if (v && !strcmp(v, "bulk")) g.impl = 2;
-  if (v && !strcmp(v, "dyn")) g.impl = 3;
+  // round-1 sweeps (profiles/r1_d_gather_sweep*.txt, r1_q_overlap_sweep.txt) settled on 16 warps x 6 stages of
+  // <= 2 KB; the other warp/stage shapes were dropped from the binary in round 2
   g.stages = env_int("FGNN_BULK_STAGES", 6);
-  g.warps = env_int("FGNN_BULK_WARPS", 16);  // r1_q c7: 16 warps x 6 stages 205 vs 8 x 8 224 us/step in the loop (113 vs 110 alone)
   g.stage_cap = (uint32_t)env_int("FGNN_BULK_STAGE_BYTES", 2048);
   g.miss_ldg = env_int("FGNN_BULK_MISS_LDG", 0);
   g.l2_hint = env_int("FGNN_GATHER_L2HINT", 1);
@@ -697,147 +525,74 @@ const GatherTuning &tuning() {
   return t;
 }
 
-template <int S, int NW>
+constexpr int kBulkWarps = 16;
+
+template <int S>
 int launch_bulk(char *out, const uint32_t *nodes, uint32_t n_max, const uint32_t *d_n,
                 const uint32_t *table, const RowSrc &rs, uint32_t G, uint32_t stage_bytes,
                 unsigned long long *d_stats, cudaStream_t st) {
-  auto kern = gather_bulk_kernel<S, NW>;
-  const size_t smem = (size_t)NW * S * stage_bytes;
-  static size_t configured = 0;
-  if (smem > configured) {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return (int)e;
-    configured = smem;
-  }
-  int occ = tuning().ctas_per_sm ? tuning().ctas_per_sm : occupancy(kern, NW * 32, smem);
-  // at least kMinSub sub-groups per warp so the ring fills
+  auto kern = gather_bulk_kernel<S, kBulkWarps>;
+  const size_t smem = (size_t)kBulkWarps * S * stage_bytes;
+  // the opt-in is per device and cheap: set it on every launch (a process may drive several GPUs)
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return (int)e;
+  int occ = tuning().ctas_per_sm ? tuning().ctas_per_sm : occupancy(kern, kBulkWarps * 32, smem);
   const uint64_t subs = ((uint64_t)n_max + G - 1) / G;
-  const int grid = persistent_grid(subs, NW * 4, occ, false, true);
-  kern<<<grid, NW * 32, smem, st>>>(out, nodes, n_max, d_n, table, rs, G, stage_bytes,
-                                    (tuning().miss_ldg ? 1 : 0) | (tuning().l2_hint ? 2 : 0), d_stats);
+  const int grid = persistent_grid(subs, kBulkWarps * 4, occ, false, true);  // >= 4 sub-groups per warp
+  kern<<<grid, kBulkWarps * 32, smem, st>>>(out, nodes, n_max, d_n, table, rs, G, stage_bytes,
+                                            (tuning().miss_ldg ? 1 : 0) | (tuning().l2_hint ? 2 : 0), d_stats);
   return 0;
-}
-
-template <int NW>
-int launch_bulk_s(int stages, char *out, const uint32_t *nodes, uint32_t n_max, const uint32_t *d_n,
-                  const uint32_t *table, const RowSrc &rs, uint32_t G, uint32_t stage_bytes,
-                  unsigned long long *d_stats, cudaStream_t st) {
-  switch (stages) {
-    case 3: return launch_bulk<3, NW>(out, nodes, n_max, d_n, table, rs, G, stage_bytes, d_stats, st);
-    case 4: return launch_bulk<4, NW>(out, nodes, n_max, d_n, table, rs, G, stage_bytes, d_stats, st);
-    case 6: return launch_bulk<6, NW>(out, nodes, n_max, d_n, table, rs, G, stage_bytes, d_stats, st);
-    case 12: return launch_bulk<12, NW>(out, nodes, n_max, d_n, table, rs, G, stage_bytes, d_stats, st);
-    case 16: return launch_bulk<16, NW>(out, nodes, n_max, d_n, table, rs, G, stage_bytes, d_stats, st);
-    default: return launch_bulk<8, NW>(out, nodes, n_max, d_n, table, rs, G, stage_bytes, d_stats, st);
-  }
-}
-
-// ticket pair for the next dynamic-gather launch of this process (one device per process in the engine and the
-// benches; the address is re-resolved when the current device changes)
-inline int next_tick(unsigned int **out) {
-  static unsigned int *tick_base = nullptr;
-  static int tick_dev = -1;
-  static unsigned int seq = 0;
-  int dev = 0;
-  cudaGetDevice(&dev);
-  if (!tick_base || tick_dev != dev) {
-    cudaError_t e = cudaGetSymbolAddress((void **)&tick_base, g_gather_tick);
-    if (e != cudaSuccess) return (int)e;
-    tick_dev = dev;
-  }
-  *out = tick_base + 2 * (seq++ % kTickSlots);
-  return 0;
-}
-
-template <int S, int NW>
-int launch_bulk_dyn(char *out, const uint32_t *nodes, uint32_t n_max, const uint32_t *d_n,
-                    const uint32_t *table, const RowSrc &rs, uint32_t G, uint32_t stage_bytes,
-                    unsigned long long *d_stats, cudaStream_t st) {
-  auto kern = gather_bulk_dyn_kernel<S, NW>;
-  const size_t smem = (size_t)NW * S * stage_bytes;
-  static size_t configured = 0;
-  if (smem > configured) {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return (int)e;
-    configured = smem;
-  }
-  unsigned int *tick = nullptr;
-  if (int rc = next_tick(&tick)) return rc;
-  int occ = tuning().ctas_per_sm ? tuning().ctas_per_sm : occupancy(kern, NW * 32, smem);
-  const uint64_t sgs = ((uint64_t)n_max + 31) / 32;
-  const int grid = persistent_grid(sgs, NW * 2, occ, false, true);  // >= 2 super-groups per warp
-  kern<<<grid, NW * 32, smem, st>>>(out, nodes, n_max, d_n, table, rs, G, stage_bytes,
-                                    (tuning().miss_ldg ? 1 : 0) | (tuning().l2_hint ? 2 : 0), d_stats, tick);
-  return 0;
-}
-
-template <int NW>
-int launch_bulk_dyn_s(int stages, char *out, const uint32_t *nodes, uint32_t n_max, const uint32_t *d_n,
-                      const uint32_t *table, const RowSrc &rs, uint32_t G, uint32_t stage_bytes,
-                      unsigned long long *d_stats, cudaStream_t st) {
-  switch (stages) {
-    case 3: return launch_bulk_dyn<3, NW>(out, nodes, n_max, d_n, table, rs, G, stage_bytes, d_stats, st);
-    case 4: return launch_bulk_dyn<4, NW>(out, nodes, n_max, d_n, table, rs, G, stage_bytes, d_stats, st);
-    case 6: return launch_bulk_dyn<6, NW>(out, nodes, n_max, d_n, table, rs, G, stage_bytes, d_stats, st);
-    case 12: return launch_bulk_dyn<12, NW>(out, nodes, n_max, d_n, table, rs, G, stage_bytes, d_stats, st);
-    case 16: return launch_bulk_dyn<16, NW>(out, nodes, n_max, d_n, table, rs, G, stage_bytes, d_stats, st);
-    default: return launch_bulk_dyn<8, NW>(out, nodes, n_max, d_n, table, rs, G, stage_bytes, d_stats, st);
-  }
 }
 }  // namespace
 }  // namespace fgnn
 
-static int gather_cached_impl(void *out, const uint32_t *nodes, uint32_t n_max,
-                              const uint32_t *d_n, const uint32_t *table,
-                              const void *const *shards, uint32_t num_shards,
-                              const void *miss_src, uint64_t miss_mask, size_t row_bytes,
-                              unsigned long long *d_stats, fgnn_stream_t stream) {
+extern "C" int fgnn_k_gather_cached_layout(void *out, const uint32_t *nodes, uint32_t n_max,
+                                           const uint32_t *d_n, const fgnn_cache_layout *lay,
+                                           unsigned long long *d_stats, unsigned long long *d_remote,
+                                           fgnn_stream_t stream) {
+  if (!lay) return FGNN_ERR_BAD_ARG;
+  const size_t row_bytes = lay->row_bytes;
   if (n_max == 0 || row_bytes == 0) return 0;
-  if (!out || !nodes || !table || !shards || num_shards == 0 || !miss_src) return FGNN_ERR_BAD_ARG;
+  if (!out || !nodes || !lay->table || !lay->shards || lay->num_shards == 0 || !lay->miss_src) return FGNN_ERR_BAD_ARG;
+  if (lay->num_replicated > 0 && !lay->replica) return FGNN_ERR_BAD_ARG;
+  if (lay->self_shard >= lay->num_shards) return FGNN_ERR_BAD_ARG;
   cudaStream_t st = (cudaStream_t)stream;
-  // shard bases are cudaMalloc'ed (256-B aligned); only out/miss_src/row_bytes decide
-  const int w = vec_width(row_bytes, out, miss_src);
+  trace_mark(st, FGNN_TRACE_GATHER_BEGIN);
+  // shard bases are cudaMalloc'ed (256-B aligned); only out/miss_src/replica/row_bytes decide
+  const int w = vec_width(row_bytes, out, lay->miss_src, lay->replica);
   const uint32_t cpr = (uint32_t)(row_bytes / w);
   const GatherTuning &tn = tuning();
-  if (w == 16 && tn.impl != 0) {
-    RowSrc rs;
-    rs.shards = shards;
-    rs.shard0 = nullptr;  // fetched from shards[0] by the kernel
-    rs.num_shards = num_shards;
-    rs.miss_src = (const char *)miss_src;
-    rs.miss_mask = miss_mask;
-    rs.row_bytes = row_bytes;
-    if (tn.impl >= 2) {
-      // stage = the most rows (power of two, <= 32) that fit the stage cap; the ring depth
-      // shrinks for long rows so that warps * stages * stage_bytes stays within shared memory
-      uint32_t G = 32;
-      while (G > 1 && (size_t)G * row_bytes > tn.stage_cap) G >>= 1;
-      const uint32_t stage_bytes = (uint32_t)(G * row_bytes);
-      const int warps = (tn.warps == 4 || tn.warps == 16) ? tn.warps : 8;
-      int stages = tn.stages;
-      const size_t kSmemBudget = 200 * 1024;
-      while (stages > 3 && (size_t)warps * stages * stage_bytes > kSmemBudget)
-        stages = stages > 12 ? 12 : stages > 8 ? 8 : stages > 6 ? 6 : stages > 4 ? 4 : 3;
-      if ((size_t)warps * stages * stage_bytes <= kSmemBudget) {
-        int rc;
-        if (tn.impl == 3 && warps == 4)
-          rc = launch_bulk_dyn_s<4>(stages, (char *)out, nodes, n_max, d_n, table, rs, G, stage_bytes, d_stats, st);
-        else if (tn.impl == 3 && warps == 16)
-          rc = launch_bulk_dyn_s<16>(stages, (char *)out, nodes, n_max, d_n, table, rs, G, stage_bytes, d_stats, st);
-        else if (tn.impl == 3)
-          rc = launch_bulk_dyn_s<8>(stages, (char *)out, nodes, n_max, d_n, table, rs, G, stage_bytes, d_stats, st);
-        else if (warps == 4)
-          rc = launch_bulk_s<4>(stages, (char *)out, nodes, n_max, d_n, table, rs, G, stage_bytes, d_stats, st);
-        else if (warps == 16)
-          rc = launch_bulk_s<16>(stages, (char *)out, nodes, n_max, d_n, table, rs, G, stage_bytes, d_stats, st);
-        else
-          rc = launch_bulk_s<8>(stages, (char *)out, nodes, n_max, d_n, table, rs, G, stage_bytes, d_stats, st);
-        if (rc) return rc;
-        note_launch();
-        return check_last();
-      }
-      // rows too long for a shared-memory ring: warp-group kernel below
+  RowSrc rs;
+  rs.shards = lay->shards;
+  rs.shard0 = nullptr;  // fetched from shards[0] by the kernel
+  rs.num_shards = lay->num_shards;
+  rs.miss_src = (const char *)lay->miss_src;
+  rs.miss_mask = lay->miss_mask;
+  rs.row_bytes = row_bytes;
+  rs.replica = (const char *)lay->replica;
+  rs.num_replicated = lay->num_replicated;
+  rs.self_shard = lay->self_shard;
+  rs.d_remote = d_remote;
+  const uint32_t *table = lay->table;
+  int rc = 0;
+  bool done = false;
+  if (w == 16 && tn.impl >= 2) {
+    // stage = the most rows (power of two, <= 32) that fit the stage cap; long rows get the 3-stage ring so that
+    // 16 warps * stages * stage_bytes stays within shared memory, longer ones the warp-group kernel
+    uint32_t G = 32;
+    while (G > 1 && (size_t)G * row_bytes > tn.stage_cap) G >>= 1;
+    const uint32_t stage_bytes = (uint32_t)(G * row_bytes);
+    const size_t kSmemBudget = 200 * 1024;
+    int stages = tn.stages >= 6 ? 6 : 3;
+    if ((size_t)kBulkWarps * stages * stage_bytes > kSmemBudget) stages = 3;
+    if ((size_t)kBulkWarps * stages * stage_bytes <= kSmemBudget) {
+      rc = stages == 6 ? launch_bulk<6>((char *)out, nodes, n_max, d_n, table, rs, G, stage_bytes, d_stats, st)
+                       : launch_bulk<3>((char *)out, nodes, n_max, d_n, table, rs, G, stage_bytes, d_stats, st);
+      if (rc) return rc;
+      done = true;
     }
+  }
+  if (!done && w == 16 && tn.impl != 0) {
     uint32_t G = tn.group_rows ? tn.group_rows : kGroupChunks / cpr;
     if (G > 32) G = 32;
     if (G < 1 || G * cpr > kGroupChunks) G = 1;
@@ -846,24 +601,25 @@ static int gather_cached_impl(void *out, const uint32_t *nodes, uint32_t n_max,
     const uint64_t groups = ((uint64_t)n_max + G - 1) / G;
     const int grid = persistent_grid(groups, kBlock / 32, occ, false, true);
     gather_group_kernel<<<grid, kBlock, 0, st>>>((char *)out, nodes, n_max, d_n, table, rs, cpr, G, d_stats);
-    note_launch();
-    return check_last();
+    done = true;
   }
+  if (!done) {
 #define FGNN_GC(V)                                                                               \
   do {                                                                                           \
     static const int occ = occupancy(gather_cached_kernel<V>, kBlock, 0);                        \
     const int grid = copy_grid((uint64_t)n_max * cpr, occ);                                      \
-    gather_cached_kernel<V><<<grid, kBlock, 0, st>>>((char *)out, nodes, n_max, d_n, table,      \
-                                                     shards, num_shards, (const char *)miss_src, \
-                                                     miss_mask, row_bytes, cpr, d_stats);        \
+    gather_cached_kernel<V><<<grid, kBlock, 0, st>>>((char *)out, nodes, n_max, d_n, table, rs, cpr, d_stats); \
   } while (0)
-  if (w == 16) FGNN_GC(uint4);
-  else if (w == 8) FGNN_GC(uint2);
-  else if (w == 4) FGNN_GC(uint32_t);
-  else FGNN_GC(uint8_t);
+    if (w == 16) FGNN_GC(uint4);
+    else if (w == 8) FGNN_GC(uint2);
+    else if (w == 4) FGNN_GC(uint32_t);
+    else FGNN_GC(uint8_t);
 #undef FGNN_GC
+  }
   note_launch();
-  return check_last();
+  rc = check_last();
+  trace_mark(st, FGNN_TRACE_GATHER_END);
+  return rc;
 }
 
 extern "C" int fgnn_k_gather_cached(void *out, const uint32_t *nodes, uint32_t n_max,
@@ -871,9 +627,13 @@ extern "C" int fgnn_k_gather_cached(void *out, const uint32_t *nodes, uint32_t n
                                     const void *const *shards, uint32_t num_shards,
                                     const void *miss_src, uint64_t miss_mask, size_t row_bytes,
                                     unsigned long long *d_stats, fgnn_stream_t stream) {
-  trace_mark((cudaStream_t)stream, FGNN_TRACE_GATHER_BEGIN);
-  const int rc = gather_cached_impl(out, nodes, n_max, d_n, table, shards, num_shards, miss_src, miss_mask,
-                                    row_bytes, d_stats, stream);
-  trace_mark((cudaStream_t)stream, FGNN_TRACE_GATHER_END);
-  return rc;
+  fgnn_cache_layout lay;
+  memset(&lay, 0, sizeof(lay));
+  lay.table = table;
+  lay.shards = shards;
+  lay.num_shards = num_shards;
+  lay.miss_src = miss_src;
+  lay.miss_mask = miss_mask;
+  lay.row_bytes = row_bytes;
+  return fgnn_k_gather_cached_layout(out, nodes, n_max, d_n, &lay, d_stats, nullptr, stream);
 }

@@ -52,6 +52,16 @@ __device__ __forceinline__ uint32_t ld_relaxed_u32(const uint32_t *p) {
   return v;
 }
 
+// spin until the owner of bucket `bp` has received its local id; returns the whole local word
+__device__ __forceinline__ uint32_t wait_local_word(const Bucket *table, uint32_t bp) {
+  uint32_t w = ld_relaxed_u32(&table[bp].local);
+  while (w & kPending) {
+    __nanosleep(32);
+    w = ld_relaxed_u32(&table[bp].local);
+  }
+  return w;
+}
+
 // optional "insert while sampling" target handed to the sampler kernels
 struct HtInsert {
   Bucket *table;      // nullptr: do not insert
@@ -84,5 +94,12 @@ int ht_compact_pad_launch(void *table, const uint32_t *dst, uint32_t n_seed_max,
 int ht_fill_unique_first_launch(void *table, size_t capacity, const uint32_t *input, uint32_t n_max,
                                 const uint32_t *d_n, uint32_t *n2o, uint32_t *d_num_items,
                                 uint32_t *count_copy, cudaStream_t stream);
+
+// the two-launch-per-layer uniform k-hop chain for up to FGNN_MAX_SUPER mini-batches (fast_chain.cu)
+bool fast_chain_supported(const fgnn_sample_plan *pl);
+int fast_chain_launch(const fgnn_sample_plan *const *plans, const fgnn_sample_out *const *outs,
+                      const uint32_t *const *seeds, const uint32_t *n_seeds_max,
+                      const uint32_t *const *d_n_seeds, const uint64_t *batch_keys, uint32_t K,
+                      cudaStream_t stream);
 
 }  // namespace fgnn

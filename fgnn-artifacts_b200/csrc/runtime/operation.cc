@@ -70,6 +70,8 @@ void samgraph_config(const char **config_keys, const char **config_values, const
   if (c.count("seed")) RC.seed = std::stoull(c["seed"]);                    // ours, optional
   if (c.count("partition_cache")) RC.partition_cache = std::stoi(c["partition_cache"]) != 0;
   else if (RC.run_arch == kArch5) RC.partition_cache = true;                // partitioned over trainer GPUs
+  if (c.count("replicate_percentage")) RC.replicate_percentage = std::stod(c["replicate_percentage"]);
+  else if (!GetEnv("FGNN_REPLICATE_PCT").empty()) RC.replicate_percentage = std::stod(GetEnv("FGNN_REPLICATE_PCT"));
   RC.LoadFromEnv();
   RC.is_configured = true;
 }

@@ -116,6 +116,9 @@ struct RunConfig {
   // ours (optional keys / env): RNG seed, partitioned cache over trainer GPUs
   uint64_t seed = 0x46474E4E;
   bool partition_cache = false;
+  // partitioned cache, hybrid layout: every trainer keeps the hottest replicate_percentage * V ranks, only the
+  // rest of the cache is striped over the trainers (config key "replicate_percentage", env FGNN_REPLICATE_PCT)
+  double replicate_percentage = 0.25;
 
   bool UseGPUCache() const { return cache_percentage > 0 && run_arch != kArch1; }  // run_config.h:81-83
   void LoadFromEnv();

@@ -73,6 +73,7 @@ struct SharedRing {
   uint64_t slot_bytes;
   uint64_t ranking_off, slots_off;
   std::atomic<uint32_t> presample_done;
+  std::atomic<uint32_t> live_workers, left_workers;  // shutdown rendezvous of the arch5 worker processes
   // partitioned cache: one IPC handle per trainer
   unsigned char ipc_handle[16][FGNN_IPC_HANDLE_BYTES];
   uint64_t shard_rows[16];
@@ -124,8 +125,11 @@ class BlockPool : public std::enable_shared_from_this<BlockPool> {
     {
       std::lock_guard<std::mutex> lk(mu_);
       if (free_.empty()) free_.push_back(NewBlock());
-      b = free_.back();
-      free_.pop_back();
+      // FIFO: the block that has been free the longest.  A block returns to the pool when Python drops the last
+      // tensor that views it; kernels the consumer queued on ITS stream may still read it (the reference's
+      // WorkspacePool has the same hazard, common.cc:68-75), so the most recently freed block is reused last.
+      b = free_.front();
+      free_.pop_front();
     }
     std::shared_ptr<BlockPool> self = shared_from_this();
     return std::shared_ptr<TaskBlock>(b, [self](TaskBlock *x) {
@@ -163,7 +167,8 @@ class BlockPool : public std::enable_shared_from_this<BlockPool> {
   std::vector<size_t> edge_max_;
   bool with_data_;
   std::mutex mu_;
-  std::vector<TaskBlock *> all_, free_;
+  std::vector<TaskBlock *> all_;
+  std::deque<TaskBlock *> free_;
 };
 
 // One sampling slot = one mini-batch in flight: its own stream, hash table and scratch.  A single 8000-seed
@@ -176,13 +181,13 @@ struct SlowScope {
   Timer t;
   explicit SlowScope(const char *n) : name(n) {}
   ~SlowScope() {
-    static const bool on = IsEnvSet("FGNN_TRACE_HOST") && GetEnv("FGNN_TRACE_HOST") != "0";
+    static const bool on = IsEnvSet("FGNN_TRACE_HOST");
     if (on && t.Passed() > 1e-3) fprintf(stderr, "[fgnn slow] %s %.3f ms\n", name, t.Passed() * 1e3);
   }
 };
 
 static bool TraceGpu() {
-  static const bool on = IsEnvSet("FGNN_TRACE_GPU") && GetEnv("FGNN_TRACE_GPU") != "0";
+  static const bool on = IsEnvSet("FGNN_TRACE_GPU");
   return on;
 }
 
@@ -191,8 +196,10 @@ struct SampleSlot {
   cudaEvent_t done = nullptr;   // counts are on the host
   cudaEvent_t idle = nullptr;   // scratch marker used by Reshuffle
   cudaEvent_t begin = nullptr;  // FGNN_TRACE_GPU=1: device-side start of the batch
-  TensorPtr table, num_items, chain, counts_dev, counts_host, ws;
+  TensorPtr table, num_items, chain, ws;
+  uint32_t *counts_dev = nullptr, *counts_host = nullptr;  // views of the sampler's contiguous count arrays
   std::vector<TensorPtr> dst, pos;   // scratch: sampled global ids, their bucket positions
+  uint32_t ver_state = 0;            // versioned table reset (fgnn_k_ht_next_version)
 };
 
 class Sampler {
@@ -201,14 +208,22 @@ class Sampler {
   ~Sampler();
   // next mini-batch of this sampler's share of the epoch; nullptr when all epochs are done
   TaskPtr Next();
-  void Enqueue(const TaskPtr &task);              // all kernels of the batch + async count read-back, no host sync
+  // Super-batch: the next (up to) GroupSize() mini-batches, on consecutive slots of one slot group, enqueued with
+  // ONE call into the kernel layer (two launches per layer for all of them) + one async count read-back.
+  void NextGroup(std::vector<TaskPtr> *group);
+  void EnqueueGroup(const std::vector<TaskPtr> &group);
+  void Enqueue(const TaskPtr &task) { EnqueueGroup({task}); }
   void Finish(const TaskPtr &task);               // the ONE host sync of the batch + exact-size tensors
   void Sample(const TaskPtr &task) { Enqueue(task); Finish(task); }
+  size_t GroupSize() const { return group_; }
   void CountFrequency(const TaskPtr &task, uint32_t *d_freq);  // PreSC: freq[input_nodes] += 1 (after Enqueue)
   void SyncAll();
   bool Done(const TaskPtr &task) { return cudaEventQuery(slots_[task->slot].done) == cudaSuccess; }
   void SyncSlot(const TaskPtr &task) { CUDA_CALL(cudaStreamSynchronize(slots_[task->slot].stream)); }
-  void ResetShuffler() { cur_epoch_ = 0; cur_step_ = 0; shuffled_epoch_ = (uint64_t)-1; }
+  void ResetShuffler() {
+    cur_epoch_ = 0; cur_step_ = 0; shuffled_epoch_ = (uint64_t)-1;
+    next_slot_ = (next_slot_ + group_ - 1) / group_ * group_;  // slot groups stay aligned
+  }
   // PreSC draws its neighbours from its own Philox stream.  The reference pre-samples with the live cuRAND states
   // and then rewinds only the shuffler (pre_sampler.cc:101-103), so its training epochs never repeat the
   // pre-sampling draws; with a counter-based RNG keyed by (seed, batch key) they would be repeated exactly and
@@ -244,7 +259,8 @@ class Sampler {
   size_t max_nodes_, ht_cap_;
   std::vector<size_t> in_max_, edge_max_;
   std::vector<SampleSlot> slots_;
-  size_t next_slot_ = 0;
+  size_t next_slot_ = 0, group_ = 1;
+  TensorPtr counts_dev_, counts_host_;  // [slot][3L+1], contiguous: one read-back per group
   std::shared_ptr<BlockPool> pool_;
 };
 
@@ -295,12 +311,24 @@ Sampler::Sampler(const Dataset *ds, Context ctx, int worker_id, int num_worker, 
     if (rc_.sample_type == kRandomWalk)
       ws_bytes = std::max(ws_bytes, fgnn_k_sample_random_walk_workspace_bytes((uint32_t)in_max_[i], (uint32_t)fanout_[i]));
   }
-  size_t nslots = 4;  // r1_q c7: 4 slots + padded sampler 205 us/step, 3 slots 212 us (6 slots 200 us, +54 MB tables)
-  if (IsEnvSet("FGNN_SAMPLER_SLOTS")) nslots = (size_t)std::max(1, atoi(GetEnv("FGNN_SAMPLER_SLOTS").c_str()));
-  nslots = std::min<size_t>(nslots, 8);
+  // Super-batch (round 2): `group_` mini-batches are enqueued together, every layer being two launches for all of
+  // them (fgnn_k_sample_batch_multi), on ONE stream per slot group; two groups alternate so that one is sampled
+  // while the other is consumed.  FGNN_SUPER_BATCH=1 restores round 1's one-batch-per-stream slots.
+  group_ = 4;
+  if (!GetEnv("FGNN_SUPER_BATCH").empty()) group_ = (size_t)std::max(1, atoi(GetEnv("FGNN_SUPER_BATCH").c_str()));
+  group_ = std::min<size_t>(group_, FGNN_MAX_SUPER);
+  size_t nslots = group_ > 1 ? 2 * group_ : 4;
+  // numeric / "0" knobs are read by value: IsEnvSet() is only true for 1/ON/On/on (common.cc semantics)
+  if (group_ == 1 && !GetEnv("FGNN_SAMPLER_SLOTS").empty())
+    nslots = (size_t)std::min(8, std::max(1, atoi(GetEnv("FGNN_SAMPLER_SLOTS").c_str())));
   slots_.resize(nslots);
-  for (auto &sl : slots_) {
-    CUDA_CALL(cudaStreamCreateWithFlags(&sl.stream, cudaStreamNonBlocking));
+  const size_t cw = L_ * 3 + 1;
+  counts_dev_ = Tensor::Device(kI32, {nslots * cw}, dev_, stream_, "counts");
+  counts_host_ = Tensor::Pinned(kI32, {nslots * cw}, "counts_host");
+  for (size_t si = 0; si < nslots; ++si) {
+    SampleSlot &sl = slots_[si];
+    if (si % group_ == 0) CUDA_CALL(cudaStreamCreateWithFlags(&sl.stream, cudaStreamNonBlocking));
+    else sl.stream = slots_[si - si % group_].stream;  // a slot group shares one stream
     CUDA_CALL(cudaEventCreateWithFlags(&sl.done, TraceGpu() ? cudaEventDefault : cudaEventDisableTiming));
     CUDA_CALL(cudaEventCreateWithFlags(&sl.idle, cudaEventDisableTiming));
     if (TraceGpu()) CUDA_CALL(cudaEventCreate(&sl.begin));
@@ -308,8 +336,8 @@ Sampler::Sampler(const Dataset *ds, Context ctx, int worker_id, int num_worker, 
     sl.num_items = Tensor::Device(kI32, {4}, dev_, sl.stream, "num_items");
     sl.chain = Tensor::Device(kU8, {FGNN_CHAIN_WS_BYTES}, dev_, sl.stream, "chain_ws");
     CUDA_CALL(cudaMemsetAsync(sl.chain->data, 0, FGNN_CHAIN_WS_BYTES, sl.stream));
-    sl.counts_dev = Tensor::Device(kI32, {L_ * 3 + 1}, dev_, sl.stream, "counts");
-    sl.counts_host = Tensor::Pinned(kI32, {L_ * 3 + 1}, "counts_host");
+    sl.counts_dev = (uint32_t *)counts_dev_->data + si * cw;
+    sl.counts_host = (uint32_t *)counts_host_->data + si * cw;
     sl.ws = Tensor::Device(kU8, {ws_bytes}, dev_, sl.stream, "sample_ws");
     for (size_t i = 0; i < L_; ++i) {
       sl.dst.push_back(Tensor::Device(kI32, {edge_max_[i] + 1}, dev_, sl.stream, "scratch_dst"));
@@ -388,63 +416,92 @@ TaskPtr Sampler::Next() {
   return task;
 }
 
-void Sampler::Enqueue(const TaskPtr &task) {
-  SlowScope ss("Sampler::Enqueue");
-  CUDA_CALL(cudaSetDevice(dev_));
-  FCHECK(task->slot >= 0 && (size_t)task->slot < slots_.size());
-  SampleSlot &sl = slots_[task->slot];
-  cudaStream_t stream = sl.stream;
-  fgnn_stream_t st = (fgnn_stream_t)stream;
-  const uint32_t n_seed = (uint32_t)task->output_nodes->NumItems();
-  uint32_t *counts = (uint32_t *)sl.counts_dev->data;  // [L][3] = num_dst, num_edge, num_src
-  uint32_t *num_items = (uint32_t *)sl.num_items->data;
-  TaskBlock *blk = static_cast<TaskBlock *>(task->block.get());
-  IdType *n2o = blk->n2o;
-  const IdType *indptr = d_indptr(), *indices = d_indices();
+void Sampler::NextGroup(std::vector<TaskPtr> *group) {
+  group->clear();
+  next_slot_ = (next_slot_ + group_ - 1) / group_ * group_;  // a group never straddles two slot groups
+  while (group->size() < group_) {
+    TaskPtr t = Next();
+    if (!t) break;
+    group->push_back(t);
+  }
+}
 
-  if (sl.begin) CUDA_CALL(cudaEventRecord(sl.begin, stream));
-  // the whole of DoGPUSample (cuda_loops.cc:50-267) is one call into the kernel layer: reset + seeds, then per
-  // layer sample(+insert) -> compact(+remap); nothing below waits on the host
-  fgnn_sample_plan pl;
-  memset(&pl, 0, sizeof(pl));
-  pl.sample_type = (int32_t)rc_.sample_type;
-  pl.num_layers = (uint32_t)L_;
-  for (size_t i = 0; i < L_; ++i) {
-    pl.fanout[i] = (uint32_t)fanout_[i];
-    pl.in_max[i] = (uint32_t)in_max_[i];
-    pl.dst[i] = (uint32_t *)sl.dst[i]->data;
-    pl.pos[i] = (uint32_t *)sl.pos[i]->data;
-  }
-  pl.indptr = indptr;
-  pl.indices = indices;
-  pl.prob_table = prob_ ? (const float *)prob_->data : nullptr;
-  pl.alias_table = alias_ ? (const IdType *)alias_->data : nullptr;
-  pl.prob_prefix_table = prefix_ ? (const float *)prefix_->data : nullptr;
-  pl.walk_len = (uint32_t)rc_.random_walk_length;
-  pl.num_walk = (uint32_t)rc_.num_random_walk;
-  pl.restart_prob = rc_.random_walk_restart_prob;
-  pl.seed = rc_.seed ^ rng_salt_;
-  pl.table = sl.table->data;
-  pl.capacity = ht_cap_;
-  pl.num_items = num_items;
-  pl.chain_ws = sl.chain->data;
-  pl.workspace = sl.ws->data;
-  pl.workspace_bytes = sl.ws->nbytes;
-  fgnn_sample_out so;
-  memset(&so, 0, sizeof(so));
-  so.n2o = n2o;
-  so.counts = counts;
-  for (size_t i = 0; i < L_; ++i) {
-    so.row[i] = blk->row[i];
-    so.col[i] = blk->col[i];
-    so.data[i] = blk->data[i];
-  }
+void Sampler::EnqueueGroup(const std::vector<TaskPtr> &group) {
+  SlowScope ss("Sampler::EnqueueGroup");
+  if (group.empty()) return;
+  CUDA_CALL(cudaSetDevice(dev_));
+  const size_t K = group.size();
+  FCHECK_LE(K, (size_t)FGNN_MAX_SUPER);
+  const size_t first_slot = (size_t)group[0]->slot;
+  cudaStream_t stream = slots_[first_slot].stream;
+  fgnn_stream_t st = (fgnn_stream_t)stream;
+  const bool versioned = (rc_.sample_type == kKHop2) && GetEnv("FGNN_HT_VERSIONED") != "0";
   if (rc_.sample_type == kRandomWalk)
     for (size_t i = 0; i < L_; ++i) FCHECK_EQ(fanout_[i], rc_.num_neighbor);
-  FGNN_CALL(fgnn_k_sample_batch(&pl, &so, (const IdType *)task->output_nodes->data, n_seed, nullptr, task->key, st));
-  // all counts of the batch go to the host at once
-  CUDA_CALL(cudaMemcpyAsync(sl.counts_host->data, counts, L_ * 3 * 4, cudaMemcpyDeviceToHost, stream));
-  CUDA_CALL(cudaEventRecord(sl.done, stream));
+
+  // the whole of DoGPUSample (cuda_loops.cc:50-267) for every mini-batch of the group is one call into the
+  // kernel layer: per layer sample(+insert) -> compact(+remap); nothing below waits on the host
+  fgnn_sample_plan pl[FGNN_MAX_SUPER];
+  fgnn_sample_out so[FGNN_MAX_SUPER];
+  const fgnn_sample_plan *plp[FGNN_MAX_SUPER];
+  const fgnn_sample_out *sop[FGNN_MAX_SUPER];
+  const uint32_t *seeds[FGNN_MAX_SUPER];
+  uint32_t n_seed[FGNN_MAX_SUPER];
+  uint64_t keys[FGNN_MAX_SUPER];
+  memset(pl, 0, sizeof(pl));
+  memset(so, 0, sizeof(so));
+  for (size_t k = 0; k < K; ++k) {
+    const TaskPtr &task = group[k];
+    FCHECK(task->slot >= 0 && (size_t)task->slot == first_slot + k && first_slot / group_ == (first_slot + k) / group_)
+        << "a super-batch uses consecutive slots of one slot group";
+    SampleSlot &sl = slots_[task->slot];
+    TaskBlock *blk = static_cast<TaskBlock *>(task->block.get());
+    if (sl.begin) CUDA_CALL(cudaEventRecord(sl.begin, stream));
+    fgnn_sample_plan &p = pl[k];
+    p.sample_type = (int32_t)rc_.sample_type;
+    p.num_layers = (uint32_t)L_;
+    for (size_t i = 0; i < L_; ++i) {
+      p.fanout[i] = (uint32_t)fanout_[i];
+      p.in_max[i] = (uint32_t)in_max_[i];
+      p.dst[i] = (uint32_t *)sl.dst[i]->data;
+      p.pos[i] = (uint32_t *)sl.pos[i]->data;
+    }
+    p.indptr = d_indptr();
+    p.indices = d_indices();
+    p.prob_table = prob_ ? (const float *)prob_->data : nullptr;
+    p.alias_table = alias_ ? (const IdType *)alias_->data : nullptr;
+    p.prob_prefix_table = prefix_ ? (const float *)prefix_->data : nullptr;
+    p.walk_len = (uint32_t)rc_.random_walk_length;
+    p.num_walk = (uint32_t)rc_.num_random_walk;
+    p.restart_prob = rc_.random_walk_restart_prob;
+    p.seed = rc_.seed ^ rng_salt_;
+    p.table = sl.table->data;
+    p.capacity = ht_cap_;
+    p.num_items = (uint32_t *)sl.num_items->data;
+    p.chain_ws = sl.chain->data;
+    p.workspace = sl.ws->data;
+    p.workspace_bytes = sl.ws->nbytes;
+    p.version = versioned ? fgnn_k_ht_next_version(&sl.ver_state, p.table, ht_cap_, st) : 0u;
+    fgnn_sample_out &o = so[k];
+    o.n2o = blk->n2o;
+    o.counts = sl.counts_dev;  // [L][3] = num_dst, num_edge, num_src
+    for (size_t i = 0; i < L_; ++i) {
+      o.row[i] = blk->row[i];
+      o.col[i] = blk->col[i];
+      o.data[i] = blk->data[i];
+    }
+    plp[k] = &p;
+    sop[k] = &o;
+    seeds[k] = (const IdType *)task->output_nodes->data;
+    n_seed[k] = (uint32_t)task->output_nodes->NumItems();
+    keys[k] = task->key;
+  }
+  FGNN_CALL(fgnn_k_sample_batch_multi(plp, sop, seeds, n_seed, keys, (uint32_t)K, st));
+  // all counts of the group go to the host at once (the slots' count arrays are contiguous)
+  const size_t cw = L_ * 3 + 1;
+  CUDA_CALL(cudaMemcpyAsync(slots_[first_slot].counts_host, slots_[first_slot].counts_dev, K * cw * 4,
+                            cudaMemcpyDeviceToHost, stream));
+  for (size_t k = 0; k < K; ++k) CUDA_CALL(cudaEventRecord(slots_[first_slot + k].done, stream));
 }
 
 void Sampler::Finish(const TaskPtr &task) {
@@ -458,7 +515,7 @@ void Sampler::Finish(const TaskPtr &task) {
     CUDA_CALL(cudaEventElapsedTime(&ms, sl.begin, sl.done));
     Profiler::Get().LogStep(task->key, kLogL2IdCopyTime, ms * 1e-3);  // trace: device time of the sampling chain
   }
-  const uint32_t *h = (const uint32_t *)sl.counts_host->data;
+  const uint32_t *h = sl.counts_host;
 
   // exact-size views of the batch's block (TrainGraph: row = neighbour local id, col = seed local id, :210-229)
   TaskBlock *blk = static_cast<TaskBlock *>(task->block.get());
@@ -520,7 +577,10 @@ class Extractor {
   TensorPtr feat_pinned_, label_dev_, cache_table_, shard_ptrs_, stats_, stats_host_;
   unsigned long long last_stats_[2] = {0, 0};
   uint64_t enq_seq_ = 0;
-  void *shard_ = nullptr;              // this GPU's cache rows (cudaMalloc: IPC exportable)
+  void *shard_ = nullptr;              // this GPU's stripe of the cache rows (cudaMalloc: IPC exportable)
+  void *replica_ = nullptr;            // hybrid layout: the hottest rows, held by every trainer
+  size_t num_replicated_ = 0;
+  fgnn_cache_layout layout_;
   std::vector<void *> peer_shards_;
   int num_shards_ = 1, shard_id_ = 0;
 };
@@ -535,7 +595,7 @@ Extractor::Extractor(const Dataset *ds, Context ctx, const IdType *ranking_host,
     // SM) must not queue behind the many small CTAs of the latency-bound sampling kernels of other slots
     int lo = 0, hi = 0;
     CUDA_CALL(cudaDeviceGetStreamPriorityRange(&lo, &hi));
-    const bool prio = !(IsEnvSet("FGNN_EXTRACT_PRIORITY") && GetEnv("FGNN_EXTRACT_PRIORITY") == "0");
+    const bool prio = GetEnv("FGNN_EXTRACT_PRIORITY") != "0";
     CUDA_CALL(cudaStreamCreateWithPriority(&stream_, cudaStreamNonBlocking, prio ? hi : lo));
   }
   const size_t V = ds->num_node, D = ds->feat_dim;
@@ -565,8 +625,8 @@ Extractor::Extractor(const Dataset *ds, Context ctx, const IdType *ranking_host,
   label_dev_ = Tensor::Device(kI64, {V}, dev_, stream_, "label");
   CUDA_CALL(cudaMemcpyAsync(label_dev_->data, ds->label->data, V * 8, cudaMemcpyHostToDevice, stream_));
 
-  stats_ = Tensor::Device(kI64, {2}, dev_, stream_, "gather_stats");
-  CUDA_CALL(cudaMemsetAsync(stats_->data, 0, 16, stream_));
+  stats_ = Tensor::Device(kI64, {4}, dev_, stream_, "gather_stats");  // hits, misses, rows read from peer shards
+  CUDA_CALL(cudaMemsetAsync(stats_->data, 0, 32, stream_));
   stats_host_ = Tensor::Pinned(kI64, {2 * kDepth}, "gather_stats_host");
 
   // ---- cache: node -> slot table + the rows of this shard -------------------------------------
@@ -599,8 +659,21 @@ Extractor::Extractor(const Dataset *ds, Context ctx, const IdType *ranking_host,
   }
   FGNN_CALL(fgnn_k_cache_table_build((uint32_t *)cache_table_->data, V, rank, num_cached_, (fgnn_stream_t)stream_));
 
-  // rows of this shard: slots shard_id, shard_id+T, ...  (owner = slot % T, local row = slot / T)
-  const size_t local_rows = num_cached_ > (size_t)shard_id ? (num_cached_ - shard_id + num_shards - 1) / num_shards : 0;
+  // Hybrid layout (num_shards > 1): the hottest R = replicate_percentage * V ranks are kept by EVERY trainer
+  // (with a power-law hotness ranking they take most of the hits off the NVLink path); the slots behind them are
+  // striped: slot s >= R lives on trainer (s-R) % T at local row (s-R) / T.  Each trainer fills only its own
+  // replica and stripe from the host table (the reference has every trainer gather ALL cached rows,
+  // dist_cache_manager_host.cc:98-109).
+  if (num_shards > 1) {
+    num_replicated_ = std::min(num_cached_, (size_t)((double)V * std::max(0.0, rc_.replicate_percentage)));
+    if (num_replicated_) {
+      FGNN_CALL(fgnn_k_shard_alloc(&replica_, num_replicated_ * row_bytes_));
+      FGNN_CALL(fgnn_k_row_copy(replica_, nullptr, feat_src_, rank, feat_mask_, (uint32_t)num_replicated_, nullptr,
+                                row_bytes_, (fgnn_stream_t)stream_));
+    }
+  }
+  const size_t striped = num_cached_ - num_replicated_;
+  const size_t local_rows = striped > (size_t)shard_id ? (striped - shard_id + num_shards - 1) / num_shards : 0;
   FGNN_CALL(fgnn_k_shard_alloc(&shard_, std::max<size_t>(local_rows, 1) * row_bytes_));
   if (local_rows) {
     if (num_shards == 1) {
@@ -609,7 +682,7 @@ Extractor::Extractor(const Dataset *ds, Context ctx, const IdType *ranking_host,
     } else {
       // strided slice of the ranking: gather ids first
       auto ids = Tensor::Device(kI32, {local_rows}, dev_, stream_, "shard_ids");
-      CUDA_CALL(cudaMemcpy2DAsync(ids->data, 4, rank + shard_id, (size_t)num_shards * 4, 4, local_rows,
+      CUDA_CALL(cudaMemcpy2DAsync(ids->data, 4, rank + num_replicated_ + shard_id, (size_t)num_shards * 4, 4, local_rows,
                                   cudaMemcpyDeviceToDevice, stream_));
       FGNN_CALL(fgnn_k_row_copy(shard_, nullptr, feat_src_, (const IdType *)ids->data, feat_mask_, (uint32_t)local_rows,
                                 nullptr, row_bytes_, (fgnn_stream_t)stream_));
@@ -635,8 +708,19 @@ Extractor::Extractor(const Dataset *ds, Context ctx, const IdType *ranking_host,
   CUDA_CALL(cudaMemcpyAsync(shard_ptrs_->data, peer_shards_.data(), num_shards * sizeof(void *), cudaMemcpyHostToDevice,
                             stream_));
   CUDA_CALL(cudaStreamSynchronize(stream_));
-  FLOG(Info) << "GPU cache: " << num_cached_ << " / " << V << " nodes, shard " << shard_id << "/" << num_shards
-             << " holds " << local_rows << " rows (" << (local_rows * row_bytes_ >> 20) << " MiB)";
+  memset(&layout_, 0, sizeof(layout_));
+  layout_.table = (const uint32_t *)cache_table_->data;
+  layout_.shards = (const void *const *)shard_ptrs_->data;
+  layout_.num_shards = (uint32_t)num_shards;
+  layout_.self_shard = (uint32_t)shard_id;
+  layout_.replica = replica_;
+  layout_.num_replicated = (uint32_t)num_replicated_;
+  layout_.miss_src = feat_src_;
+  layout_.miss_mask = feat_mask_;
+  layout_.row_bytes = row_bytes_;
+  FLOG(Info) << "GPU cache: " << num_cached_ << " / " << V << " nodes, " << num_replicated_ << " replicated, shard "
+             << shard_id << "/" << num_shards << " holds " << local_rows << " rows ("
+             << (local_rows * row_bytes_ >> 20) << " MiB)";
 }
 
 Extractor::~Extractor() {
@@ -645,6 +729,7 @@ Extractor::~Extractor() {
   for (int t = 0; t < (int)peer_shards_.size(); ++t)
     if (t != shard_id_ && peer_shards_[t]) fgnn_k_ipc_close(peer_shards_[t]);
   if (shard_) fgnn_k_shard_free(shard_);
+  if (replica_) fgnn_k_shard_free(replica_);
   if (feat_registered_) cudaHostUnregister(const_cast<void *>(feat_src_));
   cudaGetLastError();
 }
@@ -689,10 +774,9 @@ void Extractor::Enqueue(const TaskPtr &task) {
     CUDA_CALL(cudaEventRecord(task->xbegin, stream_));
   }
   // one fused kernel instead of GetMissCacheIndex + ExtractMissData + H2D + 2 combine kernels
-  FGNN_CALL(fgnn_k_gather_cached(task->input_feat->data, (const IdType *)task->input_nodes->data, (uint32_t)n_in,
-                                 nullptr, (const uint32_t *)cache_table_->data, (const void *const *)shard_ptrs_->data,
-                                 (uint32_t)num_shards_, feat_src_, feat_mask_, row_bytes_,
-                                 (unsigned long long *)stats_->data, (fgnn_stream_t)stream_));
+  FGNN_CALL(fgnn_k_gather_cached_layout(task->input_feat->data, (const IdType *)task->input_nodes->data, (uint32_t)n_in,
+                                        nullptr, &layout_, (unsigned long long *)stats_->data,
+                                        (unsigned long long *)stats_->data + 2, (fgnn_stream_t)stream_));
   // labels: GPUExtract with D = 1, int64 (cuda_extraction.cu:74-117)
   FGNN_CALL(fgnn_k_row_copy(task->output_label->data, nullptr, label_dev_->data, (const IdType *)task->output_nodes->data,
                             ~0ull, (uint32_t)n_out, nullptr, 8, (fgnn_stream_t)stream_));
@@ -858,8 +942,10 @@ void Engine::CreateSharedState() {  // dist_engine.cc:115-153 + memory_queue.cc:
   ring_->ranking_off = hdr;
   ring_->slots_off = hdr + rank_bytes;
   ring_->presample_done = 0;
+  ring_->live_workers = 0;
+  ring_->left_workers = 0;
   // SAMGRAPH_NVLINK_QUEUE=0 restores the reference's D2H -> pinned slot -> H2D bounce (task_queue.cc:131-137,241-255)
-  ring_->devq_enabled = (IsEnvSet("SAMGRAPH_NVLINK_QUEUE") && GetEnv("SAMGRAPH_NVLINK_QUEUE") == "0") ? 0u : 1u;
+  ring_->devq_enabled = GetEnv("SAMGRAPH_NVLINK_QUEUE") == "0" ? 0u : 1u;
   ring_->devq_trainers = (uint32_t)std::min<size_t>(rc.num_train_worker, 16);
   if (rc.num_train_worker > 16) ring_->devq_enabled = 0;
   for (int t = 0; t < 16; ++t) ring_->devq_ready[t] = 0;
@@ -935,16 +1021,21 @@ void Engine::DoPreSample() {
   CUDA_CALL(cudaStreamSynchronize(s->stream()));  // freq is zeroed before any slot stream adds to it
   s->SetRngSalt(0x5052455343000000ull);  // "PRESC": not the stream of the training epochs (see SetRngSalt)
   std::deque<TaskPtr> hold;  // a batch's block may only return to the pool once its slot has drained
-  for (size_t i = 0; i < total; ++i) {
-    if (hold.size() == s->NumSlots()) {
+  for (size_t i = 0; i < total;) {
+    while (hold.size() + s->GroupSize() > s->NumSlots()) {
       s->SyncSlot(hold.front());
       hold.pop_front();
     }
-    TaskPtr task = s->Next();
-    if (!task) break;
-    s->Enqueue(task);  // no count read-back wait: PreSC only needs the unique list on the device
-    s->CountFrequency(task, (uint32_t *)freq->data);
-    hold.push_back(task);
+    std::vector<TaskPtr> grp;
+    s->NextGroup(&grp);
+    while (!grp.empty() && i + grp.size() > total) grp.pop_back();  // drawn past the pre-sampling epochs: not sampled
+    if (grp.empty()) break;
+    s->EnqueueGroup(grp);  // no count read-back wait: PreSC only needs the unique lists on the device
+    for (auto &task : grp) {
+      s->CountFrequency(task, (uint32_t *)freq->data);
+      hold.push_back(task);
+    }
+    i += grp.size();
   }
   s->SyncAll();
   hold.clear();
@@ -1039,6 +1130,7 @@ void Engine::SampleInit(int worker_id, Context ctx) {  // dist_engine.cc:231-364
   Profiler::Get().LogInit(kLogInitL3DistQueuePin, tp.Passed());
   sampler_.reset(new Sampler(dataset_.get(), ctx, worker_id, (int)rc.num_sample_worker, num_epoch_));
   num_local_step_ = sampler_->NumLocalStep();
+  ring_->live_workers.fetch_add(1);
   if (rc.UseGPUCache() && rc.cache_policy == kCacheByPreSample) {
     Timer tps;
     if (worker_id == 0) {  // dist_engine.cc:323-337: sampler 0 pre-samples over the WHOLE train set
@@ -1046,14 +1138,18 @@ void Engine::SampleInit(int worker_id, Context ctx) {  // dist_engine.cc:231-364
       std::swap(full, sampler_);
       DoPreSample();
       std::swap(full, sampler_);
-      ring_->presample_done = 1;
+      ring_->presample_done.store(1, std::memory_order_release);
     }
     pthread_barrier_wait(&ring_->sampler_barrier);
     Profiler::Get().LogInit(kLogInitL2Presample, tps.Passed());
   } else if (dataset_->ranking_nodes && worker_id == 0) {
     memcpy(ring_->ranking(), dataset_->ranking_nodes->data, dataset_->num_node * 4);
+    ring_->presample_done.store(1, std::memory_order_release);
   } else if (rc.UseGPUCache() && !dataset_->ranking_nodes) {
-    if (worker_id == 0) DoGpuRanking();
+    if (worker_id == 0) {
+      DoGpuRanking();
+      ring_->presample_done.store(1, std::memory_order_release);
+    }
     pthread_barrier_wait(&ring_->sampler_barrier);
   }
   Profiler::Get().Reset(num_epoch_, num_step_);
@@ -1071,10 +1167,22 @@ void Engine::TrainInit(int worker_id, Context ctx) {  // dist_engine.cc:366-465
   sampler_ctx_ = ctx;
   CUDA_CALL(cudaSetDevice(ctx.device_id));
   CUDA_CALL(cudaHostRegister(shared_base_, shared_bytes_, cudaHostRegisterPortable));
+  ring_->live_workers.fetch_add(1);
   EnsureHostTables(dataset_.get());
   graph_pool_.reset(new TaskPool(rc.max_copying_jobs));
   const int T = (int)rc.num_train_worker;
   const bool partition = rc.partition_cache && T > 1 && rc.UseGPUCache();
+  if (rc.UseGPUCache()) {
+    // the ranking is published by sampler 0 (PreSC, file or GPU-computed policy): the scripts order this with a
+    // barrier (notify_sampler_ready / wait_for_sampler_ready); a driver that forgets it must not build the cache
+    // from a half-written ranking
+    Timer tw;
+    while (ring_->presample_done.load(std::memory_order_acquire) == 0) {
+      FCHECK(!stop_) << "shutdown while waiting for the cache ranking";
+      if (tw.Passed() > 600) FCHECK(false) << "no sampler published the cache ranking within 600 s";
+      std::this_thread::sleep_for(std::chrono::milliseconds(1));
+    }
+  }
   Timer tc;
   extractor_.reset(new Extractor(dataset_.get(), ctx, rc.UseGPUCache() ? ring_->ranking() : nullptr, nullptr, 0,
                                  partition ? worker_id : 0, partition ? T : 1, ring_));
@@ -1089,6 +1197,10 @@ void Engine::TrainInit(int worker_id, Context ctx) {  // dist_engine.cc:366-465
     devq_own_ = worker_id;
     ring_->devq_ready[worker_id].store(1, std::memory_order_release);
   }
+  FLOG(Info) << "arch5 queue transport: "
+             << (ring_->devq_enabled ? "device ring (payload slots in trainer HBM, peer copies)"
+                                     : "host bounce (pinned shared-memory slots)")
+             << ", trainer " << worker_id << " on cuda:" << ctx.device_id;
   // steps this trainer consumes: step % T == worker_id (train_graphsage.py:298)
   num_local_step_ = num_step_ / T + ((size_t)worker_id < num_step_ % T ? 1 : 0);
   Profiler::Get().LogInit(kLogInitL1Trainer, t0.Passed());
@@ -1221,13 +1333,17 @@ static inline void CpuRelax(int &idle) {
 }
 
 void Engine::FillSamplerSlots() {
-  while (inflight_.size() < sampler_->NumSlots()) {
+  while (inflight_.size() + sampler_->GroupSize() <= sampler_->NumSlots()) {  // a whole slot group is free
     Timer te;
-    TaskPtr next = sampler_->Next();
-    if (!next) break;
-    sampler_->Enqueue(next);
-    Profiler::Get().LogStep(next->key, kLogL2ShuffleTime, te.Passed());  // host time spent enqueueing
-    inflight_.push_back(next);
+    std::vector<TaskPtr> grp;
+    sampler_->NextGroup(&grp);
+    if (grp.empty()) break;
+    sampler_->EnqueueGroup(grp);
+    const double each = te.Passed() / (double)grp.size();
+    for (auto &next : grp) {
+      Profiler::Get().LogStep(next->key, kLogL2ShuffleTime, each);  // host time spent enqueueing
+      inflight_.push_back(next);
+    }
   }
 }
 
@@ -1374,6 +1490,15 @@ void Engine::Shutdown() {
   inflight_.clear();
   x_inflight_.clear();
   if (extractor_) { cudaSetDevice(extractor_->device()); cudaStreamSynchronize(extractor_->stream()); }
+  if (dist_ && ring_ && initialized_ && role_ != kRoleBoth) {
+    // Cache shards and device-ring slots are mapped by the other worker processes (CUDA IPC): nobody unmaps or
+    // frees until every initialised worker has stopped touching them.  Bounded: a crashed peer must not hang us.
+    // Samplers only hold mappings (closing them is always safe) and just report; trainers own memory and wait.
+    ring_->left_workers.fetch_add(1);
+    Timer tw;
+    while (role_ == kRoleTrainer && ring_->left_workers.load() < ring_->live_workers.load() && tw.Passed() < 10.0)
+      std::this_thread::sleep_for(std::chrono::milliseconds(1));
+  }
   for (int t = 0; t < (int)devq_base_.size(); ++t)
     if (devq_base_[t] && t != devq_own_) { fgnn_k_ipc_close(devq_base_[t]); devq_base_[t] = nullptr; }
   // the own part of the device ring is left to process exit: a sampler may still be copying into it

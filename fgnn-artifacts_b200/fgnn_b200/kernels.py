@@ -35,12 +35,19 @@ class SamplePlan(C.Structure):
                 ("num_walk", C.c_uint32), ("restart_prob", C.c_double), ("seed", C.c_uint64),
                 ("table", C.c_void_p), ("capacity", C.c_size_t), ("num_items", C.c_void_p),
                 ("chain_ws", C.c_void_p), ("workspace", C.c_void_p), ("workspace_bytes", C.c_size_t),
-                ("dst", _P8), ("pos", _P8)]
+                ("dst", _P8), ("pos", _P8), ("version", C.c_uint32)]
 
 
 class SampleOut(C.Structure):
     """fgnn_sample_out (include/fgnn_kernels.h)"""
     _fields_ = [("n2o", C.c_void_p), ("row", _P8), ("col", _P8), ("data", _P8), ("counts", C.c_void_p)]
+
+
+class CacheLayout(C.Structure):
+    """fgnn_cache_layout (include/fgnn_kernels.h): replicated head + striped tail of the feature cache"""
+    _fields_ = [("table", C.c_void_p), ("shards", C.c_void_p), ("num_shards", C.c_uint32), ("self_shard", C.c_uint32),
+                ("replica", C.c_void_p), ("num_replicated", C.c_uint32), ("miss_src", C.c_void_p),
+                ("miss_mask", C.c_uint64), ("row_bytes", C.c_size_t)]
 
 
 class KernelError(RuntimeError):
@@ -66,10 +73,12 @@ _SIGS = {
     "fgnn_k_ht_map": [_vp, _sz, _vp, _vp, _u32, _vp, _vp, _vp],
     "fgnn_k_ht_fill_duplicates_map": [_vp, _sz, _vp, _u32, _vp, _vp, _vp, _vp, _vp, _vp, _vp],
     "fgnn_k_sample_batch": [C.POINTER(SamplePlan), C.POINTER(SampleOut), _vp, _u32, _vp, _u64, _vp],
+    "fgnn_k_sample_batch_multi": [_vp, _vp, _vp, _vp, _vp, _u32, _vp],
     "fgnn_k_cache_table_build": [_vp, _sz, _vp, _sz, _vp],
     "fgnn_k_cache_split": [_vp, _vp, _u32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp],
     "fgnn_k_row_copy": [_vp, _vp, _vp, _vp, _u64, _u32, _vp, _sz, _vp],
     "fgnn_k_gather_cached": [_vp, _vp, _u32, _vp, _vp, _vp, _u32, _vp, _u64, _sz, _vp, _vp],
+    "fgnn_k_gather_cached_layout": [_vp, _vp, _u32, _vp, C.POINTER(CacheLayout), _vp, _vp, _vp],
     "fgnn_k_freq_count": [_vp, _vp, _u32, _vp, _vp],
     "fgnn_k_presc_rank": [_vp, _sz, _vp, _vp, _sz, _vp],
     "fgnn_k_shuffle": [_vp, _sz, _u64, _u64, _vp, _vp, _sz, _vp],
@@ -107,7 +116,7 @@ _lib = None
 
 def exported_symbols():
     return list(_SIGS) + list(_SIZE_FNS) + ["fgnn_k_version", "fgnn_k_error_string", "fgnn_k_launch_count",
-                                            "fgnn_k_trace_dump"]
+                                            "fgnn_k_trace_dump", "fgnn_k_ht_next_version"]
 
 
 def load(path=None):
@@ -246,6 +255,31 @@ def sample_batch(plan, out, seeds, n_seeds_max, d_n_seeds, batch_key):
                                       batch_key & 0xFFFFFFFFFFFFFFFF, _stream()), "sample_batch")
 
 
+MAX_SUPER = 8
+
+
+def sample_batch_multi(plans, outs, seeds, n_seeds, batch_keys):
+    """DoGPUSample for up to MAX_SUPER mini-batches of one configuration in one call (fgnn_k_sample_batch_multi):
+    for the uniform k-hop sampler every layer is two launches for all of them."""
+    k = len(plans)
+    assert 0 < k <= MAX_SUPER and len(outs) == len(seeds) == len(n_seeds) == len(batch_keys) == k
+    pp = (C.c_void_p * k)(*[C.addressof(p) for p in plans])
+    oo = (C.c_void_p * k)(*[C.addressof(o) for o in outs])
+    ss = (C.c_void_p * k)(*[_ptr(s) for s in seeds])
+    nn = (C.c_uint32 * k)(*n_seeds)
+    kk = (C.c_uint64 * k)(*[b & 0xFFFFFFFFFFFFFFFF for b in batch_keys])
+    _check(load().fgnn_k_sample_batch_multi(pp, oo, ss, nn, kk, k, _stream()), "sample_batch_multi")
+
+
+def ht_next_version(state, table, capacity):
+    """Next version tag (1..126) of a hash table; `state` is a ctypes c_uint32 kept by the table's owner.  The
+    table is cleared on the current stream when the tags wrap."""
+    lib = load()
+    lib.fgnn_k_ht_next_version.argtypes = [C.POINTER(C.c_uint32), _vp, _sz, _vp]
+    lib.fgnn_k_ht_next_version.restype = C.c_uint32
+    return int(lib.fgnn_k_ht_next_version(C.byref(state), _ptr(table), capacity, _stream()))
+
+
 def ht_map(table, capacity, glob, pos, n_max, d_n, out_local):
     _check(load().fgnn_k_ht_map(_ptr(table), capacity, _ptr(glob), _ptr(pos), n_max, _ptr(d_n), _ptr(out_local),
                                 _stream()), "ht_map")
@@ -272,6 +306,12 @@ def gather_cached(out, nodes, n_max, d_n, table, shards, num_shards, miss_src, r
     _check(load().fgnn_k_gather_cached(_ptr(out), _ptr(nodes), n_max, _ptr(d_n), _ptr(table), _ptr(shards),
                                        num_shards, _ptr(miss_src), miss_mask, row_bytes, _ptr(d_stats), _stream()),
            "gather_cached")
+
+
+def gather_cached_layout(out, nodes, n_max, d_n, layout, d_stats=None, d_remote=None):
+    """The cache-aware gather over a hybrid layout (hottest slots replicated, the rest striped over the shards)."""
+    _check(load().fgnn_k_gather_cached_layout(_ptr(out), _ptr(nodes), n_max, _ptr(d_n), C.byref(layout),
+                                              _ptr(d_stats), _ptr(d_remote), _stream()), "gather_cached_layout")
 
 
 def freq_count(freq, nodes, n_max, d_n):

@@ -23,9 +23,13 @@ def stripe_rows(num_cached, num_shards, shard_id):
     return (num_cached - shard_id + num_shards - 1) // num_shards
 
 
-def slot_owner(slot, num_shards):
-    """(owner, local_row) of a cache slot; must match RowSrc::resolve in csrc/kernels/gather.cu."""
-    return slot % num_shards, slot // num_shards
+def slot_owner(slot, num_shards, num_replicated=0):
+    """(owner, local_row) of a cache slot; must match RowSrc::resolve in csrc/kernels/gather.cu.  Slots below
+    `num_replicated` are held by every GPU (owner None); the slots behind them are striped."""
+    if slot < num_replicated:
+        return None, slot
+    s = slot - num_replicated
+    return s % num_shards, s // num_shards
 
 
 def _comm_device(device):
@@ -60,13 +64,21 @@ def exchange_handles(handle, device="cpu"):
 class CacheShards:
     """This rank's stripe of the feature cache plus the peer mappings of all the others."""
 
-    def __init__(self, ranking_nodes, num_cached, feat_src, row_bytes, feat_mask, rank, world, device):
+    def __init__(self, ranking_nodes, num_cached, feat_src, row_bytes, feat_mask, rank, world, device,
+                 num_replicated=0):
         self.rank, self.world, self.row_bytes = rank, world, row_bytes
-        self.local_rows = stripe_rows(num_cached, world, rank)
+        # hybrid layout: the hottest `num_replicated` ranks on every GPU, the tail striped over the GPUs
+        self.num_replicated = R = min(int(num_replicated), num_cached)
+        self.replica_ptr, self.replica_bytes = None, 0
+        if R:
+            self.replica_bytes = R * row_bytes
+            self.replica_ptr = K.shard_alloc(self.replica_bytes)
+            K.row_copy(self.replica_ptr, None, feat_src, ranking_nodes[:R].contiguous(), R, None, row_bytes, feat_mask)
+        self.local_rows = stripe_rows(num_cached - R, world, rank)
         nbytes = max(1, self.local_rows) * row_bytes
         self.ptr = K.shard_alloc(nbytes)                       # plain cudaMalloc: exportable
         if self.local_rows:
-            idx = ranking_nodes[rank:num_cached:world].contiguous()
+            idx = ranking_nodes[R + rank:num_cached:world].contiguous()
             K.row_copy(self.ptr, None, feat_src, idx, self.local_rows, None, row_bytes, feat_mask)
         torch.cuda.synchronize()
         handles = exchange_handles(K.ipc_export(self.ptr), device)
@@ -92,3 +104,6 @@ class CacheShards:
         if self.ptr:
             K.shard_free(self.ptr)
             self.ptr = 0
+        if self.replica_ptr:
+            K.shard_free(self.replica_ptr)
+            self.replica_ptr = None

@@ -80,6 +80,7 @@ class Slot:
             out.row[i], out.col[i] = self.row[i].data_ptr(), self.col[i].data_ptr()
             out.data[i] = self.data[i].data_ptr() if self.data is not None else None
         self.plan, self.out = pl, out
+        self.ver_state = C.c_uint32(0)      # versioned table reset: fgnn_k_ht_next_version hands out the tags
 
 
 class HotPath:
@@ -107,6 +108,8 @@ class HotPath:
         self.edge_max = [self.in_max[i] * self.fanouts[i] for i in range(self.L)]
         # ht_capacity: power-of-two override for experiments; must exceed the batch's unique-node count
         self.cap = ht_capacity if ht_capacity else K.ht_capacity(self.max_nodes)
+        import os
+        self.versioned = os.environ.get("FGNN_HT_VERSIONED", "1") != "0"
         self.slots = [Slot(self) for _ in range(max(1, num_slots))]
         self._alias_slot(0)
         # cache state (set by build_cache)
@@ -133,7 +136,21 @@ class HotPath:
     def sample(self, seeds, n_seeds, batch_key, slot=0):
         """DoGPUSample: seeds (device int32/u32) -> per-layer (row, col[, data]) + input_nodes; one C call."""
         sl = self.slots[slot]
+        self._next_version(sl)
         K.sample_batch(sl.plan, sl.out, seeds, n_seeds, None, batch_key)
+
+    def _next_version(self, sl):
+        sl.plan.version = K.ht_next_version(sl.ver_state, sl.table, self.cap) if self.versioned else 0
+
+    def sample_multi(self, batches):
+        """Super-batch: `batches` = [(seeds, n_seeds, batch_key, slot), ...] (distinct slots) enqueued together on
+        the current stream with ONE call; results land in the slots exactly as `sample` would leave them."""
+        slots = [self.slots[b[3]] for b in batches]
+        assert len(set(b[3] for b in batches)) == len(batches)
+        for sl in slots:
+            self._next_version(sl)
+        K.sample_batch_multi([sl.plan for sl in slots], [sl.out for sl in slots], [b[0] for b in batches],
+                             [b[1] for b in batches], [b[2] for b in batches])
 
     # ------------------------------------------------------------------
     def presample_count(self, freq, slot=0):
@@ -141,18 +158,25 @@ class HotPath:
         K.freq_count(freq, sl.n2o, self.max_nodes, sl.num_items)
 
     def build_cache(self, ranking_nodes, cache_percentage, feat_src, row_bytes, feat_mask=0xFFFFFFFFFFFFFFFF,
-                    num_shards=1, shard_id=0, peer_ptrs=None, fill_local=True):
+                    num_shards=1, shard_id=0, peer_ptrs=None, fill_local=True, num_replicated=0, replica_ptr=None):
         """GPUCacheManager / DistCacheManager ctor (cuda_cache_manager_host.cc:60-127): node->slot table and
         the cached rows.  With num_shards > 1 only rows slot % num_shards == shard_id are stored locally;
         `peer_ptrs` then lists the base pointer of every shard (own + NVLink peer mappings, see
-        fgnn_b200/partition.py) and, with fill_local=False, the caller has already filled its own shard."""
+        fgnn_b200/partition.py) and, with fill_local=False, the caller has already filled its own shard.
+        Hybrid layout: the hottest `num_replicated` slots live in `replica_ptr` on every GPU, only the slots
+        behind them are striped (fgnn_cache_layout)."""
         V = self.num_nodes
         self.row_bytes = row_bytes
         self.num_cached = int(V * cache_percentage)
         self.cache_table = torch.empty(V, dtype=torch.int32, device=self.dev)
         K.cache_table_build(self.cache_table, V, ranking_nodes, self.num_cached)
         self.num_shards = num_shards
-        local_rows = (self.num_cached - shard_id + num_shards - 1) // num_shards if self.num_cached > shard_id else 0
+        self.shard_id = shard_id
+        self.num_replicated = min(int(num_replicated), self.num_cached)
+        self.replica_ptr = replica_ptr
+        assert self.num_replicated == 0 or (replica_ptr and not fill_local)
+        striped = self.num_cached - self.num_replicated
+        local_rows = (striped - shard_id + num_shards - 1) // num_shards if striped > shard_id else 0
         self.cache = None
         if fill_local:
             self.cache = torch.empty((max(1, local_rows), row_bytes), dtype=torch.uint8, device=self.dev)
@@ -165,6 +189,13 @@ class HotPath:
             peer_ptrs = [self.cache.data_ptr()]
         assert len(peer_ptrs) == num_shards
         self.shard_ptrs = torch.tensor(peer_ptrs, dtype=torch.int64, device=self.dev)
+        lay = K.CacheLayout()
+        lay.table, lay.shards = self.cache_table.data_ptr(), self.shard_ptrs.data_ptr()
+        lay.num_shards, lay.self_shard = num_shards, shard_id
+        lay.replica, lay.num_replicated = replica_ptr, self.num_replicated
+        lay.miss_src, lay.miss_mask, lay.row_bytes = K._ptr(feat_src), feat_mask, row_bytes
+        self.layout = lay
+        self.remote = torch.zeros(1, dtype=torch.int64, device=self.dev)
         if self.feat_out is None:
             self.feat_out = torch.empty((self.max_nodes, row_bytes), dtype=torch.uint8, device=self.dev)
         return local_rows
@@ -176,8 +207,8 @@ class HotPath:
     def gather(self, slot=0):
         """DoCacheFeatureCopy: the fused cache-aware feature gather of the slot's input_nodes."""
         sl = self.slots[slot]
-        K.gather_cached(self.feat_out, sl.n2o, self.max_nodes, sl.num_items, self.cache_table, self.shard_ptrs,
-                        self.num_shards, self.miss_src, self.row_bytes, self.stats, self.miss_mask)
+        K.gather_cached_layout(self.feat_out, sl.n2o, self.max_nodes, sl.num_items, self.layout, self.stats,
+                               self.remote)
 
     def gather_labels(self, seeds, n_seeds):
         """DoCPULabelExtractAndCopy, on the GPU (GPUExtract with D = 1, int64)."""

@@ -206,6 +206,11 @@ typedef struct fgnn_sample_plan {
   size_t workspace_bytes;
   uint32_t *dst[FGNN_MAX_LAYERS]; /* scratch: sampled global ids */
   uint32_t *pos[FGNN_MAX_LAYERS]; /* scratch: their hash buckets */
+  /* Versioned reset of the ordered hash table (cuda_hashtable.cu:714-723 keeps a `version` per bucket): 0 = the
+   * call clears the table itself (memset); 1..126 = the caller guarantees that no bucket still carries this tag
+   * (fgnn_k_ht_next_version hands out the tags and clears the table when they wrap), and the uniform k-hop
+   * chain then never touches the buckets it does not use.  Honoured by sample_type khop2; other samplers clear. */
+  uint32_t version;
 } fgnn_sample_plan;
 typedef struct fgnn_sample_out {
   uint32_t *n2o;
@@ -216,6 +221,20 @@ int fgnn_k_sample_batch(const fgnn_sample_plan *plan, const fgnn_sample_out *out
                         const uint32_t *seeds, uint32_t n_seeds_max,
                         const uint32_t *d_n_seeds, uint64_t batch_key,
                         fgnn_stream_t stream);
+/* "Super-batch": num_batches (<= FGNN_MAX_SUPER) independent mini-batches of the same configuration enqueued
+ * together on ONE stream.  plans[k] / outs[k] are mini-batch k's own table, scratch and outputs (they may
+ * differ in nothing else: topology, sampler, fanouts and capacity are taken from plans[0]).  For the uniform
+ * k-hop sampler (khop2) every layer is two launches for ALL the mini-batches (gridDim.y = mini-batch), which
+ * is what lets 8000-seed batches fill a 148-SM GPU; other samplers run batch after batch on the stream.
+ * Results are exactly those of num_batches fgnn_k_sample_batch calls. */
+#define FGNN_MAX_SUPER 8
+int fgnn_k_sample_batch_multi(const fgnn_sample_plan *const *plans, const fgnn_sample_out *const *outs,
+                              const uint32_t *const *seeds, const uint32_t *n_seeds_max,
+                              const uint64_t *batch_keys, uint32_t num_batches,
+                              fgnn_stream_t stream);
+/* Next version tag of a table (host-side counter *state, start it at 0): returns 1..126 and clears the table
+ * on `stream` whenever the tags wrap, so that plan->version = the returned tag is always safe. */
+uint32_t fgnn_k_ht_next_version(uint32_t *state, void *table, size_t capacity, fgnn_stream_t stream);
 
 /* ---- feature cache ---------------------------------------------------------- */
 /* SampleCacheTableInit / DistCacheManager ctor steps 1-2 (dist_engine.cc:193-229,
@@ -258,6 +277,26 @@ int fgnn_k_gather_cached(void *out, const uint32_t *nodes, uint32_t n_max,
                          const void *miss_src, uint64_t miss_mask,
                          size_t row_bytes, unsigned long long *d_stats,
                          fgnn_stream_t stream);
+/* The same gather over a HYBRID cache layout (BASELINE north_star: cache partitioned across the trainer GPUs and
+ * served by NVLink peer loads): the hottest `num_replicated` slots are held by every trainer (`replica`, local
+ * HBM), the remaining slots are striped over the trainers' shards: slot s >= R lives on shard (s-R) % num_shards
+ * at local row (s-R) / num_shards.  With a power-law hotness ranking a few % of replicated rows take most of the
+ * hits off the NVLink path.  num_replicated = 0 is the plain striped layout of fgnn_k_gather_cached.
+ * d_stats[0] += hits, d_stats[1] += misses; *d_remote += rows read from a peer's shard (optional). */
+typedef struct fgnn_cache_layout {
+  const uint32_t *table;      /* node -> slot, EMPTY = not cached */
+  const void *const *shards;  /* DEVICE array of num_shards shard base pointers */
+  uint32_t num_shards, self_shard;
+  const void *replica;        /* rows of slots [0, num_replicated) on this GPU, or NULL */
+  uint32_t num_replicated;
+  const void *miss_src;       /* pinned host feature table (UVA) */
+  uint64_t miss_mask;
+  size_t row_bytes;
+} fgnn_cache_layout;
+int fgnn_k_gather_cached_layout(void *out, const uint32_t *nodes, uint32_t n_max, const uint32_t *d_n,
+                                const fgnn_cache_layout *layout, unsigned long long *d_stats,
+                                unsigned long long *d_remote, fgnn_stream_t stream);
+
 
 /* ---- partitioned cache plumbing ------------------------------------------------ */
 /* The reference replicates the feature cache in every trainer process

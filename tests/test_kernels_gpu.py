@@ -335,7 +335,7 @@ def test_gather_cached_matches_reference_pipeline(K, oracle, num_shards, dim, pc
     assert stats.tolist() == [len(cs), len(ms)]
 
 
-@pytest.mark.parametrize("impl", ["bulk", "dyn", "group", "flat"])
+@pytest.mark.parametrize("impl", ["bulk", "group", "flat"])
 @pytest.mark.parametrize("row_bytes,n,n_max,pct,shards", [
     (512, 0, 64, 0.5, 1), (512, 1, 1, 0.5, 1), (512, 3, 3, 1.0, 1), (512, 33, 40, 0.0, 1),
     (512, 70001, 70001, 0.9, 1), (512, 70001, 90000, 1.0, 3), (400, 12345, 12345, 0.7, 2),
@@ -382,6 +382,58 @@ def test_gather_cached_impls_edge_cases(K, oracle, impl, row_bytes, n, n_max, pc
     assert (got[n:] == 0xA5).all(), "rows beyond the device count must not be written"
     hit = int((table_ref[nodes[:n]] != 0xFFFFFFFF).sum())
     assert stats.tolist() == [hit, n - hit]
+
+
+@pytest.mark.parametrize("impl", ["bulk", "group", "flat"])
+@pytest.mark.parametrize("row_bytes,shards,self_shard,pct,repl", [(512, 4, 1, 0.8, 0.2), (512, 2, 0, 1.0, 0.5),
+                                                                 (1024, 8, 7, 0.6, 0.05), (400, 3, 2, 0.7, 0.3),
+                                                                 (512, 1, 0, 0.5, 0.5), (512, 4, 3, 0.3, 0.6)])
+def test_gather_cached_hybrid_layout(K, oracle, impl, row_bytes, shards, self_shard, pct, repl, monkeypatch):
+    """fgnn_k_gather_cached_layout: the hottest R slots in a local replica, slots >= R striped over `shards`
+    buffers ((s-R) % T, (s-R) // T), misses from pinned host memory: bit-exact rows; the kernel's remote-row
+    counter equals the number of gathered rows whose stripe owner is not `self_shard`."""
+    from fgnn_b200 import partition as P
+    monkeypatch.setenv("FGNN_TUNING_DYNAMIC", "1")
+    monkeypatch.setenv("FGNN_GATHER_IMPL", impl)
+    rng = np.random.default_rng(row_bytes + shards)
+    V, n = 30000, 40001
+    src = rng.integers(0, 256, size=(V, row_bytes), dtype=np.uint8)
+    rank = rng.permutation(V).astype(np.uint32)
+    nc = oracle.num_cached(V, pct)
+    R = min(nc, int(V * repl))
+    table_ref = oracle.cache_table_build(rank, V, nc)
+    nodes = rng.integers(0, V, size=n).astype(np.uint32)
+    cache = src[rank[:nc]]
+    replica = torch.from_numpy(np.ascontiguousarray(cache[:R])).cuda() if R else None
+    bufs = []
+    for t in range(shards):
+        rows = cache[R + t::shards]
+        assert len(rows) == P.stripe_rows(nc - R, shards, t)
+        bufs.append(torch.from_numpy(np.ascontiguousarray(rows)).cuda() if len(rows) else
+                    torch.zeros((1, row_bytes), dtype=torch.uint8, device="cuda"))
+    ptrs = torch.tensor([b.data_ptr() for b in bufs], dtype=torch.int64, device="cuda")
+    host_src = torch.from_numpy(src).pin_memory()
+    d_table, d_nodes = dev(table_ref), dev(nodes)
+    lay = K.CacheLayout()
+    lay.table, lay.shards, lay.num_shards, lay.self_shard = d_table.data_ptr(), ptrs.data_ptr(), shards, self_shard
+    lay.replica, lay.num_replicated = (replica.data_ptr() if R else None), R
+    lay.miss_src, lay.miss_mask, lay.row_bytes = host_src.data_ptr(), 0xFFFFFFFFFFFFFFFF, row_bytes
+    out = torch.zeros((n, row_bytes), dtype=torch.uint8, device="cuda")
+    stats = torch.zeros(2, dtype=torch.int64, device="cuda")
+    remote = torch.zeros(1, dtype=torch.int64, device="cuda")
+    K.gather_cached_layout(out, d_nodes, n, None, lay, stats, remote)
+    torch.cuda.synchronize()
+    assert np.array_equal(out.cpu().numpy(), src[nodes])
+    slots = table_ref[nodes]
+    hit = slots != 0xFFFFFFFF
+    assert stats.tolist() == [int(hit.sum()), int((~hit).sum())]
+    striped = hit & (slots >= R)
+    owners = (slots[striped].astype(np.int64) - R) % shards
+    assert int(remote.item()) == (int((owners != self_shard).sum()) if shards > 1 else 0)
+    for s_ in (0, R - 1, R, R + 1, nc - 1):
+        if 0 <= s_ < nc:
+            o, r = P.slot_owner(int(s_), shards, R)
+            assert (o is None and r == s_) if s_ < R else (o == (s_ - R) % shards and r == (s_ - R) // shards)
 
 
 # ---------------------------------------------------------------------------
@@ -491,7 +543,7 @@ def test_random_walk_topk_matches_oracle(K, oracle, gs, n, W, L, Kn, p):
     ("khop2", [5, 10, 15], 2000), ("khop2", [25, 10], 777), ("khop0", [5, 10], 1500), ("khop1", [10, 5], 900),
     ("weighted_khop", [10, 5], 900), ("weighted_khop_prefix", [8, 4], 500), ("weighted_khop_hash_dedup", [6, 3], 400),
     ("random_walk", [5, 5, 5], 300), ("khop2", [3], 0), ("khop2", [4, 4], 1)])
-@pytest.mark.parametrize("fuse,grid_div", [(2, 1), (6, 1), (0, 1), (6, 16), (2, 16)])
+@pytest.mark.parametrize("fuse,grid_div", [(14, 1), (2, 1), (6, 1), (0, 1), (6, 16), (2, 16)])
 def test_sample_batch_call_matches_oracle_driver(K, oracle, gs, gm, sample_type, fanouts, n_seed, fuse, grid_div,
                                                  monkeypatch):
     """fgnn_k_sample_batch (the one C call the engine makes per mini-batch: fused sample+insert and
@@ -499,12 +551,13 @@ def test_sample_batch_call_matches_oracle_driver(K, oracle, gs, gm, sample_type,
     (cuda_loops.cc:50-267), for every SampleType; two slots used alternately on two streams."""
     from fgnn_b200.pipeline import HotPath
     from oracle.oracle import sample_batch_oracle
-    if (fuse, grid_div) != (2, 1) and sample_type != "khop2":
+    if (fuse, grid_div) != (14, 1) and sample_type != "khop2":
         pytest.skip("FGNN_BATCH_FUSE only changes the uniform k-hop kernel sequence")
     # FGNN_GRID_DIV = 16 shrinks every persistent grid: chunks of the chained scans span many tiles
     monkeypatch.setenv("FGNN_TUNING_DYNAMIC", "1")
     monkeypatch.setenv("FGNN_GRID_DIV", str(grid_div))
-    # bit 1: remap folded into the compaction pass; bit 2: padded sampler + one dual-count chained scan
+    # bit 1: remap folded into the compaction pass; bit 2: padded sampler + one dual-count chained scan;
+    # bit 3: the two-launch-per-layer chain of fast_chain.cu (default)
     monkeypatch.setenv("FGNN_BATCH_FUSE", str(fuse))
     g = gm if sample_type in ("khop2", "khop0") else gs
     graph = dict(indptr=g.indptr_np, indices=g.indices_np)
@@ -547,6 +600,87 @@ def test_sample_batch_call_matches_oracle_driver(K, oracle, gs, gm, sample_type,
                     if sample_type == "random_walk":
                         assert np.array_equal(host(sl.data[i], m), lay["data"])
                 assert int(sl.chain.abs().sum().item()) == 0
+
+
+def check_slot(oracle, graph, hp, slot, seeds, fanouts, key):
+    from oracle.oracle import sample_batch_oracle
+    exp = sample_batch_oracle(oracle, graph, seeds, fanouts, "khop2", SEED, key)
+    sl = hp.slots[slot]
+    cnt = sl.counts.cpu().numpy().astype(np.int64)
+    n_in = int(sl.num_items.item())
+    assert np.array_equal(host(sl.n2o, n_in), exp["input_nodes"])
+    for i in range(len(fanouts)):
+        lay = exp["layers"][i]
+        assert cnt[i].tolist() == [lay["num_dst"], lay["num_edge"], lay["num_src"]]
+        m = lay["num_edge"]
+        assert np.array_equal(host(sl.row[i], m), lay["row"])
+        assert np.array_equal(host(sl.col[i], m), lay["col"])
+    assert int(sl.chain.abs().sum().item()) == 0
+
+
+@pytest.mark.parametrize("graph_kind", ["medium", "dense", "hub"])
+@pytest.mark.parametrize("fanouts,n_seed,k_super", [([25, 10], 777, 4), ([5, 10, 15], 1500, 3), ([3], 0, 2),
+                                                    ([4, 4], 1, 1), ([25, 10], 3000, 8), ([40, 33], 300, 2)])
+@pytest.mark.parametrize("versioned", [1, 0])
+def test_sample_batch_multi_matches_oracle(K, oracle, gm, graph_kind, fanouts, n_seed, k_super, versioned, monkeypatch):
+    """fgnn_k_sample_batch_multi: k_super mini-batches (own table / scratch / outputs each) in ONE call, every
+    layer two launches for all of them; versioned table reset (no memset between batches) and the cleared-table
+    mode; batches of different sizes in one call; slots reused across calls.  Bit-exact vs the oracle driver.
+    dense = most rows longer than the fanout (several Fisher-Yates rounds per tile); hub = a few 20k-neighbour
+    rows among isolated and short ones."""
+    from fgnn_b200.pipeline import HotPath
+    monkeypatch.setenv("FGNN_HT_VERSIONED", str(versioned))
+    monkeypatch.delenv("FGNN_BATCH_FUSE", raising=False)
+    if graph_kind == "medium":
+        g = gm
+    elif graph_kind == "dense":
+        from conftest import small_graph
+        g = G(*small_graph(4000, 400000, seed=21, zero_deg_frac=0.01))
+    else:
+        rng = np.random.default_rng(5)
+        V = 30000
+        deg = rng.integers(0, 6, size=V)
+        deg[rng.permutation(V)[:12]] = 20000
+        indptr = np.concatenate([[0], np.cumsum(deg)]).astype(np.uint32)
+        indices = rng.integers(0, V, size=int(indptr[-1])).astype(np.uint32)
+        g = G(indptr, indices)
+    graph = dict(indptr=g.indptr_np, indices=g.indices_np)
+    batch = max(n_seed, 8)
+    hp = HotPath(g.indptr, g.indices, len(g.indptr_np) - 1, fanouts, batch, "khop2", seed=SEED, num_slots=k_super)
+    for rep in range(3):                      # slots reused: versions advance, workspaces must come back clean
+        batches, keep = [], []
+        for k in range(k_super):
+            n_k = n_seed if k % 2 == 0 else n_seed // 2          # ragged super-batch
+            seeds = pick_seeds(g.indptr_np, n_k, 1000 + 10 * rep + k)
+            if graph_kind == "hub" and n_k >= 12:
+                hubs = np.nonzero(np.diff(g.indptr_np.astype(np.int64)) == 20000)[0].astype(np.uint32)
+                seeds = np.concatenate([hubs, np.setdiff1d(seeds, hubs)])[:n_k].astype(np.uint32)
+            d_seeds = dev(seeds) if n_k else torch.zeros(1, dtype=torch.int32, device="cuda")
+            batches.append((d_seeds, n_k, 500 + 10 * rep + k, k))
+            keep.append(seeds)
+        hp.sample_multi(batches)
+        torch.cuda.synchronize()
+        for k in range(k_super):
+            check_slot(oracle, graph, hp, k, keep[k], fanouts, 500 + 10 * rep + k)
+
+
+def test_versioned_table_wraps(K, oracle, gs):
+    """130 consecutive mini-batches on one slot: the 7-bit version tag wraps once (the table is cleared by
+    fgnn_k_ht_next_version), every batch bit-exact; stale buckets of earlier batches must read as free."""
+    from fgnn_b200.pipeline import HotPath
+    graph = dict(indptr=gs.indptr_np, indices=gs.indices_np)
+    fanouts = [6, 4]
+    hp = HotPath(gs.indptr, gs.indices, len(gs.indptr_np) - 1, fanouts, 64, "khop2", seed=SEED, num_slots=1)
+    assert hp.versioned
+    seen = set()
+    for rep in range(130):
+        seeds = pick_seeds(gs.indptr_np, 64, 3000 + rep)
+        hp.sample(dev(seeds), 64, 9000 + rep)
+        seen.add(int(hp.slots[0].plan.version))
+        if rep % 13 == 0 or rep > 124:
+            torch.cuda.synchronize()
+            check_slot(oracle, graph, hp, 0, seeds, fanouts, 9000 + rep)
+    assert min(seen) == 1 and max(seen) == 126
 
 
 # ---------------------------------------------------------------------------

@@ -43,7 +43,7 @@ def dataset(tmp_path_factory, oracle):
     return ds
 
 
-def run_driver(tmp_path, scenario):
+def run_driver(tmp_path, scenario, want_log=False):
     sc_path = os.path.join(str(tmp_path), "scenario.json")
     out = os.path.join(str(tmp_path), "out.npz")
     json.dump(scenario, open(sc_path, "w"))
@@ -52,7 +52,7 @@ def run_driver(tmp_path, scenario):
     r = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "runtime_driver.py"), sc_path, out],
                        capture_output=True, text=True, timeout=300, env=env)
     assert r.returncode == 0, "driver failed:\n%s\n%s" % (r.stdout[-3000:], r.stderr[-3000:])
-    return out
+    return (out, r.stdout + r.stderr) if want_log else out
 
 
 def check_batches(oracle, ds, cfg, data, num_step, keys=None):
@@ -155,17 +155,19 @@ def test_arch1_all_features_resident(tmp_path, oracle, dataset):
     assert all(float(data["miss/%d" % int(k)]) == 0.0 for k in data["keys"])
 
 
-@pytest.mark.parametrize("S,T,nvlink_queue", [(1, 1, 1), (2, 2, 1), (1, 2, 0)])
-def test_arch5_forked_sampler_and_trainer_processes(tmp_path, oracle, dataset, S, T, nvlink_queue):
-    """Factored mode on one GPU (the scripts' --single-gpu placement): sampler and trainer processes forked
-    after data_init, cache partitioned over the T trainers (CUDA IPC peer mappings).  Tasks travel through the
-    device queue (payload slots in trainer HBM written by the samplers through IPC mappings) or,
-    with SAMGRAPH_NVLINK_QUEUE=0, through the reference's pinned shared-memory bounce."""
-    cfg = base_config(dataset["path"], arch="arch5", cache=0.4)
-    cfg.update(num_sample_worker=S, num_train_worker=T)
-    sc = {"mode": "arch5", "config": cfg, "sample_devices": ["cuda:0"] * S, "train_devices": ["cuda:0"] * T,
-          "env": {"SAMGRAPH_NVLINK_QUEUE": str(nvlink_queue)}}
-    out = run_driver(tmp_path, sc)
+def arch5_scenario(tmp_path, oracle, dataset, S, T, nvlink_queue, sample_devices, train_devices, replicate_pct,
+                   sample_type="khop2", partition=True):
+    cfg = base_config(dataset["path"], arch="arch5", cache=0.4, sample_type=sample_type)
+    cfg.update(num_sample_worker=S, num_train_worker=T, partition_cache=int(partition),
+               replicate_percentage=replicate_pct)
+    sc = {"mode": "arch5", "config": cfg, "sample_devices": sample_devices, "train_devices": train_devices,
+          "env": {"SAMGRAPH_NVLINK_QUEUE": str(nvlink_queue), "SAMGRAPH_LOG_LEVEL": "info"}}
+    out, log = run_driver(tmp_path, sc, want_log=True)
+    # the transport that actually ran (SAMGRAPH_NVLINK_QUEUE=0 was unreachable)
+    want = "device ring" if nvlink_queue else "host bounce"
+    assert log.count("arch5 queue transport: " + want) == T, log[-3000:]
+    for t, d in enumerate(train_devices):
+        assert "trainer %d on %s" % (t, d) in log
     meta = np.load(out)
     assert int(meta["bad"]) == 0
     num_step = int(meta["num_step"])
@@ -175,3 +177,30 @@ def test_arch5_forked_sampler_and_trainer_processes(tmp_path, oracle, dataset, S
         check_batches(oracle, dataset, cfg, data, num_step)
         seen += [int(k) for k in data["keys"]]
     assert sorted(seen) == list(range(num_step * cfg["num_epoch"]))
+
+
+@pytest.mark.parametrize("S,T,nvlink_queue,replicate_pct", [(1, 1, 1, 0.25), (2, 2, 1, 0.25), (1, 2, 0, 0.0),
+                                                            (2, 2, 1, 0.0)])
+def test_arch5_forked_sampler_and_trainer_processes(tmp_path, oracle, dataset, S, T, nvlink_queue, replicate_pct):
+    """Factored mode on one GPU (the scripts' --single-gpu placement): sampler and trainer processes forked
+    after data_init, cache partitioned over the T trainers (hybrid: hottest ranks replicated, tail striped over
+    CUDA IPC peer mappings; replicate_pct = 0: all striped).  Tasks travel through the device queue (payload slots
+    in trainer HBM written by the samplers through IPC mappings) or, with SAMGRAPH_NVLINK_QUEUE=0,
+    through the reference's pinned shared-memory bounce; the test asserts which transport ran."""
+    arch5_scenario(tmp_path, oracle, dataset, S, T, nvlink_queue, ["cuda:0"] * S, ["cuda:0"] * T, replicate_pct)
+
+
+@pytest.mark.parametrize("S,T,nvlink_queue,partition,replicate_pct,sample_type", [
+    (1, 1, 1, True, 0.25, "khop2"), (1, 1, 0, True, 0.25, "khop2"),
+    (2, 2, 1, True, 0.1, "khop2"), (2, 2, 0, True, 0.0, "khop2"), (2, 2, 1, False, 0.0, "khop2"),
+    (1, 3, 1, True, 0.1, "weighted_khop"), (2, 6, 1, True, 0.1, "khop2"), (2, 2, 1, True, 0.1, "random_walk")])
+def test_arch5_samplers_and_trainers_on_different_gpus(tmp_path, oracle, dataset, S, T, nvlink_queue, partition,
+                                                       replicate_pct, sample_type):
+    """The factored split of dist_engine.cc:231-465 across REAL GPUs (common_config.py:182-185 placement:
+    samplers on cuda:0..S-1, trainers on cuda:S..S+T-1): task payloads cross NVLink into the trainers' device
+    ring (or bounce through pinned host memory), the cache stripes are read by NVLink peer loads.  Every batch
+    every trainer receives is bit-exact against the oracle.  Needs S+T GPUs (run with gpurun --gpus N)."""
+    if torch.cuda.device_count() < S + T:
+        pytest.skip("needs %d GPUs, this box has %d" % (S + T, torch.cuda.device_count()))
+    arch5_scenario(tmp_path, oracle, dataset, S, T, nvlink_queue, ["cuda:%d" % i for i in range(S)],
+                   ["cuda:%d" % (S + i) for i in range(T)], replicate_pct, sample_type, partition)
