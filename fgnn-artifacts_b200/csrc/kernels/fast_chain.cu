@@ -2,8 +2,8 @@
 // for up to FGNN_MAX_SUPER mini-batches at once ("super-batch": blockIdx.y = mini-batch, every mini-batch has
 // its own hash table, unique list, scratch and scan workspace side by side).
 //
-//   fc_sample_insert_kernel   sample_khop2 + count/compact bookkeeping + FillWithDuplicates' insert half
-//                             (cuda_sampling_khop2.cu:42-90, cuda_hashtable.cu:49-61,131-174); the first sampled
+//   fc_sample_kernel          sample_khop2 (cuda_sampling_khop2.cu:42-90) into a padded [seed][fanout] block
+//   fc_insert_kernel          FillWithDuplicates' insert half (cuda_hashtable.cu:49-61,131-174); the first sampled
 //                             layer also does FillWithUnique of the seeds (cuda_hashtable.cu:1017-1037)
 //   fc_compact_kernel         count_edge + DeviceScan + compact_edge + the numbering half of FillWithDuplicates
 //                             + GPUMapEdges (cuda_sampling_khop2.cu:121-175, cuda_hashtable.cu:387-438,725-807,
@@ -14,9 +14,11 @@
 //     has more than `fanout` neighbours.  Here the seeds that need a Fisher-Yates are compacted into dense lanes
 //     first, and each keeps its virtual swaps in a small open-addressed map in shared memory ([slot][thread]
 //     layout: the bank depends on the thread only, so random slots never conflict): ~30x fewer instructions.
-//   * the neighbour gather is edge-parallel over the padded [seed][fanout] tile (coalesced, 4 loads in flight per
-//     thread) and every gathered id goes straight into the batch's OrderedHashTable, so the padded id array is
-//     never written: only the bucket position of every pick is (EMPTY = hole).
+//   * the neighbour gather is edge-parallel over the padded [seed][fanout] tile (coalesced, 8 loads in flight per
+//     thread).  Inserting the picks from inside the sampler was tried twice (round 1 r1_n, round 2 r2_b/r2_c:
+//     268-350 us per 4 mini-batches): the sampler's CTAs are phase-structured and shared-memory-limited, too few
+//     threads are in the probe at any time to hide the table's latency.  The insert is its own launch again:
+//     256-thread CTAs at full occupancy, four independent probes per thread.
 //   * compaction: one CTA owns 2048 consecutive padded slots held in registers, counts with warp ballots (two
 //     block barriers instead of 24), and the cross-CTA prefix is a block-wide DIRECT sum of the lower tickets'
 //     aggregates (one L2 round trip) instead of a warp look-back (~10 dependent round trips for 700 tickets).
@@ -44,6 +46,7 @@ struct FcBatch {
   Bucket *table;
   uint32_t *num_items;       // device: unique ids so far
   uint32_t *counts;          // device [L][3] = num_dst, num_edge, num_src
+  uint32_t *dst;             // this layer's scratch: sampled global id of every padded slot (EMPTY = hole)
   uint32_t *pos;             // this layer's scratch: bucket of every padded slot
   uint32_t *row, *col;       // this layer's outputs
   ChainWs *ws;
@@ -101,7 +104,7 @@ __device__ __forceinline__ uint32_t fc_put(Bucket *table, uint32_t mask, uint32_
 // ---------------------------------------------------------------------------------------------------------
 template <int NT>
 __global__ void __launch_bounds__(NT)
-fc_sample_insert_kernel(const __grid_constant__ FcArgs a) {
+fc_sample_kernel(const __grid_constant__ FcArgs a) {
   extern __shared__ __align__(16) uint32_t dyn[];
   const FcBatch &B = a.b[blockIdx.y];
   const uint32_t f = a.fanout, fs = f | 1u;
@@ -136,11 +139,7 @@ fc_sample_insert_kernel(const __grid_constant__ FcArgs a) {
       const uint32_t v = __ldg(input + i);
       off = __ldg(a.indptr + v);
       deg = __ldg(a.indptr + v + 1) - off;
-      if (a.first) {
-        B.n2o[i] = v;
-        const uint32_t hp = hash_id(v, a.mask);
-        fc_put(B.table, a.mask, a.vmask, B.vtag, v, B.vtag | i, hp, ld_bucket_cg(B.table + hp));
-      }
+      if (a.first) B.n2o[i] = v;  // the seeds open the unique list (local id = position)
     }
     s_off[tid] = off;
     s_deg[tid] = deg;
@@ -194,19 +193,16 @@ fc_sample_insert_kernel(const __grid_constant__ FcArgs a) {
       __syncthreads();
     }
 
-    // ---- phase C: edge-parallel gather of the padded tile + insertion of every pick ----------------------
+    // ---- phase C: edge-parallel gather of the padded tile, coalesced write (EMPTY = hole) -----------------
     const uint32_t rows = n - t0 < (uint32_t)NT ? n - t0 : (uint32_t)NT;
     const uint32_t tile_items = rows * f;
-    const uint32_t base = t0 * f;  // < 2^31 (checked by the launcher)
-    uint32_t *pos_out = B.pos + base;
-    for (uint32_t e0 = tid; e0 < tile_items; e0 += NT * 4) {
-      uint32_t nbr[4], hp[4];
-      uint2 hb[4];
-      bool valid[4];
+    uint32_t *dst_out = B.dst + (size_t)t0 * f;
+    constexpr int kIlp = 8;
+    for (uint32_t e0 = tid; e0 < tile_items; e0 += NT * kIlp) {
+      uint32_t nbr[kIlp];
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
+      for (int u = 0; u < kIlp; ++u) {
         const uint32_t e = e0 + u * NT;
-        valid[u] = false;
         nbr[u] = kEmpty;
         if (e < tile_items) {
           const uint32_t s = e / f, j = e - s * f;
@@ -214,27 +210,60 @@ fc_sample_insert_kernel(const __grid_constant__ FcArgs a) {
           if (j < (d < f ? d : f)) {
             const uint32_t p = d > f ? s_choice[s * fs + j] : j;
             nbr[u] = __ldg(a.indices + (size_t)s_off[s] + p);
-            valid[u] = true;
           }
         }
       }
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        hp[u] = hash_id(nbr[u], a.mask);
-        if (valid[u]) hb[u] = ld_bucket_cg(B.table + hp[u]);
-      }
-#pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        const uint32_t e = e0 + u * NT;
-        if (e < tile_items) {
-          uint32_t bp = kEmpty;
-          if (valid[u])
-            bp = fc_put(B.table, a.mask, a.vmask, B.vtag, nbr[u], B.vtag | kPending | (base + e), hp[u], hb[u]);
-          pos_out[e] = bp;
-        }
-      }
+      for (int u = 0; u < kIlp; ++u)
+        if (e0 + u * NT < tile_items) dst_out[e0 + u * NT] = nbr[u];
     }
     __syncthreads();
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// insert: seeds (first layer) as assigned ids, every pick as a candidate owner of its id
+// ---------------------------------------------------------------------------------------------------------
+constexpr int kFcInsIlp = 4;
+
+__global__ void __launch_bounds__(kBlock)
+fc_insert_kernel(const __grid_constant__ FcArgs a) {
+  const FcBatch &B = a.b[blockIdx.y];
+  const uint32_t n_in = a.first ? load_count(B.n_seed_max, B.d_n_seeds) : load_count(a.n_max, B.counts + 3 * a.layer);
+  const uint32_t n_pad = n_in * a.fanout;
+  const uint32_t n_seed = a.first ? n_in : 0u;   // seed items come first in the item space
+  const uint32_t total = n_seed + n_pad;
+  const uint32_t stride = gridDim.x * kBlock;
+  for (uint32_t i0 = blockIdx.x * kBlock + threadIdx.x; i0 < total; i0 += stride * kFcInsIlp) {
+    uint32_t id[kFcInsIlp], hp[kFcInsIlp], mine[kFcInsIlp];
+    uint2 hb[kFcInsIlp];
+#pragma unroll
+    for (int u = 0; u < kFcInsIlp; ++u) {
+      const uint32_t i = i0 + u * stride;
+      id[u] = kEmpty;
+      mine[u] = 0;
+      if (i < n_seed) {
+        id[u] = __ldg(B.seeds + i);
+        mine[u] = B.vtag | i;
+      } else if (i < total) {
+        id[u] = __ldcs(B.dst + (i - n_seed));
+        mine[u] = B.vtag | kPending | (i - n_seed);
+      }
+      hp[u] = hash_id(id[u], a.mask);
+    }
+#pragma unroll
+    for (int u = 0; u < kFcInsIlp; ++u) {
+      hb[u] = make_uint2(0u, 0u);
+      if (id[u] != kEmpty) hb[u] = ld_bucket_cg(B.table + hp[u]);
+    }
+#pragma unroll
+    for (int u = 0; u < kFcInsIlp; ++u) {
+      const uint32_t i = i0 + u * stride;
+      if (i >= total) continue;
+      uint32_t bp = kEmpty;
+      if (id[u] != kEmpty) bp = fc_put(B.table, a.mask, a.vmask, B.vtag, id[u], mine[u], hp[u], hb[u]);
+      if (i >= n_seed) B.pos[i - n_seed] = bp;
+    }
   }
 }
 
@@ -384,10 +413,10 @@ fc_compact_kernel(const __grid_constant__ FcArgs a) {
 }
 
 template <int NT>
-int launch_sample_insert(const FcArgs &a, uint32_t K, cudaStream_t st) {
+int launch_sample(const FcArgs &a, uint32_t K, cudaStream_t st) {
   const uint32_t f = a.fanout, fs = f | 1u;
   const size_t smem = ((size_t)3 * NT + ((NT * fs + 3u) & ~3u) + 2 * (size_t)a.hslots * a.nfy) * sizeof(uint32_t);
-  auto kern = fc_sample_insert_kernel<NT>;
+  auto kern = fc_sample_kernel<NT>;
   if (smem > 48 * 1024) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
@@ -411,7 +440,7 @@ bool fast_chain_supported(const fgnn_sample_plan *pl) {
     if (pl->fanout[i] == 0 || pl->fanout[i] > 128) return false;
     const uint64_t slots = (uint64_t)pl->in_max[i] * pl->fanout[i];
     if (slots > (uint64_t)kMaxChainCtas * kFcChunk) return false;  // one aggregate slot per 2048-slot chunk
-    if (!pl->pos[i]) return false;
+    if (!pl->pos[i] || !pl->dst[i]) return false;
   }
   return pl->capacity <= 0x80000000ull;
 }
@@ -459,6 +488,7 @@ int fast_chain_launch(const fgnn_sample_plan *const *plans, const fgnn_sample_ou
       b.table = (Bucket *)plans[k]->table;
       b.num_items = plans[k]->num_items;
       b.counts = outs[k]->counts;
+      b.dst = plans[k]->dst[i];
       b.pos = plans[k]->pos[i];
       b.row = outs[k]->row[i];
       b.col = outs[k]->col[i];
@@ -485,9 +515,23 @@ int fast_chain_launch(const fgnn_sample_plan *const *plans, const fgnn_sample_ou
     uint32_t nfy = NT;
     while (nfy > 32 && (size_t)2 * H * nfy * 4 > 16 * 1024) nfy >>= 1;
     a.nfy = nfy;
-    int rc = small ? launch_sample_insert<64>(a, K, st) : launch_sample_insert<128>(a, K, st);
+    int rc = small ? launch_sample<64>(a, K, st) : launch_sample<128>(a, K, st);
     if (rc) return rc;
     trace_mark(st, FGNN_TRACE_LAYER(i) + FGNN_TRACE_SAMPLE);
+    {
+      static const int occ_ins = occupancy(fc_insert_kernel, kBlock, 0);
+      const uint64_t items = (uint64_t)a.n_max * (a.fanout + (a.first ? 1u : 0u));
+      uint64_t gi = (items + (uint64_t)kBlock * kFcInsIlp - 1) / ((uint64_t)kBlock * kFcInsIlp);
+      uint64_t cap_i = (uint64_t)sm_count() * occ_ins / K;
+      if (cap_i < 1) cap_i = 1;
+      if (gi > cap_i) gi = cap_i;
+      if (gi < 1) gi = 1;
+      fc_insert_kernel<<<dim3((unsigned)gi, K), kBlock, 0, st>>>(a);
+      note_launch();
+      rc = check_last();
+      if (rc) return rc;
+      trace_mark(st, FGNN_TRACE_LAYER(i) + FGNN_TRACE_INSERT);
+    }
     if (a.first) a.n_max = p0->in_max[i];  // the compaction bounds by the plan (counts clamp it)
     const uint64_t slots = (uint64_t)a.n_max * a.fanout;
     uint64_t P = (slots + kFcChunk - 1) / kFcChunk;

@@ -1269,11 +1269,51 @@ void Engine::SendTask(const TaskPtr &t) {
     put(t->graphs[i].col);
     put(t->graphs[i].data);
   }
-  CUDA_CALL(cudaStreamSynchronize(st));
-  RingEndWrite(&ring_->ctl, &h->ready, idx);
-  (void)sent_bytes;
+  // The slot is published as soon as the copies' event has fired.  The sampler waits for it here (send_stream_
+  // carries nothing but these copies, the slots' sampling streams keep running): a batch must never stay
+  // unpublished behind the last sample_once of an epoch share, the scripts wait on a barrier after it.
+  cudaEvent_t ev = XferEvent();
+  CUDA_CALL(cudaEventRecord(ev, st));
+  pending_sends_.push_back(PendingXfer{idx, ev, t});
+  PollSends(true);
+  Profiler::Get().LogStep(t->key, kLogL1GraphBytes, sent_bytes);
   Profiler::Get().LogStep(t->key, kLogL1SendTime, ts.Passed());
   Profiler::Get().LogEpochAdd(t->key, kLogEpochSampleSendTime, ts.Passed());
+}
+
+cudaEvent_t Engine::XferEvent() {
+  if (!xfer_events_.empty()) {
+    cudaEvent_t e = xfer_events_.back();
+    xfer_events_.pop_back();
+    return e;
+  }
+  cudaEvent_t e;
+  CUDA_CALL(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+  return e;
+}
+
+void Engine::PollSends(bool drain) {
+  while (!pending_sends_.empty()) {
+    PendingXfer &x = pending_sends_.front();
+    if (drain) CUDA_CALL(cudaEventSynchronize(x.ev));
+    else if (cudaEventQuery(x.ev) != cudaSuccess) { cudaGetLastError(); break; }
+    SlotHeader *h = reinterpret_cast<SlotHeader *>(ring_->slot(x.idx));
+    RingEndWrite(&ring_->ctl, &h->ready, x.idx);
+    xfer_events_.push_back(x.ev);
+    pending_sends_.pop_front();
+  }
+}
+
+void Engine::PollRecvs(bool drain) {
+  while (!pending_recvs_.empty()) {
+    PendingXfer &x = pending_recvs_.front();
+    if (drain) CUDA_CALL(cudaEventSynchronize(x.ev));
+    else if (cudaEventQuery(x.ev) != cudaSuccess) { cudaGetLastError(); break; }
+    SlotHeader *h = reinterpret_cast<SlotHeader *>(ring_->slot(x.idx));
+    RingEndRead(&ring_->ctl, &h->ready, x.idx);
+    xfer_events_.push_back(x.ev);
+    pending_recvs_.pop_front();
+  }
 }
 
 TaskPtr Engine::RecvTask(bool block) {
@@ -1309,8 +1349,12 @@ TaskPtr Engine::RecvTask(bool block) {
     g.col = get(g.num_edge, "train_graph.col");
     if (h->have_data) g.data = get(g.num_edge, "train_graph.data");
   }
-  CUDA_CALL(cudaStreamSynchronize(st));
-  RingEndRead(&ring_->ctl, &h->ready, idx);
+  // no host wait: the extraction kernels are ordered behind these copies on the same stream; the slot goes back
+  // to the samplers (PollRecvs) once the copies' event has fired
+  cudaEvent_t ev = XferEvent();
+  CUDA_CALL(cudaEventRecord(ev, st));
+  pending_recvs_.push_back(PendingXfer{idx, ev, nullptr});
+  PollRecvs(false);
   Profiler::Get().LogStep(task->key, kLogL1RecvTime, tr.Passed());
   return task;
 }
@@ -1427,6 +1471,7 @@ bool Engine::PumpTrainer(int depth) {
   TaskPtr task = x_inflight_.front();
   x_inflight_.pop_front();
   extractor_->Finish(task);
+  PollRecvs(true);  // the batch is extracted, so its copies out of the ring are done: the slots go back
   LogExtracted(task, (double)(Timer::NowMicro() - task->t_extract) * 1e-6);
   graph_pool_->Submit(task);
   return true;
@@ -1487,6 +1532,8 @@ void Engine::Shutdown() {
   threads_.clear();
   current_.reset();
   if (sampler_) sampler_->SyncAll();
+  if (ring_ && role_ == kRoleSampler && send_stream_) { cudaSetDevice(sampler_->device()); PollSends(true); }
+  if (ring_ && role_ == kRoleTrainer && extractor_) { cudaSetDevice(extractor_->device()); PollRecvs(true); }
   inflight_.clear();
   x_inflight_.clear();
   if (extractor_) { cudaSetDevice(extractor_->device()); cudaStreamSynchronize(extractor_->stream()); }

@@ -86,6 +86,14 @@ class Engine {
   void LogExtracted(const TaskPtr &t, double finish_time);
   TaskPtr RecvTask(bool block = true);
   void SendTask(const TaskPtr &t);
+  // arch5 transport without a host wait per batch: copies are enqueued, the ring slot is published / released
+  // when their event has fired (polled by the pump)
+  struct PendingXfer { uint64_t idx; cudaEvent_t ev; TaskPtr keep; };
+  void PollSends(bool drain);
+  void PollRecvs(bool drain);
+  cudaEvent_t XferEvent();
+  std::deque<PendingXfer> pending_sends_, pending_recvs_;
+  std::vector<cudaEvent_t> xfer_events_;
   void DoPreSample();
   void DoGpuRanking();
   void CreateSharedState();

@@ -487,3 +487,137 @@ def sample_batch_oracle(o, graph, seeds, fanouts, sample_type, seed, batch_key, 
                          num_src=len(unique), num_dst=len(cur), num_edge=len(s))
         cur = unique
     return dict(layers=layers, input_nodes=cur, output_nodes=_u32(seeds), raw=raw)
+
+
+# ---------------------------------------------------------------------------
+# the reference's own CUDA kernels (oracle/_ref/libsamgraph_ref_cuda.so, built by `make -C oracle refcuda` from
+# the reference's .cu files in place): GPU-side checker for tests/test_vs_reference_cuda_gpu.py.  All array
+# arguments are torch CUDA tensors (int32-typed views of uint32 data, float32 tables).
+# ---------------------------------------------------------------------------
+def have_ref_cuda():
+    return os.path.exists(os.path.join(HERE, "_ref", "libsamgraph_ref_cuda.so"))
+
+
+class RefCUDA:
+    KINDS = {"khop0": 0, "khop1": 1, "weighted_khop": 2, "random_walk": 3, "weighted_khop_prefix": 4, "khop2": 5,
+             "weighted_khop_hash_dedup": 6}
+
+    def __init__(self, device=0, path=None):
+        path = path or os.path.join(HERE, "_ref", "libsamgraph_ref_cuda.so")
+        if not os.path.exists(path):
+            raise FileNotFoundError(path)
+        self.lib = L = C.CDLL(path)
+        vp, sz = C.c_void_p, C.c_size_t
+        L.refcuda_set_device.argtypes = [C.c_int]
+        L.refcuda_states_new.restype = vp
+        L.refcuda_states_new.argtypes = [C.c_int, szp, sz, sz, sz]
+        L.refcuda_states_free.argtypes = [vp]
+        L.refcuda_sample.restype = sz
+        L.refcuda_sample.argtypes = [C.c_int, vp, vp, vp, vp, vp, vp, sz, sz, vp, vp, vp]
+        L.refcuda_freqmap_new.restype = vp
+        L.refcuda_freqmap_new.argtypes = [sz, sz]
+        L.refcuda_freqmap_free.argtypes = [vp]
+        L.refcuda_random_walk.restype = sz
+        L.refcuda_random_walk.argtypes = [vp, vp, vp, sz, sz, C.c_double, sz, sz, vp, vp, vp, vp, vp]
+        L.refcuda_topk.restype = sz
+        L.refcuda_topk.argtypes = [vp, vp, vp, sz, vp, sz, sz, vp, vp, vp]
+        L.refcuda_ht_new.restype = vp
+        L.refcuda_ht_new.argtypes = [sz]
+        L.refcuda_ht_free.argtypes = [vp]
+        L.refcuda_ht_reset.argtypes = [vp]
+        L.refcuda_ht_fill_unique.argtypes = [vp, vp, sz]
+        L.refcuda_ht_fill_duplicates.restype = sz
+        L.refcuda_ht_fill_duplicates.argtypes = [vp, vp, sz, vp]
+        L.refcuda_ht_num_items.restype = sz
+        L.refcuda_ht_num_items.argtypes = [vp]
+        L.refcuda_map_edges.argtypes = [vp, vp, vp, vp, vp, sz]
+        L.refcuda_get_miss_cache_index.argtypes = [vp, vp, vp, szp, vp, vp, szp, vp, sz]
+        L.refcuda_set_device(device)
+
+    @staticmethod
+    def _d(t):
+        return None if t is None else t.data_ptr()
+
+    def states(self, sample_type, fanouts, batch_size, num_random_walk=1):
+        f = (C.c_size_t * len(fanouts))(*fanouts)
+        return self.lib.refcuda_states_new(self.KINDS[sample_type], f, len(fanouts), batch_size, num_random_walk)
+
+    def states_free(self, s):
+        self.lib.refcuda_states_free(s)
+
+    def sample(self, sample_type, indptr, indices, inp, fanout, states, prob=None, alias=None, prefix=None):
+        """One layer of the reference sampler; returns (src, dst) device tensors trimmed to the edge count."""
+        import torch
+        n = inp.numel()
+        out_src = torch.empty(max(1, n * fanout), dtype=torch.int32, device=inp.device)
+        out_dst = torch.empty_like(out_src)
+        m = self.lib.refcuda_sample(self.KINDS[sample_type], self._d(indptr), self._d(indices), self._d(prob),
+                                    self._d(alias), self._d(prefix), self._d(inp), n, fanout, self._d(out_src),
+                                    self._d(out_dst), states)
+        return out_src[:m], out_dst[:m]
+
+    def freqmap(self, max_nodes, edges_per_node):
+        return self.lib.refcuda_freqmap_new(max_nodes, edges_per_node)
+
+    def freqmap_free(self, m):
+        self.lib.refcuda_freqmap_free(m)
+
+    def random_walk(self, indptr, indices, inp, walk_len, restart_prob, num_walk, K, freqmap, states):
+        import torch
+        n = inp.numel()
+        outs = [torch.empty(max(1, n * K), dtype=torch.int32, device=inp.device) for _ in range(3)]
+        m = self.lib.refcuda_random_walk(self._d(indptr), self._d(indices), self._d(inp), n, walk_len, restart_prob,
+                                         num_walk, K, self._d(outs[0]), self._d(outs[1]), self._d(outs[2]), freqmap,
+                                         states)
+        return [o[:m] for o in outs]
+
+    def topk(self, freqmap, tmp_src, tmp_dst, inp, K):
+        import torch
+        n = inp.numel()
+        outs = [torch.empty(max(1, n * K), dtype=torch.int32, device=inp.device) for _ in range(3)]
+        m = self.lib.refcuda_topk(freqmap, self._d(tmp_src), self._d(tmp_dst), tmp_src.numel(), self._d(inp), n, K,
+                                  self._d(outs[0]), self._d(outs[1]), self._d(outs[2]))
+        return [o[:m] for o in outs]
+
+    def hashtable(self, size):
+        return RefCudaHashTable(self, size)
+
+    def get_miss_cache_index(self, table, nodes):
+        import torch
+        n = nodes.numel()
+        outs = [torch.empty(max(1, n), dtype=torch.int32, device=nodes.device) for _ in range(4)]
+        nm, nc = C.c_size_t(0), C.c_size_t(0)
+        self.lib.refcuda_get_miss_cache_index(self._d(table), self._d(outs[0]), self._d(outs[1]), C.byref(nm),
+                                              self._d(outs[2]), self._d(outs[3]), C.byref(nc), self._d(nodes), n)
+        return outs[0][:nm.value], outs[1][:nm.value], outs[2][:nc.value], outs[3][:nc.value]
+
+
+class RefCudaHashTable:
+    def __init__(self, ref, size):
+        self.r, self.h = ref, ref.lib.refcuda_ht_new(size)
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            self.r.lib.refcuda_ht_free(self.h)
+            self.h = None
+
+    def reset(self):
+        self.r.lib.refcuda_ht_reset(self.h)
+
+    def fill_unique(self, ids):
+        self.r.lib.refcuda_ht_fill_unique(self.h, ids.data_ptr(), ids.numel())
+
+    def fill_duplicates(self, ids):
+        import torch
+        unique = torch.empty(ids.numel() + self.num_items() + 1, dtype=torch.int32, device=ids.device)
+        m = self.r.lib.refcuda_ht_fill_duplicates(self.h, ids.data_ptr(), ids.numel(), unique.data_ptr())
+        return unique[:m]
+
+    def num_items(self):
+        return int(self.r.lib.refcuda_ht_num_items(self.h))
+
+    def map_edges(self, src, dst):
+        import torch
+        ns, nd = torch.empty_like(src), torch.empty_like(dst)
+        self.r.lib.refcuda_map_edges(self.h, src.data_ptr(), ns.data_ptr(), dst.data_ptr(), nd.data_ptr(), src.numel())
+        return ns, nd

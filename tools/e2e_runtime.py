@@ -2,7 +2,7 @@
 """End-to-end leg of bench.py: the hot path through the public API (samgraph.torch over the samgraph_*
 C-ABI of the C++ engine), one process, dataset loaded from the reference's on-disk format.
 
-  python tools/e2e_runtime.py <dataset_dir> <steps> <warmup> <cache_pct> <device> <seed>
+  python tools/e2e_runtime.py <dataset_dir> <steps> <warmup> <cache_pct> <device> <seed> [sample_type] [fanout,...]
 
 Per timed step: (sam.sample_once();) key = sam.get_next_batch(); the batch label tensor and the per-layer
 edge counts are read back to the host.  Prints one JSON object."""
@@ -18,25 +18,30 @@ sys.path.insert(0, os.path.join(ROOT, "fgnn-artifacts_b200"))
 def main():
     path, steps, warmup, cache_pct, dev, seed = sys.argv[1], int(sys.argv[2]), int(sys.argv[3]), float(sys.argv[4]), \
         sys.argv[5], int(sys.argv[6])
+    sample_type = sys.argv[7] if len(sys.argv) > 7 else "khop2"
+    fanout = [int(x) for x in sys.argv[8].split(",")] if len(sys.argv) > 8 else [25, 10]
     import torch
     import samgraph.torch as sam
-    fanout = [25, 10]
     meta = dict(l.split() for l in open(os.path.join(path, "meta.txt")) if l.strip())
     spe_guess = (int(meta["NUM_TRAIN_SET"]) + 7999) // 8000
     # enough epochs for warm-up + timed steps + the batches the pipelined sampler keeps in flight
     # (the profiler keeps one record per (epoch, step), so this is sized, not "infinite")
     num_epoch = (steps + warmup + 32) // spe_guess + 2
-    cfg = {"dataset_path": path, "_arch": sam.kArch3, "_sample_type": sam.kKHop2, "batch_size": 8000,
+    cfg = {"dataset_path": path, "_arch": sam.kArch3, "_sample_type": sam.sample_types[sample_type], "batch_size": 8000,
            "num_epoch": num_epoch, "_cache_policy": sam.kCacheByPreSample, "cache_percentage": cache_pct,
            "max_sampling_jobs": 10, "max_copying_jobs": 2, "omp_thread_num": os.cpu_count() or 1,
-           "sampler_ctx": dev, "trainer_ctx": dev, "fanout": fanout, "num_fanout": 2, "presample_epoch": 1,
-           "seed": seed}
+           "sampler_ctx": dev, "trainer_ctx": dev, "presample_epoch": 1, "seed": seed}
+    if sample_type == "random_walk":
+        cfg.update(random_walk_length=3, random_walk_restart_prob=0.5, num_random_walk=4, num_neighbor=5, num_layer=3)
+        fanout = [5, 5, 5]
+    else:
+        cfg.update(fanout=fanout, num_fanout=len(fanout), num_layer=len(fanout))
     t0 = time.time()
     sam.config(cfg)
     sam.init()
     init_s = time.time() - t0
     torch.cuda.set_device(torch.device(dev))
-    L = 2
+    L = len(fanout)
     pipeline = os.environ.get("FGNN_E2E_PIPELINE", "1") != "0"
     if pipeline:
         sam.start()                                            # background sampler + extractor threads (--pipeline)
@@ -78,6 +83,11 @@ def main():
            "note": "host->device bytes per step = feature rows missing from the HBM cache, read from the pinned host "
                    "feature table inside the gather kernel; device->host = labels + edge counts; host clock around "
                    "the loop"}
+    sw = sorted(step_wall)
+    out["steps"] = steps
+    out["warmup"] = warmup
+    out["step_wall_us_p50_p99_max"] = [round(sw[len(sw) // 2] * 1e6, 1), round(sw[min(len(sw) - 1, int(len(sw) * 0.99))] * 1e6, 1),
+                                       round(sw[-1] * 1e6, 1)]
     if os.environ.get("FGNN_E2E_DIAG"):
         names = ["kLogL1SampleTime", "kLogL2ShuffleTime", "kLogL2CoreSampleTime", "kLogL1CopyTime",
                  "kLogL2GraphCopyTime", "kLogL2CacheCopyTime", "kLogL2IdCopyTime", "kLogL2ExtractTime"]
