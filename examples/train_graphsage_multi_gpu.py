@@ -190,6 +190,8 @@ def main(argv=None):
     a = parse(argv)
     import samgraph.torch as sam
     S, T = a.num_sample_worker, a.num_train_worker
+    if a.single_gpu and T > 1:
+        a.no_ddp = True      # NCCL refuses two ranks on one device; the reference forces T = 1 there (common_config.py:186-191)
     sam.config(run_config(a, sam))
     sam.data_init()                                        # no CUDA before fork (dist_engine.cc:611-632)
     ctx = mp.get_context("fork")

@@ -46,8 +46,8 @@ struct FcBatch {
   Bucket *table;
   uint32_t *num_items;       // device: unique ids so far
   uint32_t *counts;          // device [L][3] = num_dst, num_edge, num_src
-  uint32_t *dst;             // this layer's scratch: sampled global id of every padded slot (EMPTY = hole)
-  uint32_t *pos;             // this layer's scratch: bucket of every padded slot
+  uint32_t *dst;             // this layer's scratch: sampled global id of every padded slot (EMPTY = hole) ...
+  uint32_t *pos;             // ... overwritten in place by the slot's bucket position (same array)
   uint32_t *row, *col;       // this layer's outputs
   ChainWs *ws;
   RngKey key;                // Philox key of (seed, batch_key, layer)
@@ -440,7 +440,7 @@ bool fast_chain_supported(const fgnn_sample_plan *pl) {
     if (pl->fanout[i] == 0 || pl->fanout[i] > 128) return false;
     const uint64_t slots = (uint64_t)pl->in_max[i] * pl->fanout[i];
     if (slots > (uint64_t)kMaxChainCtas * kFcChunk) return false;  // one aggregate slot per 2048-slot chunk
-    if (!pl->pos[i] || !pl->dst[i]) return false;
+    if (!pl->pos[i]) return false;
   }
   return pl->capacity <= 0x80000000ull;
 }
@@ -488,7 +488,9 @@ int fast_chain_launch(const fgnn_sample_plan *const *plans, const fgnn_sample_ou
       b.table = (Bucket *)plans[k]->table;
       b.num_items = plans[k]->num_items;
       b.counts = outs[k]->counts;
-      b.dst = plans[k]->dst[i];
+      // ONE padded scratch array per layer: the sampler writes the picked ids into it, the insert replaces every id
+      // by its bucket position in place (each slot is read and rewritten by the same thread)
+      b.dst = plans[k]->pos[i];
       b.pos = plans[k]->pos[i];
       b.row = outs[k]->row[i];
       b.col = outs[k]->col[i];

@@ -515,6 +515,7 @@ def test_sample_weighted_hash_dedup_matches_oracle(K, oracle, gs, n, fanout):
 
 
 @pytest.mark.parametrize("n,W,L,Kn,p", [(0, 4, 3, 5, 0.5), (1, 4, 3, 5, 0.5), (3000, 4, 3, 5, 0.5), (777, 3, 3, 4, 0.3),
+                                        (500, 6, 8, 5, 0.1), (300, 10, 10, 7, 0.05), (40, 40, 30, 10, 0.02),
                                         (500, 8, 4, 10, 0.0), (500, 1, 1, 1, 0.9), (300, 5, 2, 3, 1.0)])
 def test_random_walk_topk_matches_oracle(K, oracle, gs, n, W, L, Kn, p):
     seeds = pick_seeds(gs.indptr_np, n, 8)

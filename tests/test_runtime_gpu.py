@@ -194,13 +194,66 @@ def test_arch5_forked_sampler_and_trainer_processes(tmp_path, oracle, dataset, S
     (1, 1, 1, True, 0.25, "khop2"), (1, 1, 0, True, 0.25, "khop2"),
     (2, 2, 1, True, 0.1, "khop2"), (2, 2, 0, True, 0.0, "khop2"), (2, 2, 1, False, 0.0, "khop2"),
     (1, 3, 1, True, 0.1, "weighted_khop"), (2, 6, 1, True, 0.1, "khop2"), (2, 2, 1, True, 0.1, "random_walk")])
+@pytest.mark.parametrize("trainers_first", [False, True])
 def test_arch5_samplers_and_trainers_on_different_gpus(tmp_path, oracle, dataset, S, T, nvlink_queue, partition,
-                                                       replicate_pct, sample_type):
+                                                       replicate_pct, sample_type, trainers_first):
     """The factored split of dist_engine.cc:231-465 across REAL GPUs (common_config.py:182-185 placement:
     samplers on cuda:0..S-1, trainers on cuda:S..S+T-1): task payloads cross NVLink into the trainers' device
     ring (or bounce through pinned host memory), the cache stripes are read by NVLink peer loads.  Every batch
     every trainer receives is bit-exact against the oracle.  Needs S+T GPUs (run with gpurun --gpus N)."""
     if torch.cuda.device_count() < S + T:
         pytest.skip("needs %d GPUs, this box has %d" % (S + T, torch.cuda.device_count()))
-    arch5_scenario(tmp_path, oracle, dataset, S, T, nvlink_queue, ["cuda:%d" % i for i in range(S)],
-                   ["cuda:%d" % (S + i) for i in range(T)], replicate_pct, sample_type, partition)
+    if trainers_first:      # the reference's placement, common_config.py:182-185 ("trainer gpu id should start from 0")
+        if (S, T, nvlink_queue) not in ((1, 1, 1), (2, 2, 1), (2, 6, 1)):
+            pytest.skip("placement variant run on a subset")
+        s_dev, t_dev = ["cuda:%d" % (T + i) for i in range(S)], ["cuda:%d" % i for i in range(T)]
+    else:
+        s_dev, t_dev = ["cuda:%d" % i for i in range(S)], ["cuda:%d" % (S + i) for i in range(T)]
+    arch5_scenario(tmp_path, oracle, dataset, S, T, nvlink_queue, s_dev, t_dev, replicate_pct, sample_type, partition)
+
+
+def run_factored_example(dataset, extra, timeout=400):
+    cmd = [sys.executable, os.path.join(ROOT, "examples", "train_graphsage_multi_gpu.py"), "--dataset-path",
+           dataset["path"], "--batch-size", "512", "--fanout", "5", "10", "--num-epoch", "3", "--cache-percentage", "0.3",
+           "--json", "--timeout", "300"] + extra
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=timeout, env=dict(os.environ, SAMGRAPH_LOG_LEVEL="warn"))
+    assert r.returncode == 0, "example failed:\n%s\n%s" % (r.stdout[-3000:], r.stderr[-3000:])
+    line = [x for x in r.stdout.splitlines() if x.startswith("FACTORED_JSON ")][-1]
+    return json.loads(line[len("FACTORED_JSON "):])
+
+
+@pytest.mark.parametrize("S,T,train,pipeline", [(1, 1, True, True), (2, 2, True, True), (1, 2, False, True),
+                                                (1, 1, False, False)])
+def test_factored_training_example_single_gpu(dataset, S, T, train, pipeline):
+    """examples/train_graphsage_multi_gpu.py (the process structure of the reference's multi_gpu/train_graphsage.py:
+    data_init + fork, per-epoch barriers, extract_start in pipeline mode, DDP between the trainers) with everything
+    on cuda:0: every epoch delivers every mini-batch exactly once, the model trains (finite, decreasing-ish loss)."""
+    extra = ["--num-sample-worker", str(S), "--num-train-worker", str(T), "--single-gpu"]
+    if not train:
+        extra.append("--no-train")
+    if pipeline:
+        extra.append("--pipeline")
+    out = run_factored_example(dataset, extra)
+    num_step = (len(dataset["train_set"]) + 511) // 512
+    assert out["samplers"] == S and out["trainers"] == T and len(out["epochs"]) == 3
+    for ep in out["epochs"]:
+        assert ep["steps"] == num_step and ep["edges"] > 0 and ep["wall_s"] > 0
+        assert ep["feature_bytes"] == ep["rows"] * dataset["feat_dim"] * 4
+        assert 0 <= ep["miss_bytes"] <= ep["feature_bytes"]
+    if train:
+        assert all(x is not None and np.isfinite(x) for x in out["loss"])
+
+
+@pytest.mark.parametrize("S,T", [(1, 1), (1, 3), (2, 6)])
+def test_factored_training_example_across_gpus(dataset, S, T):
+    """The same example with trainers on cuda:0..T-1 and samplers on cuda:T..T+S-1 (common_config.py:182-185)."""
+    if torch.cuda.device_count() < S + T:
+        pytest.skip("needs %d GPUs, this box has %d" % (S + T, torch.cuda.device_count()))
+    out = run_factored_example(dataset, ["--num-sample-worker", str(S), "--num-train-worker", str(T), "--pipeline",
+                                         "--master-port", str(12400 + S + T)])
+    num_step = (len(dataset["train_set"]) + 511) // 512
+    assert out["trainer_ctx"] == ["cuda:%d" % i for i in range(T)]
+    assert out["sampler_ctx"] == ["cuda:%d" % (T + i) for i in range(S)]
+    for ep in out["epochs"]:
+        assert ep["steps"] == num_step and ep["edges"] > 0
+    assert all(x is not None and np.isfinite(x) for x in out["loss"])

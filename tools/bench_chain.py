@@ -37,7 +37,8 @@ def main():
     B = bench.BATCH
     ks = [int(x) for x in a.ks.split(",")]
     hp = HotPath(wl["indptr"], wl["indices"], wl["V"], fanouts, B, a.sample_type, seed=1, device="cuda:0",
-                 num_slots=max(ks), rw=bench.RW if a.sample_type == "random_walk" else None)
+                 num_slots=max(ks), rw=bench.RW if a.sample_type == "random_walk" else None,
+                 ht_capacity=(1 << int(os.environ["FGNN_DIAG_HT_LOG2"])) if os.environ.get("FGNN_DIAG_HT_LOG2") else None)
     spe = wl["T"] // B
     perm = wl["train"]
     out = {"workload": a.workload, "fanout": fanouts, "env": {k: v for k, v in os.environ.items() if k.startswith("FGNN_")}}
