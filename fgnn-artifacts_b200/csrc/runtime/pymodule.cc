@@ -84,6 +84,25 @@ PyObject *ToCapsule(const TensorPtr &t, const TaskPtr &task, DataType view_as) {
   return PyCapsule_New(m, "dltensor", CapsuleDestructor);
 }
 
+// torch.Tensor view of the same memory (adapter.cc:54-62 returns torch::from_blob tensors).  The extension does not
+// link libtorch: the DLPack capsule is adopted by torch.utils.dlpack.from_dlpack, looked up once through the CPython
+// API, so `samgraph_torch_*` hand out real tensors and the reference's adapter.py binds unmodified.
+PyObject *ToTensor(const TensorPtr &t, const TaskPtr &task, DataType view_as) {
+  static PyObject *from_dlpack = nullptr;
+  if (!from_dlpack) {
+    PyObject *mod = PyImport_ImportModule("torch.utils.dlpack");
+    if (!mod) return nullptr;
+    from_dlpack = PyObject_GetAttrString(mod, "from_dlpack");
+    Py_DECREF(mod);
+    if (!from_dlpack) return nullptr;
+  }
+  PyObject *cap = ToCapsule(t, task, view_as);
+  if (!cap) return nullptr;
+  PyObject *tensor = PyObject_CallFunctionObjArgs(from_dlpack, cap, nullptr);
+  Py_DECREF(cap);
+  return tensor;
+}
+
 TaskPtr Batch(unsigned long long key) {
   TaskPtr b = Engine::Get()->CurrentBatch();
   if (!b) {
@@ -98,13 +117,13 @@ PyObject *GetGraphFeat(PyObject *, PyObject *args) {
   unsigned long long key;
   if (!PyArg_ParseTuple(args, "K", &key)) return nullptr;
   TaskPtr b = Batch(key);
-  return b ? ToCapsule(b->input_feat, b, kF32) : nullptr;
+  return b ? ToTensor(b->input_feat, b, kF32) : nullptr;
 }
 PyObject *GetGraphLabel(PyObject *, PyObject *args) {
   unsigned long long key;
   if (!PyArg_ParseTuple(args, "K", &key)) return nullptr;
   TaskPtr b = Batch(key);
-  return b ? ToCapsule(b->output_label, b, kI64) : nullptr;
+  return b ? ToTensor(b->output_label, b, kI64) : nullptr;
 }
 template <int WHICH>
 PyObject *GetGraphEdge(PyObject *, PyObject *args) {
@@ -118,7 +137,7 @@ PyObject *GetGraphEdge(PyObject *, PyObject *args) {
     return nullptr;
   }
   const TrainGraph &g = b->graphs[layer];
-  return ToCapsule(WHICH == 0 ? g.row : (WHICH == 1 ? g.col : g.data), b, kI32);
+  return ToTensor(WHICH == 0 ? g.row : (WHICH == 1 ? g.col : g.data), b, kI32);
 }
 // Block hand-off in CSC form: (indptr, indices, edge_ids | None) of one layer, the arguments of
 // the reference's DGL patch `create_unitgraph_from_csc` (3rdparty/dgl.patch:30-57).  The reference builds COO
@@ -177,11 +196,11 @@ PyObject *GetGraphCsc(PyObject *, PyObject *args) {
     g.csc_indices = indices;
     g.csc_eids = eids;
   }
-  PyObject *a = ToCapsule(g.csc_indptr, b, kI32);
-  PyObject *c = a ? ToCapsule(g.csc_indices, b, kI32) : nullptr;
+  PyObject *a = ToTensor(g.csc_indptr, b, kI32);
+  PyObject *c = a ? ToTensor(g.csc_indices, b, kI32) : nullptr;
   PyObject *d = nullptr;
   if (c) {
-    if (g.csc_eids) d = ToCapsule(g.csc_eids, b, kI32);
+    if (g.csc_eids) d = ToTensor(g.csc_eids, b, kI32);
     else { d = Py_None; Py_INCREF(d); }
   }
   if (!a || !c || !d) {
@@ -196,36 +215,36 @@ PyObject *GetInputNodes(PyObject *, PyObject *args) {
   unsigned long long key;
   if (!PyArg_ParseTuple(args, "K", &key)) return nullptr;
   TaskPtr b = Batch(key);
-  return b ? ToCapsule(b->input_nodes, b, kI32) : nullptr;
+  return b ? ToTensor(b->input_nodes, b, kI32) : nullptr;
 }
 PyObject *GetOutputNodes(PyObject *, PyObject *args) {
   unsigned long long key;
   if (!PyArg_ParseTuple(args, "K", &key)) return nullptr;
   TaskPtr b = Batch(key);
-  return b ? ToCapsule(b->output_nodes, b, kI32) : nullptr;
+  return b ? ToTensor(b->output_nodes, b, kI32) : nullptr;
 }
 PyObject *GetDatasetFeat(PyObject *, PyObject *) {
   const Dataset *ds = Engine::Get()->GetDataset();
   if (!ds) { PyErr_SetString(PyExc_RuntimeError, "samgraph: dataset not loaded"); return nullptr; }
-  return ToCapsule(ds->feat, nullptr, kF32);
+  return ToTensor(ds->feat, nullptr, kF32);
 }
 PyObject *GetDatasetLabel(PyObject *, PyObject *) {
   const Dataset *ds = Engine::Get()->GetDataset();
   if (!ds) { PyErr_SetString(PyExc_RuntimeError, "samgraph: dataset not loaded"); return nullptr; }
-  return ToCapsule(ds->label, nullptr, kI64);
+  return ToTensor(ds->label, nullptr, kI64);
 }
 
 PyMethodDef kMethods[] = {
-    {"samgraph_torch_get_graph_feat", GetGraphFeat, METH_VARARGS, "DLPack capsule: f32 [num_input, feat_dim] on the trainer GPU"},
-    {"samgraph_torch_get_graph_label", GetGraphLabel, METH_VARARGS, "DLPack capsule: i64 [batch] on the trainer GPU"},
-    {"samgraph_torch_get_graph_row", GetGraphEdge<0>, METH_VARARGS, "DLPack capsule: i32 [num_edge] (neighbour local ids)"},
-    {"samgraph_torch_get_graph_col", GetGraphEdge<1>, METH_VARARGS, "DLPack capsule: i32 [num_edge] (seed local ids)"},
-    {"samgraph_torch_get_graph_data", GetGraphEdge<2>, METH_VARARGS, "DLPack capsule: i32 [num_edge] (random-walk visit counts)"},
-    {"samgraph_torch_get_graph_csc", GetGraphCsc, METH_VARARGS, "(indptr i32 [num_dst+1], indices i32 [num_edge], edge_ids i32 [num_edge] | None) DLPack capsules"},
-    {"samgraph_torch_get_dataset_feat", GetDatasetFeat, METH_NOARGS, "DLPack capsule: host feature table"},
-    {"samgraph_torch_get_dataset_label", GetDatasetLabel, METH_NOARGS, "DLPack capsule: host label table"},
-    {"samgraph_torch_get_graph_input_nodes", GetInputNodes, METH_VARARGS, "DLPack capsule: i32 [num_input]"},
-    {"samgraph_torch_get_graph_output_nodes", GetOutputNodes, METH_VARARGS, "DLPack capsule: i32 [batch]"},
+    {"samgraph_torch_get_graph_feat", GetGraphFeat, METH_VARARGS, "torch.Tensor: f32 [num_input, feat_dim] on the trainer GPU"},
+    {"samgraph_torch_get_graph_label", GetGraphLabel, METH_VARARGS, "torch.Tensor: i64 [batch] on the trainer GPU"},
+    {"samgraph_torch_get_graph_row", GetGraphEdge<0>, METH_VARARGS, "torch.Tensor: i32 [num_edge] (neighbour local ids)"},
+    {"samgraph_torch_get_graph_col", GetGraphEdge<1>, METH_VARARGS, "torch.Tensor: i32 [num_edge] (seed local ids)"},
+    {"samgraph_torch_get_graph_data", GetGraphEdge<2>, METH_VARARGS, "torch.Tensor: i32 [num_edge] (random-walk visit counts)"},
+    {"samgraph_torch_get_graph_csc", GetGraphCsc, METH_VARARGS, "(indptr i32 [num_dst+1], indices i32 [num_edge], edge_ids i32 [num_edge] | None) tensors"},
+    {"samgraph_torch_get_dataset_feat", GetDatasetFeat, METH_NOARGS, "torch.Tensor: host feature table"},
+    {"samgraph_torch_get_dataset_label", GetDatasetLabel, METH_NOARGS, "torch.Tensor: host label table"},
+    {"samgraph_torch_get_graph_input_nodes", GetInputNodes, METH_VARARGS, "torch.Tensor: i32 [num_input]"},
+    {"samgraph_torch_get_graph_output_nodes", GetOutputNodes, METH_VARARGS, "torch.Tensor: i32 [batch]"},
     {nullptr, nullptr, 0, nullptr}};
 
 PyModuleDef kModule = {PyModuleDef_HEAD_INIT, "c_lib", "samgraph B200 runtime: tensor hand-off", -1, kMethods,

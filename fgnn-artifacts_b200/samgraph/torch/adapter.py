@@ -1,10 +1,14 @@
 """samgraph.torch — the API the training scripts use (`import samgraph.torch as sam`).
 
-Same functions as the reference's samgraph/torch/adapter.py:30-179.  Tensors come out of the C++
-engine as DLPack capsules (csrc/runtime/pymodule.cc) and are adopted zero-copy with
-torch.from_dlpack; DGL is imported lazily so that sampling/extraction works on boxes without it."""
+Same functions as the reference's samgraph/torch/adapter.py:30-179.  The C++ engine hands out torch.Tensor
+views of its own memory (csrc/runtime/pymodule.cc: DLPack capsule adopted zero-copy by torch.utils.dlpack inside
+the extension), exactly what the reference's c_lib returns, so the reference's adapter.py binds to this c_lib
+unmodified too; DGL is imported lazily so that sampling/extraction works on boxes without it."""
 import torch
-from torch.utils.dlpack import from_dlpack as _from_dlpack
+
+
+def _from_dlpack(t):
+    return t           # c_lib returns tensors (round 1 returned capsules)
 
 from samgraph.common import *  # noqa: F401,F403  (enum constants, sample_types, builtin_archs, ...)
 from samgraph.common import SamGraphBasics

@@ -111,3 +111,55 @@ def test_reference_single_process_scripts_config(dataset_root, script, sample_ty
     out = run_script(REF, script, root, ["--dataset", "papers100M", "--root-path", root, "--cache-percentage", "0.1",
                                          "--num-epoch", "2", "--arch", "arch3"])
     assert out["arch"] == "arch3" and out["sample_type"] == sample_type and out["num_epoch_cfg"] == 3
+
+
+ADAPTER_DRIVER = textwrap.dedent('''
+    import json, sys, types, os
+    pkg, ref_adapter, dataset = sys.argv[1:4]
+    sys.path.insert(0, pkg)
+    import torch
+    for name in ("dgl", "dgl.heterograph"):
+        sys.modules[name] = types.ModuleType(name)
+    sys.modules["dgl.heterograph"].DGLBlock = object
+    import samgraph.torch as ours                      # package + c_lib of this repo
+    # the reference's adapter.py, UNMODIFIED, executed as a module of this package: it binds this repo's c_lib
+    # (`from samgraph.torch import c_lib`) and this repo's samgraph.common (SamGraphBasics, enum tables)
+    mod = types.ModuleType("samgraph.torch.adapter_ref")
+    mod.__file__ = os.path.join(os.path.dirname(ours.__file__), "adapter.py")
+    mod.__package__ = "samgraph.torch"
+    exec(compile(open(ref_adapter).read(), ref_adapter, "exec"), mod.__dict__)
+    cfg = {"dataset_path": dataset, "_arch": mod.kArch5, "arch": "arch5", "_sample_type": mod.kKHop2, "sample_type": "khop2",
+           "batch_size": 100, "num_epoch": 2, "_cache_policy": mod.kCacheByPreSample, "cache_policy": "pre_sample",
+           "cache_percentage": 0.1, "max_sampling_jobs": 4, "max_copying_jobs": 1, "omp_thread_num": 2,
+           "num_sample_worker": 1, "num_train_worker": 1, "fanout": [5, 3], "num_fanout": 2, "num_layer": 2,
+           "presample_epoch": 1}
+    mod.config(cfg)
+    mod.data_init()
+    feat, label = mod.get_dataset_feat(), mod.get_dataset_label()
+    assert isinstance(feat, torch.Tensor) and isinstance(label, torch.Tensor), (type(feat), type(label))
+    out = {"feat_shape": list(feat.shape), "feat_dtype": str(feat.dtype), "label_dtype": str(label.dtype),
+           "feat_sum": float(feat.double().sum()), "label_sum": int(label.sum()), "steps": mod.steps_per_epoch(),
+           "names": sorted(n for n in ("get_dgl_blocks", "get_dgl_blocks_with_weights", "get_graph_feat", "get_graph_row",
+                                       "get_graph_col", "get_graph_data", "notify_sampler_ready", "wait_for_sampler_ready",
+                                       "sample_init", "train_init", "extract_start", "num_local_step") if hasattr(mod, n))}
+    print("ADAPTER_JSON " + json.dumps(out))
+''')
+
+
+def test_reference_adapter_py_binds_this_c_lib_unmodified(dataset_root):
+    """samgraph/torch/adapter.py of the reference, byte for byte, on top of this repo's c_lib.so: the extension
+    returns torch.Tensor objects like the reference's (adapter.cc:181-192), so no edit is needed (round 1 returned
+    DLPack capsules and needed 9).  CPU-visible getters are exercised; the GPU getters share the same code path."""
+    import numpy as np
+    root, ds = dataset_root
+    ref_adapter = "/root/reference/samgraph/torch/adapter.py"
+    r = subprocess.run([sys.executable, "-c", ADAPTER_DRIVER, os.path.join(ROOT, "fgnn-artifacts_b200"), ref_adapter,
+                        os.path.join(root, "papers100M")], capture_output=True, text=True, timeout=300,
+                       env=dict(os.environ, CUDA_VISIBLE_DEVICES=""))
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-3000:]
+    out = json.loads([x for x in r.stdout.splitlines() if x.startswith("ADAPTER_JSON ")][-1][len("ADAPTER_JSON "):])
+    assert out["feat_shape"] == list(ds["feat"].shape) and out["feat_dtype"] == "torch.float32"
+    assert out["label_dtype"] == "torch.int64" and out["label_sum"] == int(ds["label"].sum())
+    assert abs(out["feat_sum"] - float(ds["feat"].astype(np.float64).sum())) < 1e-6 * ds["feat"].size
+    assert out["steps"] == (len(ds["train_set"]) + 99) // 100
+    assert len(out["names"]) == 12
