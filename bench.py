@@ -679,6 +679,10 @@ def run_ours(args):
         path = write_dataset_shm(args, wl, rank, world)
         try:
             out["e2e"] = run_e2e(args, wl, world, rank, dev, path)
+            if world == 1 and rank == 0 and not args.no_cpu_baseline:
+                # the reference's own CPU code on this box's cores (needs the graph: before it is released below)
+                out["cpu_baseline"] = cpu_baseline(args, wl, steps=None, budget_s=20.0)
+                args.no_cpu_baseline = True
             if not args.no_factored:
                 # the FACTORED mode (FGNN: dedicated sampler GPUs + dedicated trainer GPUs, arch5) on the same N GPUs:
                 # rank 0 forks S sampler and T trainer processes, the other ranks keep their GPUs idle meanwhile
