@@ -314,6 +314,7 @@ def run_ours(args):
     torch.cuda.set_device(local)
     dev = "cuda:%d" % local
     if world > 1:
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")   # keep stdout for the ONE json line (NCCL_DEBUG=VERSION boxes)
         dist.init_process_group("nccl", device_id=torch.device(dev))
     K.load()  # raises when the CUDA extension is missing: there is no CPU fallback
 
