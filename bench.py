@@ -64,6 +64,8 @@ def parse():
     ap.add_argument("--no-factored", action="store_true",
                     help="skip the factored (arch5: sampler GPUs + trainer GPUs) e2e leg and the measured epoch")
     ap.add_argument("--no-cache25", action="store_true", help="skip the extra 25 %% cache leg (profiling runs)")
+    ap.add_argument("--only-partition", action="store_true",
+                    help="diagnosis: N > 1, only the device-resident replicated + partitioned legs")
     ap.add_argument("--no-partition", action="store_true",
                     help="N > 1: skip the partitioned-cache legs (value is then the replicated-cache arm)")
     ap.add_argument("--replicate-pct", type=float, default=float(os.environ.get("FGNN_BENCH_REPLICATE_PCT", "0.25")),
@@ -507,6 +509,8 @@ def run_ours(args):
 
     Ksteps, W = args.steps, max(3, args.warmup)
     # reference-like regime first (25 % cache, misses over the host link) ...
+    if args.only_partition:
+        args.no_cache25 = args.no_e2e = args.no_cpu_baseline = True
     r25 = measure(0.25, min(Ksteps, steps_per_epoch), W, 2_000_000) \
         if args.cache_pct != 0.25 and not args.no_cache25 else None
     # ... then the headline regime
@@ -780,9 +784,16 @@ def run_factored(args, wl, world, rank, path):
             for line in r.stdout.splitlines():
                 if line.startswith("FACTORED_JSON "):
                     return json.loads(line[len("FACTORED_JSON "):])
-            return {"error": "%s leg failed: %s" % (tag, (r.stdout[-600:] + r.stderr[-1200:]).strip())}
+            err = r.stderr.strip()
+            keep = [l for l in err.splitlines() if "Error" in l or "error" in l or "what():" in l][:12]
+            return {"error": "%s leg failed: %s || %s" % (tag, " | ".join(keep)[:1500], err[-400:])}
         f = one(["--no-train", "--num-epoch", "4"], "e2e_factored")
         e = one(["--num-epoch", "3"], "epoch")
+        ddp_error = None
+        if "error" in e and T > 1:
+            # the measured epoch must not depend on the gradient all-reduce coming up: retry without DDP and say so
+            ddp_error = e["error"]
+            e = one(["--num-epoch", "3", "--no-ddp"], "epoch")
         res = {}
         if "error" in f:
             res["e2e_factored"] = f
@@ -814,6 +825,7 @@ def run_factored(args, wl, world, rank, path):
                 "kLogEpochConvertTime_s": sum(x["convert_s"] for x in timed) / k,
                 "kLogEpochTrainTime_s": sum(x["train_s"] for x in timed) / k,
                 "epoch_wall_s": [round(x["wall_s"], 5) for x in e["epochs"]], "loss": e["loss"],
+                "ddp": ddp_error is None and T > 1, "ddp_error": ddp_error,
                 "model": "GraphSAGE %d layers, hidden 256, mean aggregation as CSR SpMM on the CSC hand-off, Adam, "
                          "DDP (NCCL) between the trainers; examples/train_graphsage_multi_gpu.py --pipeline" % len(fanouts_of(args)),
                 "note": "measured, not extrapolated: whole epochs of the papers100M-shaped train set through samgraph.torch "

@@ -50,7 +50,7 @@ def parse(argv=None):
     ap.add_argument("--seed", type=int, default=0x5EED)
     ap.add_argument("--master-port", type=int, default=12377)
     ap.add_argument("--json", action="store_true")
-    ap.add_argument("--timeout", type=int, default=600)
+    ap.add_argument("--timeout", type=int, default=300)
     return ap.parse_args(argv)
 
 
@@ -206,11 +206,17 @@ def main(argv=None):
         p.start()
     bad = 0
     deadline = time.time() + a.timeout
+    # like sam.wait_one_child() in the reference's scripts: the first worker that dies takes the job down, the others
+    # must not sit in a barrier until it times out
+    while any(p.is_alive() for p in procs):
+        if any(p.exitcode not in (None, 0) for p in procs) or time.time() > deadline:
+            for p in procs:
+                if p.is_alive():
+                    p.kill()
+            break
+        time.sleep(0.05)
     for p in procs:
-        p.join(max(1.0, deadline - time.time()))
-        if p.is_alive():
-            p.kill()
-            p.join(10)
+        p.join(10)
         bad |= (p.exitcode != 0)
     if bad:
         print("train_graphsage_multi_gpu: a worker failed", file=sys.stderr)

@@ -85,9 +85,10 @@ extern "C" int fgnn_k_sample_batch(const fgnn_sample_plan *pl, const fgnn_sample
       case 1:
       case 2:
       case 4:
-        rc = fgnn_k_sample_replace(pl->sample_type, pl->indptr, pl->indices, pl->prob_table, pl->alias_table,
-                                   pl->prob_prefix_table, out->n2o, nmax, n_in, f, rng, nullptr, dst, col,
-                                   n_edge, pl->workspace, pl->workspace_bytes, pl->chain_ws, stream);
+        rc = fgnn_k_sample_replace_ranked(pl->sample_type, pl->indptr, pl->indices, pl->prob_table, pl->alias_table,
+                                          pl->prob_prefix_table, out->n2o, nmax, n_in, f, rng, nullptr, dst, col,
+                                          n_edge, pl->workspace, pl->workspace_bytes, pl->chain_ws, pl->rank_ws,
+                                          pl->num_nodes, stream);
         break;
       case 6:
         rc = fgnn_k_sample_weighted_hash_dedup(pl->indptr, pl->indices, pl->prob_table, pl->alias_table,

@@ -348,6 +348,7 @@ gather_bulk_kernel(char *__restrict__ out, const uint32_t *__restrict__ nodes, u
                    unsigned long long *d_stats) {
   rs.shard0 = (const char *)__ldg((const unsigned long long *)rs.shards);
   const bool hint = (miss_by_ldg & 2) != 0;  // bit 1 of the mode word: stream through L2 with evict-first
+  const bool peer_ldg = (miss_by_ldg & 4) != 0;  // bit 2: rows of NVLink-peer stripes by warp loads, not by the bulk engine
   miss_by_ldg &= 1;
   const uint64_t pol = l2_evict_first_policy();
   constexpr int A = S - 2;  // sub-groups of loads in flight ahead of the store
@@ -400,7 +401,7 @@ gather_bulk_kernel(char *__restrict__ out, const uint32_t *__restrict__ nodes, u
     const uint32_t bar = smem_u32(&s_bar[warp][s]);
     unsigned char *st = stage0 + (size_t)s * stage_bytes;
     const bool mine = (lane / G) == sub && node_i != kEmpty;
-    const bool by_bulk = mine && (slot_i != kEmpty || !miss_by_ldg);
+    const bool by_bulk = mine && (slot_i != kEmpty ? !(peer_ldg && rs.is_remote(slot_i)) : !miss_by_ldg);
     const uint32_t nbulk = __popc(__ballot_sync(0xFFFFFFFFu, by_bulk));
     if (lane == 0) mbar_expect_tx(bar, nbulk * row_bytes);
     __syncwarp();
@@ -494,6 +495,7 @@ struct GatherTuning {
   int stages;       // bulk: ring depth per warp (6, or 3 for long rows)
   uint32_t stage_cap;  // bulk: max bytes per stage
   int miss_ldg;     // bulk: host-resident rows by warp loads (1) or by the bulk engine (0)
+  int peer_ldg;     // bulk: rows of NVLink-peer stripes by warp loads (1) or by the bulk engine (0)
   int l2_hint;      // bulk: evict-first L2 policy on the streamed rows
   uint32_t group_rows; // group: rows per warp group (0 = auto)
   int ctas_per_sm;  // 0 = occupancy
@@ -514,6 +516,7 @@ GatherTuning read_tuning() {
   g.stages = env_int("FGNN_BULK_STAGES", 6);
   g.stage_cap = (uint32_t)env_int("FGNN_BULK_STAGE_BYTES", 2048);
   g.miss_ldg = env_int("FGNN_BULK_MISS_LDG", 0);
+  g.peer_ldg = env_int("FGNN_BULK_PEER_LDG", 0);
   g.l2_hint = env_int("FGNN_GATHER_L2HINT", 1);
   g.group_rows = (uint32_t)env_int("FGNN_GROUP_ROWS", 0);
   g.ctas_per_sm = env_int("FGNN_GATHER_CTAS_PER_SM", 0);
@@ -540,7 +543,8 @@ int launch_bulk(char *out, const uint32_t *nodes, uint32_t n_max, const uint32_t
   const uint64_t subs = ((uint64_t)n_max + G - 1) / G;
   const int grid = persistent_grid(subs, kBulkWarps * 4, occ, false, true);  // >= 4 sub-groups per warp
   kern<<<grid, kBulkWarps * 32, smem, st>>>(out, nodes, n_max, d_n, table, rs, G, stage_bytes,
-                                            (tuning().miss_ldg ? 1 : 0) | (tuning().l2_hint ? 2 : 0), d_stats);
+                                            (tuning().miss_ldg ? 1 : 0) | (tuning().l2_hint ? 2 : 0) |
+                                                (tuning().peer_ldg ? 4 : 0), d_stats);
   return 0;
 }
 }  // namespace

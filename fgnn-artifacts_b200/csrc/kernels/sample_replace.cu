@@ -45,10 +45,40 @@ size_t carve(ReplaceWs *w, void *base, uint32_t n_max, uint32_t fanout) {
   return (size_t)(p - (char *)base);
 }
 
-// sort key = seed id, EMPTY for rows that produce nothing (len == 0, padding)
+// ---------------------------------------------------------------------------
+// Ordering the seeds by id WITHOUT a sort (round 2; replaces the cub::DeviceRadixSort of round 1 on the
+// khop1 / weighted path, BASELINE config #5).  The seeds of a layer are unique, so the position of seed v in
+// ascending id order is simply the number of seeds with a smaller id: mark the seeds in a V-bit bitmap, keep a
+// count per 1024-bit block, scan the block counts (chained scan, common.cuh), and
+//     rank(v) = blockpre[v >> 10] + popcount(bitmap words of the block below v's word) + popcount(low bits).
+// The bitmap and the block counts live in `rank_ws`, which is all-zero between calls (the last kernel clears
+// exactly the words it set), so nothing of size V is touched per mini-batch.
+// ---------------------------------------------------------------------------
+struct RankWs {
+  uint32_t *bitmap;    // ceil(V / 32) words
+  uint32_t *blocksum;  // nb + 1 words, nb = ceil(V / 1024)
+  uint32_t *blockpre;  // nb + 1 words (scratch, no invariant)
+  uint32_t *counters;  // [0] = cursor of the rows that produce nothing
+  uint32_t nb;
+};
+
+size_t carve_rank(RankWs *w, void *base, size_t num_nodes) {
+  char *p = (char *)base;
+  const size_t words = (num_nodes + 31) / 32, nb = (num_nodes + 1023) / 1024;
+  w->bitmap = (uint32_t *)p; p += align256(words * 4);
+  w->blocksum = (uint32_t *)p; p += align256((nb + 1) * 4);
+  w->counters = (uint32_t *)p; p += 256;
+  w->blockpre = (uint32_t *)p; p += align256((nb + 1) * 4);
+  w->nb = (uint32_t)nb;
+  return (size_t)(p - (char *)base);
+}
+
+// sort key = seed id, EMPTY for rows that produce nothing (len == 0, padding); with a rank workspace the live
+// seeds are marked in the bitmap at the same time
 __global__ void __launch_bounds__(kBlock)
 replace_keys_kernel(const uint32_t *__restrict__ indptr, const uint32_t *__restrict__ input,
-                    uint32_t n_max, const uint32_t *__restrict__ d_n, uint32_t *keys, uint32_t *vals) {
+                    uint32_t n_max, const uint32_t *__restrict__ d_n, uint32_t *keys, uint32_t *vals,
+                    uint32_t *bitmap, uint32_t *blocksum) {
   const uint32_t n = load_count(n_max, d_n);
   for (uint32_t i = blockIdx.x * kBlock + threadIdx.x; i < n_max; i += gridDim.x * kBlock) {
     uint32_t key = kEmpty;
@@ -58,6 +88,75 @@ replace_keys_kernel(const uint32_t *__restrict__ indptr, const uint32_t *__restr
     }
     keys[i] = key;
     vals[i] = i;
+    if (bitmap && key != kEmpty) {
+      atomicOr(bitmap + (key >> 5), 1u << (key & 31u));
+      atomicAdd(blocksum + (key >> 10), 1u);
+    }
+  }
+}
+
+struct RankScanSmem {
+  uint32_t warp[kBlock / 32 + 1];
+  ChainSmem chain;
+};
+
+// blockpre[b] = sum of blocksum[0..b), blockpre[nb] = number of live seeds
+__global__ void __launch_bounds__(kBlock)
+rank_scan_kernel(const uint32_t *__restrict__ blocksum, uint32_t *__restrict__ blockpre, uint32_t nb, ChainWs *ws) {
+  __shared__ RankScanSmem sm;
+  const uint32_t p = chain_ticket(ws, &sm.chain);
+  uint32_t begin, end;
+  chunk_range(nb, p, gridDim.x, kBlock, &begin, &end);
+  unsigned long long partial = 0;
+  for (uint32_t i = begin + threadIdx.x; i < end; i += kBlock) partial += __ldg(blocksum + i);
+  unsigned long long chunk_total;
+  unsigned long long base = chain_scan(ws, &sm.chain, p, partial, &chunk_total);
+  if (p == gridDim.x - 1 && threadIdx.x == 0) blockpre[nb] = (uint32_t)(base + chunk_total);
+  for (uint32_t t0 = begin; t0 < end; t0 += kBlock) {
+    const uint32_t i = t0 + threadIdx.x;
+    const uint32_t v = i < end ? __ldg(blocksum + i) : 0u;
+    uint32_t tile_total;
+    const uint32_t excl = block_excl_scan(v, sm.warp, &tile_total);
+    if (i < end) blockpre[i] = (uint32_t)base + excl;
+    base += tile_total;
+  }
+  chain_finish(ws, &sm.chain);
+}
+
+// keys_out / order in ascending seed id; rows that produce nothing go behind the live ones (their order among
+// themselves is irrelevant: EMPTY keys draw and emit nothing)
+__global__ void __launch_bounds__(kBlock)
+rank_place_kernel(const uint32_t *__restrict__ keys_in, uint32_t n_max, const uint32_t *__restrict__ bitmap,
+                  const uint32_t *__restrict__ blockpre, uint32_t nb, uint32_t *counters,
+                  uint32_t *__restrict__ keys_out, uint32_t *__restrict__ order) {
+  const uint32_t live_total = __ldg(blockpre + nb);
+  for (uint32_t i = blockIdx.x * kBlock + threadIdx.x; i < n_max; i += gridDim.x * kBlock) {
+    const uint32_t v = __ldg(keys_in + i);
+    uint32_t r;
+    if (v != kEmpty) {
+      const uint32_t w = v >> 5, w0 = w & ~31u;
+      r = __ldg(blockpre + (v >> 10));
+      for (uint32_t q = w0; q < w; ++q) r += __popc(__ldg(bitmap + q));
+      r += __popc(__ldg(bitmap + w) & ((1u << (v & 31u)) - 1u));
+    } else {
+      r = live_total + atomicAdd(counters, 1u);
+    }
+    keys_out[r] = v;
+    order[r] = i;
+  }
+}
+
+// restore the all-zero invariant of the rank workspace
+__global__ void __launch_bounds__(kBlock)
+rank_clear_kernel(const uint32_t *__restrict__ keys_in, uint32_t n_max, uint32_t *bitmap, uint32_t *blocksum,
+                  uint32_t *counters) {
+  if (blockIdx.x == 0 && threadIdx.x == 0) counters[0] = 0u;
+  for (uint32_t i = blockIdx.x * kBlock + threadIdx.x; i < n_max; i += gridDim.x * kBlock) {
+    const uint32_t v = __ldg(keys_in + i);
+    if (v != kEmpty) {
+      bitmap[v >> 5] = 0u;
+      blocksum[v >> 10] = 0u;
+    }
   }
 }
 
@@ -286,6 +385,13 @@ extern "C" size_t fgnn_k_sample_replace_workspace_bytes(uint32_t n_max, uint32_t
   return carve(&w, nullptr, n_max ? n_max : 1, fanout ? fanout : 1);
 }
 
+// rank workspace for graphs of up to 2^29 vertices (64 MB bitmap); larger id spaces use the CUB sort
+extern "C" size_t fgnn_k_seed_rank_workspace_bytes(size_t num_nodes) {
+  if (num_nodes == 0 || num_nodes > ((size_t)1 << 29)) return 0;
+  RankWs w;
+  return carve_rank(&w, nullptr, num_nodes);
+}
+
 extern "C" int fgnn_k_sample_replace(int kind, const uint32_t *indptr, const uint32_t *indices,
                                      const float *prob_table, const uint32_t *alias_table,
                                      const float *prob_prefix_table, const uint32_t *input,
@@ -293,6 +399,19 @@ extern "C" int fgnn_k_sample_replace(int kind, const uint32_t *indptr, const uin
                                      uint32_t *out_src, uint32_t *out_dst, uint32_t *out_src_local,
                                      uint32_t *d_num_out, void *workspace, size_t workspace_bytes,
                                      void *chain_ws, fgnn_stream_t stream) {
+  return fgnn_k_sample_replace_ranked(kind, indptr, indices, prob_table, alias_table, prob_prefix_table, input, n_max,
+                                      d_n, fanout, rng, out_src, out_dst, out_src_local, d_num_out, workspace,
+                                      workspace_bytes, chain_ws, nullptr, 0, stream);
+}
+
+extern "C" int fgnn_k_sample_replace_ranked(int kind, const uint32_t *indptr, const uint32_t *indices,
+                                            const float *prob_table, const uint32_t *alias_table,
+                                            const float *prob_prefix_table, const uint32_t *input,
+                                            uint32_t n_max, const uint32_t *d_n, uint32_t fanout, fgnn_rng rng,
+                                            uint32_t *out_src, uint32_t *out_dst, uint32_t *out_src_local,
+                                            uint32_t *d_num_out, void *workspace, size_t workspace_bytes,
+                                            void *chain_ws, void *rank_ws, size_t num_nodes,
+                                            fgnn_stream_t stream) {
   if (!indptr || !indices || !out_dst || !d_num_out || !chain_ws) return FGNN_ERR_BAD_ARG;
   if (kind != 1 && kind != 2 && kind != 4) return FGNN_ERR_BAD_ARG;
   if (kind == 2 && (!prob_table || !alias_table)) return FGNN_ERR_BAD_ARG;
@@ -307,11 +426,25 @@ extern "C" int fgnn_k_sample_replace(int kind, const uint32_t *indptr, const uin
   carve(&w, workspace, n_max, fanout);
   const RngKey key = make_rng_key(rng);
 
-  replace_keys_kernel<<<persistent_grid(n_max, kBlock, 8, false), kBlock, 0, st>>>(
-      indptr, input, n_max, d_n, w.keys_in, w.vals_in);
-  cudaError_t e = cub::DeviceRadixSort::SortPairs(w.cub_temp, w.cub_bytes, w.keys_in, w.keys_out,
-                                                  w.vals_in, w.vals_out, (int64_t)n_max, 0, 32, st);
-  if (e != cudaSuccess) return (int)e;
+  const bool ranked = rank_ws != nullptr && fgnn_k_seed_rank_workspace_bytes(num_nodes) != 0;
+  if (ranked) {
+    RankWs rw;
+    carve_rank(&rw, rank_ws, num_nodes);
+    const int g1 = persistent_grid(n_max, kBlock, 8, false);
+    replace_keys_kernel<<<g1, kBlock, 0, st>>>(indptr, input, n_max, d_n, w.keys_in, w.vals_in, rw.bitmap, rw.blocksum);
+    rank_scan_kernel<<<persistent_grid(rw.nb, kBlock * 8, 4, true), kBlock, 0, st>>>(rw.blocksum, rw.blockpre, rw.nb,
+                                                                                    (ChainWs *)chain_ws);
+    rank_place_kernel<<<g1, kBlock, 0, st>>>(w.keys_in, n_max, rw.bitmap, rw.blockpre, rw.nb, rw.counters, w.keys_out,
+                                             w.vals_out);
+    rank_clear_kernel<<<g1, kBlock, 0, st>>>(w.keys_in, n_max, rw.bitmap, rw.blocksum, rw.counters);
+    note_launch(3);
+  } else {
+    replace_keys_kernel<<<persistent_grid(n_max, kBlock, 8, false), kBlock, 0, st>>>(
+        indptr, input, n_max, d_n, w.keys_in, w.vals_in, nullptr, nullptr);
+    cudaError_t e = cub::DeviceRadixSort::SortPairs(w.cub_temp, w.cub_bytes, w.keys_in, w.keys_out,
+                                                    w.vals_in, w.vals_out, (int64_t)n_max, 0, 32, st);
+    if (e != cudaSuccess) return (int)e;
+  }
   const uint64_t total = (uint64_t)n_max * fanout;
   const int g = persistent_grid(total, kBlock, 8, false);
   if (kind == 1)

@@ -197,7 +197,7 @@ struct SampleSlot {
   cudaEvent_t done = nullptr;   // counts are on the host
   cudaEvent_t idle = nullptr;   // scratch marker used by Reshuffle
   cudaEvent_t begin = nullptr;  // FGNN_TRACE_GPU=1: device-side start of the batch
-  TensorPtr table, num_items, chain, ws;
+  TensorPtr table, num_items, chain, ws, rank_ws;
   uint32_t *counts_dev = nullptr, *counts_host = nullptr;  // views of the sampler's contiguous count arrays
   std::vector<TensorPtr> dst, pos;   // scratch: sampled global ids, their bucket positions
   uint32_t ver_state = 0;            // versioned table reset (fgnn_k_ht_next_version)
@@ -340,6 +340,15 @@ Sampler::Sampler(const Dataset *ds, Context ctx, int worker_id, int num_worker, 
     sl.counts_dev = (uint32_t *)counts_dev_->data + si * cw;
     sl.counts_host = (uint32_t *)counts_host_->data + si * cw;
     sl.ws = Tensor::Device(kU8, {ws_bytes}, dev_, sl.stream, "sample_ws");
+    if ((rc_.sample_type == kKHop1 || rc_.sample_type == kWeightedKHop || rc_.sample_type == kWeightedKHopPrefix) &&
+        GetEnv("FGNN_SEED_RANK") != "0") {
+      // seeds ordered by id with a rank-by-bitmap (sample_replace.cu) instead of a library radix sort
+      const size_t rb = fgnn_k_seed_rank_workspace_bytes(ds->num_node);
+      if (rb) {
+        sl.rank_ws = Tensor::Device(kU8, {rb}, dev_, sl.stream, "seed_rank_ws");
+        CUDA_CALL(cudaMemsetAsync(sl.rank_ws->data, 0, rb, sl.stream));
+      }
+    }
     for (size_t i = 0; i < L_; ++i) {
       sl.dst.push_back(Tensor::Device(kI32, {edge_max_[i] + 1}, dev_, sl.stream, "scratch_dst"));
       sl.pos.push_back(Tensor::Device(kI32, {edge_max_[i] + 1}, dev_, sl.stream, "scratch_pos"));
@@ -482,6 +491,8 @@ void Sampler::EnqueueGroup(const std::vector<TaskPtr> &group) {
     p.chain_ws = sl.chain->data;
     p.workspace = sl.ws->data;
     p.workspace_bytes = sl.ws->nbytes;
+    p.rank_ws = sl.rank_ws ? sl.rank_ws->data : nullptr;
+    p.num_nodes = sl.rank_ws ? (uint32_t)ds_->num_node : 0u;
     p.version = versioned ? fgnn_k_ht_next_version(&sl.ver_state, p.table, ht_cap_, st) : 0u;
     fgnn_sample_out &o = so[k];
     o.n2o = blk->n2o;

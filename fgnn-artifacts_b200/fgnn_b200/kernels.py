@@ -35,7 +35,8 @@ class SamplePlan(C.Structure):
                 ("num_walk", C.c_uint32), ("restart_prob", C.c_double), ("seed", C.c_uint64),
                 ("table", C.c_void_p), ("capacity", C.c_size_t), ("num_items", C.c_void_p),
                 ("chain_ws", C.c_void_p), ("workspace", C.c_void_p), ("workspace_bytes", C.c_size_t),
-                ("dst", _P8), ("pos", _P8), ("version", C.c_uint32)]
+                ("dst", _P8), ("pos", _P8), ("version", C.c_uint32), ("num_nodes", C.c_uint32),
+                ("rank_ws", C.c_void_p)]
 
 
 class SampleOut(C.Structure):
@@ -63,6 +64,8 @@ _SIGS = {
     "fgnn_k_sample_khop": [C.c_int, _vp, _vp, _vp, _u32, _vp, _u32, FgnnRng, _vp, _vp, _vp, _vp, _vp, _vp],
     "fgnn_k_sample_replace": [C.c_int, _vp, _vp, _vp, _vp, _vp, _vp, _u32, _vp, _u32, FgnnRng, _vp, _vp, _vp,
                               _vp, _vp, _sz, _vp, _vp],
+    "fgnn_k_sample_replace_ranked": [C.c_int, _vp, _vp, _vp, _vp, _vp, _vp, _u32, _vp, _u32, FgnnRng, _vp, _vp, _vp,
+                                     _vp, _vp, _sz, _vp, _vp, _sz, _vp],
     "fgnn_k_sample_weighted_hash_dedup": [_vp, _vp, _vp, _vp, _vp, _u32, _vp, _u32, FgnnRng, _vp, _vp, _vp, _vp,
                                           _vp, _vp],
     "fgnn_k_sample_random_walk": [_vp, _vp, _vp, _u32, _vp, _u32, C.c_double, _u32, _u32, FgnnRng, _vp, _vp,
@@ -102,6 +105,7 @@ _SIZE_FNS = {
     "fgnn_k_ht_capacity": [_sz],
     "fgnn_k_ht_bytes": [_sz],
     "fgnn_k_sample_replace_workspace_bytes": [_u32, _u32],
+    "fgnn_k_seed_rank_workspace_bytes": [_sz],
     "fgnn_k_sample_random_walk_workspace_bytes": [_u32, _u32],
     "fgnn_k_presc_rank_workspace_bytes": [_sz],
     "fgnn_k_shuffle_workspace_bytes": [_sz],
@@ -189,12 +193,25 @@ def sample_replace_workspace_bytes(n_max, fanout):
     return int(load().fgnn_k_sample_replace_workspace_bytes(n_max, fanout))
 
 
+def seed_rank_workspace_bytes(num_nodes):
+    return int(load().fgnn_k_seed_rank_workspace_bytes(num_nodes))
+
+
+def new_rank_ws(num_nodes, device="cuda"):
+    """Zero-initialised workspace of the rank-by-bitmap seed ordering (None when the id space is too large)."""
+    nb = seed_rank_workspace_bytes(num_nodes)
+    return torch.zeros(nb, dtype=torch.uint8, device=device) if nb else None
+
+
 def sample_replace(kind, indptr, indices, prob, alias, prefix, inp, n_max, d_n, fanout, r, out_src, out_dst,
-                   out_src_local, d_num_out, workspace, chain_ws):
-    _check(load().fgnn_k_sample_replace(kind, _ptr(indptr), _ptr(indices), _ptr(prob), _ptr(alias), _ptr(prefix),
-                                        _ptr(inp), n_max, _ptr(d_n), fanout, r, _ptr(out_src), _ptr(out_dst),
-                                        _ptr(out_src_local), _ptr(d_num_out), _ptr(workspace),
-                                        workspace.numel() * workspace.element_size(), _ptr(chain_ws), _stream()),
+                   out_src_local, d_num_out, workspace, chain_ws, rank_ws=None, num_nodes=0):
+    """khop1 / weighted alias / prefix sampler; with `rank_ws` (new_rank_ws) the seeds are ordered by the
+    rank-by-bitmap kernels instead of a radix sort."""
+    _check(load().fgnn_k_sample_replace_ranked(kind, _ptr(indptr), _ptr(indices), _ptr(prob), _ptr(alias), _ptr(prefix),
+                                               _ptr(inp), n_max, _ptr(d_n), fanout, r, _ptr(out_src), _ptr(out_dst),
+                                               _ptr(out_src_local), _ptr(d_num_out), _ptr(workspace),
+                                               workspace.numel() * workspace.element_size(), _ptr(chain_ws),
+                                               _ptr(rank_ws), num_nodes if rank_ws is not None else 0, _stream()),
            "sample_replace")
 
 

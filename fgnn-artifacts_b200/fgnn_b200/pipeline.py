@@ -48,9 +48,12 @@ class Slot:
         # counts[l] = (num_dst, num_edge, num_src) of layer l
         self.counts = torch.zeros((L, 3), **i32)
         self.ws = None
+        self.rank_ws = None
         if hp.sample_type in ("khop1", "weighted_khop", "weighted_khop_prefix"):
             nb = max(K.sample_replace_workspace_bytes(hp.in_max[i], hp.fanouts[i]) for i in range(L))
             self.ws = torch.empty(nb, dtype=torch.uint8, device=hp.dev)
+            if hp.rank_by_bitmap:
+                self.rank_ws = K.new_rank_ws(hp.num_nodes, hp.dev)
         elif hp.sample_type == "random_walk":
             nb = max(K.sample_random_walk_workspace_bytes(hp.in_max[i], hp.fanouts[i]) for i in range(L))
             self.ws = torch.empty(nb, dtype=torch.uint8, device=hp.dev)
@@ -74,6 +77,8 @@ class Slot:
         pl.num_items, pl.chain_ws = self.num_items.data_ptr(), self.chain.data_ptr()
         pl.workspace = self.ws.data_ptr() if self.ws is not None else None
         pl.workspace_bytes = self.ws.numel() if self.ws is not None else 0
+        pl.num_nodes = hp.num_nodes if self.rank_ws is not None else 0
+        pl.rank_ws = self.rank_ws.data_ptr() if self.rank_ws is not None else None
         out = K.SampleOut()
         out.n2o, out.counts = self.n2o.data_ptr(), self.counts.data_ptr()
         for i in range(L):
@@ -110,6 +115,7 @@ class HotPath:
         self.cap = ht_capacity if ht_capacity else K.ht_capacity(self.max_nodes)
         import os
         self.versioned = os.environ.get("FGNN_HT_VERSIONED", "1") != "0"
+        self.rank_by_bitmap = os.environ.get("FGNN_SEED_RANK", "1") != "0"     # 0: order the seeds with the CUB sort
         self.slots = [Slot(self) for _ in range(max(1, num_slots))]
         self._alias_slot(0)
         # cache state (set by build_cache)

@@ -99,6 +99,21 @@ int fgnn_k_sample_replace(int kind, const uint32_t *indptr,
                           uint32_t *out_src_local, uint32_t *d_num_out,
                           void *workspace, size_t workspace_bytes,
                           void *chain_ws, fgnn_stream_t stream);
+/* The same sampler with the seeds ordered by a rank-by-bitmap instead of a radix sort (the seeds of a layer are
+ * unique: rank(v) = number of seeds below v = popcount of a V-bit seed bitmap below bit v).  `rank_ws` holds
+ * fgnn_k_seed_rank_workspace_bytes(num_nodes) bytes that must be ZERO before the first call; every call leaves
+ * them zero again.  rank_ws == NULL, num_nodes == 0 or num_nodes > 2^29 select the sort. */
+size_t fgnn_k_seed_rank_workspace_bytes(size_t num_nodes);
+int fgnn_k_sample_replace_ranked(int kind, const uint32_t *indptr,
+                                 const uint32_t *indices, const float *prob_table,
+                                 const uint32_t *alias_table,
+                                 const float *prob_prefix_table, const uint32_t *input,
+                                 uint32_t n_max, const uint32_t *d_n, uint32_t fanout,
+                                 fgnn_rng rng, uint32_t *out_src, uint32_t *out_dst,
+                                 uint32_t *out_src_local, uint32_t *d_num_out,
+                                 void *workspace, size_t workspace_bytes,
+                                 void *chain_ws, void *rank_ws, size_t num_nodes,
+                                 fgnn_stream_t stream);
 
 /* GPUSampleWeightedKHopHashDedup (cuda_sampling_weighted_khop_hash_dedup.cu:
  * 203-279): alias sampling with rejection until `fanout` distinct; seed-major
@@ -211,6 +226,10 @@ typedef struct fgnn_sample_plan {
    * (fgnn_k_ht_next_version hands out the tags and clears the table when they wrap), and the uniform k-hop
    * chain then never touches the buckets it does not use.  Honoured by sample_type khop2; other samplers clear. */
   uint32_t version;
+  /* khop1 / weighted samplers: zero-initialised fgnn_k_seed_rank_workspace_bytes(num_nodes) bytes (or NULL: the
+   * seeds are ordered by a library radix sort instead of the rank-by-bitmap) */
+  uint32_t num_nodes;
+  void *rank_ws;
 } fgnn_sample_plan;
 typedef struct fgnn_sample_out {
   uint32_t *n2o;

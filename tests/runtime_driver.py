@@ -95,7 +95,7 @@ def run_arch5(sc, out_path):
                 sam.sample_once()
                 key = sam.get_next_batch()
                 keys.append(key)
-                collect(sam, key, L, out, "b", False)
+                collect(sam, key, L, out, "b", cfg["_sample_type"] == sam.kRandomWalk)
         out["keys"] = np.array(keys, dtype=np.uint64)
         np.savez(out_path + ".t%d.npz" % wid, **out)
         barrier.wait()

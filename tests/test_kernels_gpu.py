@@ -465,9 +465,15 @@ def weight_tables(oracle, indptr, indices, seed=2):
 
 
 @pytest.mark.parametrize("kind", [1, 2, 4])
+@pytest.mark.parametrize("ranked", [True, False])
 @pytest.mark.parametrize("n,fanout,unique", [(0, 5, True), (1, 10, True), (700, 10, True), (2500, 25, True),
                                              (500, 7, False)])
-def test_sample_replace_matches_oracle(K, oracle, gs, kind, n, fanout, unique):
+def test_sample_replace_matches_oracle(K, oracle, gs, kind, n, fanout, unique, ranked):
+    """ranked = the seeds are ordered by the rank-by-bitmap kernels (default in the engine), else by the CUB sort;
+    the rank workspace must come back all-zero.  Duplicate seeds (unique=False) are outside the bitmap's contract
+    (a layer's inputs are unique): they only run on the sort path."""
+    if ranked and not unique:
+        pytest.skip("rank-by-bitmap needs unique seeds (always true for a layer's inputs)")
     prob, alias, prefix = weight_tables(oracle, gs.indptr_np, gs.indices_np)
     seeds = pick_seeds(gs.indptr_np, n, 4, unique)
     n_max = n + 13
@@ -479,9 +485,17 @@ def test_sample_replace_matches_oracle(K, oracle, gs, kind, n, fanout, unique):
     wsb = torch.empty(K.sample_replace_workspace_bytes(n_max, fanout), dtype=torch.uint8, device="cuda")
     ws = K.new_chain_ws()
     fprob, falias, fprefix = (torch.from_numpy(prob).cuda(), dev(alias), torch.from_numpy(prefix).cuda())
-    K.sample_replace(kind, gs.indptr, gs.indices, fprob, falias, fprefix, inp, n_max, dn, fanout,
-                     K.rng(SEED, 9, 2), outs[0], outs[1], outs[2], num, wsb, ws)
-    torch.cuda.synchronize()
+    V = len(gs.indptr_np) - 1
+    rank_ws = K.new_rank_ws(V) if ranked else None
+    for rep in range(2 if ranked else 1):      # twice: the first call must leave the rank workspace clean
+        K.sample_replace(kind, gs.indptr, gs.indices, fprob, falias, fprefix, inp, n_max, dn, fanout,
+                         K.rng(SEED, 9, 2), outs[0], outs[1], outs[2], num, wsb, ws, rank_ws=rank_ws, num_nodes=V)
+        torch.cuda.synchronize()
+    if ranked:
+        words = (V + 31) // 32
+        nbk = (V + 1023) // 1024
+        al = lambda x: (x + 255) & ~255
+        assert int(rank_ws[:al(words * 4) + al((nbk + 1) * 4) + 256].to(torch.int64).sum().item()) == 0
     m = int(num.item())
     if kind == 1:
         es, ed = oracle.sample_khop1(gs.indptr_np, gs.indices_np, seeds, fanout, SEED, 9, 2)
