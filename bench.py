@@ -583,6 +583,20 @@ def run_ours(args):
                     "nvlink_peak_GBps": 900.0, "cache_hit_rate": rp["hits"] / max(1, rp["hits"] + rp["misses"]),
                     "extract_GBps_per_gpu": rp["n_in_total"] * row_bytes / (rp["gather_ms"] * 1e-3) / 1e9,
                     "edges": p_edges, "ms_total": p_ms, "raw": rp}
+        if args.only_partition:
+            # diagnosis sweep: replicated head size x how peer rows are fetched (bulk engine / warp loads)
+            os.environ["FGNN_TUNING_DYNAMIC"] = "1"
+            diag = []
+            for rp, ldg in ((0.25, 0), (0.25, 1), (0.0, 0), (0.0, 1), (0.6, 0), (0.6, 1)):
+                os.environ["FGNN_BULK_PEER_LDG"] = str(ldg)
+                d = part_leg(rp, 5_000_000 + int(rp * 100) * 10 + ldg)
+                diag.append({"replicate_pct": rp, "peer_ldg": ldg, "ms_per_step": round(d["ms_per_step"], 4),
+                             "gather_ms_per_step": round(d["gather_ms_per_step"], 4),
+                             "remote_row_fraction": round(d["remote_row_fraction"], 4),
+                             "nvlink_GBps": round(d["nvlink_peer_GBps_per_gpu"] or 0, 1)})
+                if rank == 0:
+                    print("PARTITION_DIAG " + json.dumps(diag[-1]), file=sys.stderr, flush=True)
+            os.environ.pop("FGNN_BULK_PEER_LDG", None)
         part = part_leg(args.replicate_pct, 3_000_000)
         part["note"] = ("cache partitioned over the %d GPUs: the hottest %.0f%% of the vertices (PreSC ranks) on every "
                         "GPU, the rest striped (slot %% N) and read by NVLink peer loads inside fgnn_k_gather_cached_layout; "
@@ -785,10 +799,11 @@ def run_factored(args, wl, world, rank, path):
                 if line.startswith("FACTORED_JSON "):
                     return json.loads(line[len("FACTORED_JSON "):])
             err = r.stderr.strip()
-            keep = [l for l in err.splitlines() if "Error" in l or "error" in l or "what():" in l][:12]
+            sys.stderr.write("---- %s leg stderr (tail) ----\n%s\n" % (tag, err[-6000:]))     # for the run's log
+            keep = [l for l in err.splitlines() if "Error" in l or "error" in l or "what():" in l or "File " in l][:16]
             return {"error": "%s leg failed: %s || %s" % (tag, " | ".join(keep)[:1500], err[-400:])}
         f = one(["--no-train", "--num-epoch", "4"], "e2e_factored")
-        e = one(["--num-epoch", "3"], "epoch")
+        e = one(["--num-epoch", "3", "--timeout", "120"], "epoch")
         ddp_error = None
         if "error" in e and T > 1:
             # the measured epoch must not depend on the gradient all-reduce coming up: retry without DDP and say so

@@ -32,6 +32,9 @@ def parse(argv=None):
     ap.add_argument("--num-sample-worker", type=int, default=1)
     ap.add_argument("--num-train-worker", type=int, default=1)
     ap.add_argument("--single-gpu", action="store_true", help="samplers and trainers all on cuda:0")
+    ap.add_argument("--sampler-device", default=None,
+                    help="put every sampler on this device (e.g. cuda:0) instead of cuda:T.. : lets a box with T GPUs "
+                         "run T trainers with DDP plus a sampler that shares a trainer's GPU")
     ap.add_argument("--sample-type", default="khop2")
     ap.add_argument("--fanout", nargs="+", type=int, default=[25, 10])
     ap.add_argument("--batch-size", type=int, default=8000)
@@ -71,8 +74,16 @@ def run_config(a, sam):
     return cfg
 
 
+def _dump_on_sigusr1():
+    """a hung worker prints its Python stacks when the parent gives up (SIGUSR1), before it is killed"""
+    import faulthandler
+    import signal
+    faulthandler.register(signal.SIGUSR1, all_threads=True)
+
+
 def run_sample(worker_id, a, ctx, barrier, outdir):
     """train_graphsage.py:95-215"""
+    _dump_on_sigusr1()
     import samgraph.torch as sam
     sam.sample_init(worker_id, ctx)
     sam.notify_sampler_ready(barrier)
@@ -97,6 +108,7 @@ def run_sample(worker_id, a, ctx, barrier, outdir):
 
 def run_train(worker_id, a, ctx, barrier, outdir):
     """train_graphsage.py:217-437"""
+    _dump_on_sigusr1()
     import torch
     import samgraph.torch as sam
     T = a.num_train_worker
@@ -198,6 +210,8 @@ def main(argv=None):
     barrier = ctx.Barrier(S + T, timeout=a.timeout)
     t_ctx = ["cuda:0"] * T if a.single_gpu else ["cuda:%d" % i for i in range(T)]
     s_ctx = ["cuda:0"] * S if a.single_gpu else ["cuda:%d" % (T + i) for i in range(S)]
+    if a.sampler_device:
+        s_ctx = [a.sampler_device] * S
     outdir = tempfile.mkdtemp(prefix="fgnn_factored_")
     t_start = time.time()
     procs = [ctx.Process(target=run_sample, args=(i, a, s_ctx[i], barrier, outdir)) for i in range(S)] + \
@@ -209,7 +223,15 @@ def main(argv=None):
     # like sam.wait_one_child() in the reference's scripts: the first worker that dies takes the job down, the others
     # must not sit in a barrier until it times out
     while any(p.is_alive() for p in procs):
-        if any(p.exitcode not in (None, 0) for p in procs) or time.time() > deadline:
+        timed_out = time.time() > deadline
+        if any(p.exitcode not in (None, 0) for p in procs) or timed_out:
+            if timed_out:
+                import signal
+                print("train_graphsage_multi_gpu: timeout after %d s, worker stacks follow" % a.timeout, file=sys.stderr)
+                for p in procs:
+                    if p.is_alive():
+                        os.kill(p.pid, signal.SIGUSR1)
+                time.sleep(1.0)
             for p in procs:
                 if p.is_alive():
                     p.kill()

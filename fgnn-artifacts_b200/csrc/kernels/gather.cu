@@ -106,6 +106,9 @@ struct RowSrc {
   const char *replica;
   uint32_t num_replicated, self_shard;
   unsigned long long *d_remote;  // optional: rows read from peer shards
+  // optional deferred pass for peer rows: defer_cnt[0] = number of listed rows, entries {src pointer, dst row}
+  unsigned int *defer_cnt;
+  ulonglong2 *defer_list;
   __device__ __forceinline__ const char *resolve(uint32_t node, uint32_t slot) const {
     if (slot != kEmpty) {
       if (slot < num_replicated) return replica + (size_t)slot * row_bytes;
@@ -401,7 +404,13 @@ gather_bulk_kernel(char *__restrict__ out, const uint32_t *__restrict__ nodes, u
     const uint32_t bar = smem_u32(&s_bar[warp][s]);
     unsigned char *st = stage0 + (size_t)s * stage_bytes;
     const bool mine = (lane / G) == sub && node_i != kEmpty;
-    const bool by_bulk = mine && (slot_i != kEmpty ? !(peer_ldg && rs.is_remote(slot_i)) : !miss_by_ldg);
+    const bool remote_row = mine && rs.is_remote(slot_i);
+    const bool deferred = remote_row && rs.defer_list != nullptr;
+    if (deferred) {  // listed for the second pass (its slot of the stage is stored as is and overwritten later)
+      const unsigned int at = atomicAdd(rs.defer_cnt, 1u);
+      rs.defer_list[at] = make_ulonglong2((unsigned long long)sp, r0 + (uint64_t)(j / spg) * 32 + lane);
+    }
+    const bool by_bulk = mine && !deferred && (slot_i != kEmpty ? !(peer_ldg && remote_row) : !miss_by_ldg);
     const uint32_t nbulk = __popc(__ballot_sync(0xFFFFFFFFu, by_bulk));
     if (lane == 0) mbar_expect_tx(bar, nbulk * row_bytes);
     __syncwarp();
@@ -409,7 +418,7 @@ gather_bulk_kernel(char *__restrict__ out, const uint32_t *__restrict__ nodes, u
       if (hint) bulk_g2s(smem_u32(st + (size_t)(lane - sub * G) * row_bytes), sp, row_bytes, bar, pol);
       else bulk_g2s(smem_u32(st + (size_t)(lane - sub * G) * row_bytes), sp, row_bytes, bar);
     }
-    uint32_t ldg_rows = __ballot_sync(0xFFFFFFFFu, mine && !by_bulk);
+    uint32_t ldg_rows = __ballot_sync(0xFFFFFFFFu, mine && !by_bulk && !deferred);
     while (ldg_rows) {  // host-resident rows: warp-wide 16-byte loads into the stage
       const int r = __ffs(ldg_rows) - 1;
       ldg_rows &= ldg_rows - 1;
@@ -443,6 +452,40 @@ gather_bulk_kernel(char *__restrict__ out, const uint32_t *__restrict__ nodes, u
   rs.report(d_stats, hits, misses, remote);
 }
 
+
+// Second pass of the gather: the peer rows the main kernel listed, one warp per row, every row's loads in flight
+// at once (no ring, no in-order wait); the last CTA re-arms the list counter.
+__global__ void __launch_bounds__(kBlock)
+gather_deferred_kernel(char *__restrict__ out, unsigned int *cnt, const ulonglong2 *__restrict__ list,
+                       uint32_t row_bytes) {
+  const uint32_t n = *((volatile unsigned int *)cnt);
+  const uint32_t lane = threadIdx.x & 31;
+  const uint32_t W = gridDim.x * (kBlock / 32);
+  for (uint32_t i = blockIdx.x * (kBlock / 32) + (threadIdx.x >> 5); i < n; i += W) {
+    const ulonglong2 e = list[i];
+    const char *src = (const char *)e.x;
+    char *dst = out + (size_t)e.y * row_bytes;
+    for (uint32_t c0 = lane * 16u; c0 < row_bytes; c0 += 32u * 16u * 4u) {
+      uint4 v[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+        if (c0 + k * 512u < row_bytes) v[k] = ld_nc_na_v4(src + c0 + k * 512u);
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+        if (c0 + k * 512u < row_bytes) st_na_v4(dst + c0 + k * 512u, v[k]);
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    const unsigned int prev = atomicAdd(cnt + 1, 1u);
+    if (prev == gridDim.x - 1) {  // everybody has read the count
+      cnt[0] = 0u;
+      __threadfence();
+      cnt[1] = 0u;
+    }
+  }
+}
 
 inline int vec_width(size_t row_bytes, const void *a, const void *b, const void *c = nullptr) {
   const uintptr_t bits = (uintptr_t)row_bytes | (uintptr_t)a | (uintptr_t)b | (uintptr_t)c;
@@ -550,6 +593,8 @@ int launch_bulk(char *out, const uint32_t *nodes, uint32_t n_max, const uint32_t
 }  // namespace
 }  // namespace fgnn
 
+extern "C" size_t fgnn_k_gather_defer_workspace_bytes(uint32_t n_max) { return 256 + (size_t)n_max * sizeof(ulonglong2); }
+
 extern "C" int fgnn_k_gather_cached_layout(void *out, const uint32_t *nodes, uint32_t n_max,
                                            const uint32_t *d_n, const fgnn_cache_layout *lay,
                                            unsigned long long *d_stats, unsigned long long *d_remote,
@@ -577,6 +622,8 @@ extern "C" int fgnn_k_gather_cached_layout(void *out, const uint32_t *nodes, uin
   rs.num_replicated = lay->num_replicated;
   rs.self_shard = lay->self_shard;
   rs.d_remote = d_remote;
+  rs.defer_cnt = nullptr;
+  rs.defer_list = nullptr;
   const uint32_t *table = lay->table;
   int rc = 0;
   bool done = false;
@@ -590,9 +637,21 @@ extern "C" int fgnn_k_gather_cached_layout(void *out, const uint32_t *nodes, uin
     int stages = tn.stages >= 6 ? 6 : 3;
     if ((size_t)kBulkWarps * stages * stage_bytes > kSmemBudget) stages = 3;
     if ((size_t)kBulkWarps * stages * stage_bytes <= kSmemBudget) {
+      const bool defer = lay->defer_ws != nullptr && lay->num_shards > 1 && env_int("FGNN_GATHER_DEFER", 1) != 0;
+      if (defer) {
+        rs.defer_cnt = (unsigned int *)lay->defer_ws;
+        rs.defer_list = (ulonglong2 *)((char *)lay->defer_ws + 256);
+      }
       rc = stages == 6 ? launch_bulk<6>((char *)out, nodes, n_max, d_n, table, rs, G, stage_bytes, d_stats, st)
                        : launch_bulk<3>((char *)out, nodes, n_max, d_n, table, rs, G, stage_bytes, d_stats, st);
       if (rc) return rc;
+      if (defer) {
+        note_launch();
+        gather_deferred_kernel<<<sm_count() * 4, kBlock, 0, st>>>((char *)out, rs.defer_cnt, rs.defer_list,
+                                                                  (uint32_t)row_bytes);
+        rs.defer_cnt = nullptr;
+        rs.defer_list = nullptr;
+      }
       done = true;
     }
   }

@@ -586,7 +586,7 @@ class Extractor {
   uint64_t feat_mask_ = ~0ull;
   const void *feat_src_ = nullptr;     // pinned / registered host feature table (UVA)
   bool feat_registered_ = false;
-  TensorPtr feat_pinned_, label_dev_, cache_table_, shard_ptrs_, stats_, stats_host_;
+  TensorPtr feat_pinned_, label_dev_, cache_table_, shard_ptrs_, stats_, stats_host_, defer_ws_;
   unsigned long long last_stats_[2] = {0, 0};
   uint64_t enq_seq_ = 0;
   void *shard_ = nullptr;              // this GPU's stripe of the cache rows (cudaMalloc: IPC exportable)
@@ -730,6 +730,14 @@ Extractor::Extractor(const Dataset *ds, Context ctx, const IdType *ranking_host,
   layout_.miss_src = feat_src_;
   layout_.miss_mask = feat_mask_;
   layout_.row_bytes = row_bytes_;
+  if (num_shards > 1) {  // peer rows in a second pass (fgnn_cache_layout.defer_ws)
+    const size_t bound = PredictNumNodes(rc_.batch_size, rc_.fanout, rc_.fanout.size());
+    const size_t nb = fgnn_k_gather_defer_workspace_bytes((uint32_t)std::min<size_t>(bound, 0xFFFFFFFFu));
+    defer_ws_ = Tensor::Device(kU8, {nb}, dev_, stream_, "gather_defer_ws");
+    CUDA_CALL(cudaMemsetAsync(defer_ws_->data, 0, 256, stream_));
+    CUDA_CALL(cudaStreamSynchronize(stream_));
+    layout_.defer_ws = defer_ws_->data;
+  }
   FLOG(Info) << "GPU cache: " << num_cached_ << " / " << V << " nodes, " << num_replicated_ << " replicated, shard "
              << shard_id << "/" << num_shards << " holds " << local_rows << " rows ("
              << (local_rows * row_bytes_ >> 20) << " MiB)";

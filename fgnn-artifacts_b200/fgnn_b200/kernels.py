@@ -48,7 +48,7 @@ class CacheLayout(C.Structure):
     """fgnn_cache_layout (include/fgnn_kernels.h): replicated head + striped tail of the feature cache"""
     _fields_ = [("table", C.c_void_p), ("shards", C.c_void_p), ("num_shards", C.c_uint32), ("self_shard", C.c_uint32),
                 ("replica", C.c_void_p), ("num_replicated", C.c_uint32), ("miss_src", C.c_void_p),
-                ("miss_mask", C.c_uint64), ("row_bytes", C.c_size_t)]
+                ("miss_mask", C.c_uint64), ("row_bytes", C.c_size_t), ("defer_ws", C.c_void_p)]
 
 
 class KernelError(RuntimeError):
@@ -106,6 +106,7 @@ _SIZE_FNS = {
     "fgnn_k_ht_bytes": [_sz],
     "fgnn_k_sample_replace_workspace_bytes": [_u32, _u32],
     "fgnn_k_seed_rank_workspace_bytes": [_sz],
+    "fgnn_k_gather_defer_workspace_bytes": [_u32],
     "fgnn_k_sample_random_walk_workspace_bytes": [_u32, _u32],
     "fgnn_k_presc_rank_workspace_bytes": [_sz],
     "fgnn_k_shuffle_workspace_bytes": [_sz],

@@ -200,6 +200,12 @@ class HotPath:
         lay.num_shards, lay.self_shard = num_shards, shard_id
         lay.replica, lay.num_replicated = replica_ptr, self.num_replicated
         lay.miss_src, lay.miss_mask, lay.row_bytes = K._ptr(feat_src), feat_mask, row_bytes
+        # peer rows in a second pass (fgnn_cache_layout.defer_ws): needed once several GPUs gather at the same time
+        self.defer_ws = None
+        if num_shards > 1:
+            nb = int(K.load().fgnn_k_gather_defer_workspace_bytes(self.max_nodes))
+            self.defer_ws = torch.zeros(nb, dtype=torch.uint8, device=self.dev)
+            lay.defer_ws = self.defer_ws.data_ptr()
         self.layout = lay
         self.remote = torch.zeros(1, dtype=torch.int64, device=self.dev)
         if self.feat_out is None:

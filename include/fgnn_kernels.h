@@ -311,7 +311,15 @@ typedef struct fgnn_cache_layout {
   const void *miss_src;       /* pinned host feature table (UVA) */
   uint64_t miss_mask;
   size_t row_bytes;
+  /* Optional second pass for the rows of PEER stripes: with `defer_ws` (fgnn_k_gather_defer_workspace_bytes(n_max)
+   * bytes of device memory, zero before the first call) the main kernel does not wait for peer rows: it lists
+   * them, and a second launch on the same stream copies all listed rows at once, one warp per row.  Measured on
+   * 4 x B200: a peer row costs a warp of the pipelined ring 30-40 us when every GPU's HBM is saturated by its own
+   * gather, so a few % of peer rows tripled the kernel time (profiles/r2_partition_diag_n4.txt).  NULL = peer rows
+   * inside the ring (round 1 behaviour). */
+  void *defer_ws;
 } fgnn_cache_layout;
+size_t fgnn_k_gather_defer_workspace_bytes(uint32_t n_max);
 int fgnn_k_gather_cached_layout(void *out, const uint32_t *nodes, uint32_t n_max, const uint32_t *d_n,
                                 const fgnn_cache_layout *layout, unsigned long long *d_stats,
                                 unsigned long long *d_remote, fgnn_stream_t stream);

@@ -384,17 +384,19 @@ def test_gather_cached_impls_edge_cases(K, oracle, impl, row_bytes, n, n_max, pc
     assert stats.tolist() == [hit, n - hit]
 
 
-@pytest.mark.parametrize("impl", ["bulk", "group", "flat"])
+@pytest.mark.parametrize("impl", ["bulk", "bulk+defer", "group", "flat"])
 @pytest.mark.parametrize("row_bytes,shards,self_shard,pct,repl", [(512, 4, 1, 0.8, 0.2), (512, 2, 0, 1.0, 0.5),
                                                                  (1024, 8, 7, 0.6, 0.05), (400, 3, 2, 0.7, 0.3),
-                                                                 (512, 1, 0, 0.5, 0.5), (512, 4, 3, 0.3, 0.6)])
+                                                                 (512, 1, 0, 0.5, 0.5), (512, 4, 3, 0.3, 0.6),
+                                                                 (4096, 4, 0, 0.9, 0.0)])
 def test_gather_cached_hybrid_layout(K, oracle, impl, row_bytes, shards, self_shard, pct, repl, monkeypatch):
     """fgnn_k_gather_cached_layout: the hottest R slots in a local replica, slots >= R striped over `shards`
     buffers ((s-R) % T, (s-R) // T), misses from pinned host memory: bit-exact rows; the kernel's remote-row
     counter equals the number of gathered rows whose stripe owner is not `self_shard`."""
     from fgnn_b200 import partition as P
     monkeypatch.setenv("FGNN_TUNING_DYNAMIC", "1")
-    monkeypatch.setenv("FGNN_GATHER_IMPL", impl)
+    defer = impl == "bulk+defer"            # peer rows listed by the ring kernel and copied by a second launch
+    monkeypatch.setenv("FGNN_GATHER_IMPL", "bulk" if defer else impl)
     rng = np.random.default_rng(row_bytes + shards)
     V, n = 30000, 40001
     src = rng.integers(0, 256, size=(V, row_bytes), dtype=np.uint8)
@@ -421,9 +423,19 @@ def test_gather_cached_hybrid_layout(K, oracle, impl, row_bytes, shards, self_sh
     out = torch.zeros((n, row_bytes), dtype=torch.uint8, device="cuda")
     stats = torch.zeros(2, dtype=torch.int64, device="cuda")
     remote = torch.zeros(1, dtype=torch.int64, device="cuda")
-    K.gather_cached_layout(out, d_nodes, n, None, lay, stats, remote)
-    torch.cuda.synchronize()
-    assert np.array_equal(out.cpu().numpy(), src[nodes])
+    dws = None
+    if defer:
+        dws = torch.zeros(int(K.load().fgnn_k_gather_defer_workspace_bytes(n)), dtype=torch.uint8, device="cuda")
+        lay.defer_ws = dws.data_ptr()
+    for rep in range(2 if defer else 1):     # twice: the list counter must be re-armed by the second pass
+        out.zero_()
+        stats.zero_()
+        remote.zero_()
+        K.gather_cached_layout(out, d_nodes, n, None, lay, stats, remote)
+        torch.cuda.synchronize()
+        assert np.array_equal(out.cpu().numpy(), src[nodes])
+    if defer:
+        assert int(dws[:8].sum().item()) == 0
     slots = table_ref[nodes]
     hit = slots != 0xFFFFFFFF
     assert stats.tolist() == [int(hit.sum()), int((~hit).sum())]
