@@ -587,16 +587,16 @@ def run_ours(args):
             # diagnosis sweep: replicated head size x how peer rows are fetched (bulk engine / warp loads)
             os.environ["FGNN_TUNING_DYNAMIC"] = "1"
             diag = []
-            for rp, ldg in ((0.25, 0), (0.25, 1), (0.0, 0), (0.0, 1), (0.6, 0), (0.6, 1)):
-                os.environ["FGNN_BULK_PEER_LDG"] = str(ldg)
-                d = part_leg(rp, 5_000_000 + int(rp * 100) * 10 + ldg)
-                diag.append({"replicate_pct": rp, "peer_ldg": ldg, "ms_per_step": round(d["ms_per_step"], 4),
+            for rp, dfr in ((0.25, 1), (0.25, 0), (0.1, 1), (0.1, 0), (0.0, 1)):
+                os.environ["FGNN_GATHER_DEFER"] = str(dfr)
+                d = part_leg(rp, 5_000_000 + int(rp * 100) * 10 + dfr)
+                diag.append({"replicate_pct": rp, "deferred_peer_pass": dfr, "ms_per_step": round(d["ms_per_step"], 4),
                              "gather_ms_per_step": round(d["gather_ms_per_step"], 4),
                              "remote_row_fraction": round(d["remote_row_fraction"], 4),
                              "nvlink_GBps": round(d["nvlink_peer_GBps_per_gpu"] or 0, 1)})
                 if rank == 0:
                     print("PARTITION_DIAG " + json.dumps(diag[-1]), file=sys.stderr, flush=True)
-            os.environ.pop("FGNN_BULK_PEER_LDG", None)
+            os.environ.pop("FGNN_GATHER_DEFER", None)
         part = part_leg(args.replicate_pct, 3_000_000)
         part["note"] = ("cache partitioned over the %d GPUs: the hottest %.0f%% of the vertices (PreSC ranks) on every "
                         "GPU, the rest striped (slot %% N) and read by NVLink peer loads inside fgnn_k_gather_cached_layout; "
@@ -783,9 +783,12 @@ def run_factored(args, wl, world, rank, path):
     res = None
     if rank == 0:
         env = dict(os.environ, SAMGRAPH_EMPTY_FEAT=str(args.empty_feat), SAMGRAPH_LOG_LEVEL="error")
-        for k in ("RANK", "WORLD_SIZE", "LOCAL_RANK", "MASTER_ADDR", "MASTER_PORT", "GROUP_RANK", "LOCAL_WORLD_SIZE",
-                  "TORCHELASTIC_RUN_ID", "ROLE_RANK", "ROLE_WORLD_SIZE"):
-            env.pop(k, None)
+        for k in list(env):
+            # the children are NOT torchrun workers: with TORCHELASTIC_USE_AGENT_STORE left set, their own
+            # init_process_group(tcp://...) connects as a client to an agent store that does not exist and hangs
+            if k in ("RANK", "WORLD_SIZE", "LOCAL_RANK", "MASTER_ADDR", "MASTER_PORT", "GROUP_RANK", "LOCAL_WORLD_SIZE",
+                     "ROLE_RANK", "ROLE_WORLD_SIZE", "GROUP_WORLD_SIZE", "ROLE_NAME") or k.startswith("TORCHELASTIC_"):
+                env.pop(k, None)
         base = [sys.executable, os.path.join(ROOT, "examples", "train_graphsage_multi_gpu.py"), "--dataset-path", path,
                 "--num-sample-worker", str(S), "--num-train-worker", str(T), "--sample-type", args.sample_type,
                 "--cache-percentage", str(E2E_CACHE_PCT), "--pipeline", "--json", "--fanout"] + \

@@ -122,6 +122,8 @@ def run_train(worker_id, a, ctx, barrier, outdir):
         import torch.nn as nn
         from train_graphsage_csc import SAGE, csc_blocks
         if T > 1 and not a.no_ddp:
+            for k in [k for k in os.environ if k.startswith("TORCHELASTIC_")]:
+                os.environ.pop(k)          # not a torchrun worker even when launched from one (agent store!)
             torch.distributed.init_process_group(backend="nccl", init_method="tcp://127.0.0.1:%d" % a.master_port,
                                                  world_size=T, rank=worker_id, device_id=dev)
         model = SAGE(sam.feat_dim(), a.num_hidden, sam.num_class(), L, a.dropout).to(dev)
@@ -182,7 +184,7 @@ def run_train(worker_id, a, ctx, barrier, outdir):
         ep_edges.append(edges)
         ep_rows.append(rows)
         ep_steps.append(steps)
-        losses.append(float(loss) if loss is not None else None)
+        losses.append(float(loss.detach()) if loss is not None else None)
         barrier.wait()                                     # epoch end
     barrier.wait()                                         # run end
     ge = sam.get_log_epoch_value

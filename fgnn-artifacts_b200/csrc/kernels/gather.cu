@@ -19,6 +19,8 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <algorithm>
+
 namespace fgnn {
 namespace {
 
@@ -453,27 +455,50 @@ gather_bulk_kernel(char *__restrict__ out, const uint32_t *__restrict__ nodes, u
 }
 
 
-// Second pass of the gather: the peer rows the main kernel listed, one warp per row, every row's loads in flight
-// at once (no ring, no in-order wait); the last CTA re-arms the list counter.
-__global__ void __launch_bounds__(kBlock)
+// Second pass of the gather: the peer rows the main kernel listed.  Every warp keeps kDeferStages rows in flight
+// through the bulk-copy engine (global -> shared -> global, one elected lane; 16-byte warp loads from a peer turn
+// into 16-byte NVLink reads and reach only ~30 GB/s, r2_partition_diag_n4.txt), so with ~4700 warps all listed
+// rows are in flight at once and the pass costs about one NVLink round trip.  The last CTA re-arms the counter.
+constexpr int kDeferStages = 8;
+constexpr int kDeferWarps = 8;
+
+__global__ void __launch_bounds__(kDeferWarps * 32)
 gather_deferred_kernel(char *__restrict__ out, unsigned int *cnt, const ulonglong2 *__restrict__ list,
                        uint32_t row_bytes) {
+  extern __shared__ __align__(128) unsigned char s_raw[];
+  __shared__ __align__(8) unsigned long long s_bar[kDeferWarps][kDeferStages];
   const uint32_t n = *((volatile unsigned int *)cnt);
-  const uint32_t lane = threadIdx.x & 31;
-  const uint32_t W = gridDim.x * (kBlock / 32);
-  for (uint32_t i = blockIdx.x * (kBlock / 32) + (threadIdx.x >> 5); i < n; i += W) {
-    const ulonglong2 e = list[i];
-    const char *src = (const char *)e.x;
-    char *dst = out + (size_t)e.y * row_bytes;
-    for (uint32_t c0 = lane * 16u; c0 < row_bytes; c0 += 32u * 16u * 4u) {
-      uint4 v[4];
+  const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const uint32_t W = gridDim.x * kDeferWarps, w = blockIdx.x * kDeferWarps + warp;
+  unsigned char *stage0 = s_raw + (size_t)warp * kDeferStages * row_bytes;
+  if (lane == 0) {
 #pragma unroll
-      for (int k = 0; k < 4; ++k)
-        if (c0 + k * 512u < row_bytes) v[k] = ld_nc_na_v4(src + c0 + k * 512u);
-#pragma unroll
-      for (int k = 0; k < 4; ++k)
-        if (c0 + k * 512u < row_bytes) st_na_v4(dst + c0 + k * 512u, v[k]);
+    for (int s = 0; s < kDeferStages; ++s) mbar_init(smem_u32(&s_bar[warp][s]), 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncwarp();
+  if (lane == 0 && w < n) {
+    const uint32_t total = (n - w + W - 1) / W;  // rows of this warp: w, w + W, ...
+    auto issue = [&](uint32_t k) {
+      const ulonglong2 e = list[w + (size_t)k * W];
+      const uint32_t s = k % kDeferStages;
+      const uint32_t bar = smem_u32(&s_bar[warp][s]);
+      mbar_expect_tx(bar, row_bytes);
+      bulk_g2s(smem_u32(stage0 + (size_t)s * row_bytes), (const void *)e.x, row_bytes, bar);
+    };
+    for (uint32_t k = 0; k < (uint32_t)kDeferStages - 1 && k < total; ++k) issue(k);
+    for (uint32_t k = 0; k < total; ++k) {
+      if (k + kDeferStages - 1 < total) {
+        bulk_wait_read<0>();  // the stage about to be refilled was stored at iteration k - 1
+        issue(k + kDeferStages - 1);
+      }
+      const uint32_t s = k % kDeferStages;
+      mbar_wait(smem_u32(&s_bar[warp][s]), (k / kDeferStages) & 1u);
+      const ulonglong2 e = list[w + (size_t)k * W];
+      bulk_s2g(out + (size_t)e.y * row_bytes, smem_u32(stage0 + (size_t)s * row_bytes), row_bytes);
+      bulk_commit();
     }
+    bulk_wait_read<0>();
   }
   __syncthreads();
   if (threadIdx.x == 0) {
@@ -637,7 +662,8 @@ extern "C" int fgnn_k_gather_cached_layout(void *out, const uint32_t *nodes, uin
     int stages = tn.stages >= 6 ? 6 : 3;
     if ((size_t)kBulkWarps * stages * stage_bytes > kSmemBudget) stages = 3;
     if ((size_t)kBulkWarps * stages * stage_bytes <= kSmemBudget) {
-      const bool defer = lay->defer_ws != nullptr && lay->num_shards > 1 && env_int("FGNN_GATHER_DEFER", 1) != 0;
+      const bool defer = lay->defer_ws != nullptr && lay->num_shards > 1 && env_int("FGNN_GATHER_DEFER", 0) != 0 &&
+                         (size_t)kDeferWarps * kDeferStages * row_bytes <= kSmemBudget;
       if (defer) {
         rs.defer_cnt = (unsigned int *)lay->defer_ws;
         rs.defer_list = (ulonglong2 *)((char *)lay->defer_ws + 256);
@@ -647,8 +673,12 @@ extern "C" int fgnn_k_gather_cached_layout(void *out, const uint32_t *nodes, uin
       if (rc) return rc;
       if (defer) {
         note_launch();
-        gather_deferred_kernel<<<sm_count() * 4, kBlock, 0, st>>>((char *)out, rs.defer_cnt, rs.defer_list,
-                                                                  (uint32_t)row_bytes);
+        const size_t dsm = (size_t)kDeferWarps * kDeferStages * row_bytes;
+        cudaError_t e2 = cudaFuncSetAttribute(gather_deferred_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dsm);
+        if (e2 != cudaSuccess) return (int)e2;
+        const int dgrid = sm_count() * (int)std::max<size_t>(1, std::min<size_t>(4, (200 * 1024) / dsm));
+        gather_deferred_kernel<<<dgrid, kDeferWarps * 32, dsm, st>>>((char *)out, rs.defer_cnt, rs.defer_list,
+                                                                    (uint32_t)row_bytes);
         rs.defer_cnt = nullptr;
         rs.defer_list = nullptr;
       }

@@ -397,6 +397,7 @@ def test_gather_cached_hybrid_layout(K, oracle, impl, row_bytes, shards, self_sh
     monkeypatch.setenv("FGNN_TUNING_DYNAMIC", "1")
     defer = impl == "bulk+defer"            # peer rows listed by the ring kernel and copied by a second launch
     monkeypatch.setenv("FGNN_GATHER_IMPL", "bulk" if defer else impl)
+    monkeypatch.setenv("FGNN_GATHER_DEFER", "1" if defer else "0")
     rng = np.random.default_rng(row_bytes + shards)
     V, n = 30000, 40001
     src = rng.integers(0, 256, size=(V, row_bytes), dtype=np.uint8)
