@@ -68,7 +68,7 @@ def parse():
                     help="diagnosis: N > 1, only the device-resident replicated + partitioned legs")
     ap.add_argument("--no-partition", action="store_true",
                     help="N > 1: skip the partitioned-cache legs (value is then the replicated-cache arm)")
-    ap.add_argument("--replicate-pct", type=float, default=float(os.environ.get("FGNN_BENCH_REPLICATE_PCT", "0.25")),
+    ap.add_argument("--replicate-pct", type=float, default=float(os.environ.get("FGNN_BENCH_REPLICATE_PCT", "0.75")),
                     help="N > 1, partitioned cache: fraction of the vertices (hottest PreSC ranks) that every GPU "
                          "keeps a copy of; the rest of the cache is striped over the GPUs and read by NVLink peer loads")
     return ap.parse_args()
@@ -566,7 +566,7 @@ def run_ours(args):
     # ---- N > 1: the same workload with the cache PARTITIONED over the ranks' GPUs (north_star).
     # hybrid: every GPU keeps the hottest --replicate-pct of the vertices, the tail of the cache is striped over the
     # GPUs and read by NVLink peer loads inside the gather kernel; striped: no replicated head (round 1's layout).
-    part = part_striped = None
+    part = part_striped = part_cap = None
     if world > 1 and not args.no_partition:
         def part_leg(replicate_pct, key0):
             hp.cache = None
@@ -604,7 +604,13 @@ def run_ours(args):
                         "own stripe and replica" % (world, args.replicate_pct * 100))
         if args.replicate_pct > 0:
             part_striped = part_leg(0.0, 4_000_000)
-            part_striped["note"] = "no replicated head: every cached row striped over the GPUs (round 1's layout)"
+            part_striped["note"] = ("no replicated head: every cached row striped over the GPUs (round 1's layout); most "
+                                    "remote rows are HOT rows here, which the requesting GPU's L2 and the owner's L2 absorb")
+        if args.replicate_pct > 0.25:
+            part_cap = part_leg(0.25, 4_500_000)
+            part_cap["note"] = ("capacity-oriented point: only the hottest 25% replicated; the ~3% of rows that are then "
+                                "read from peers are COLD rows, which the fabric serves at a few tens of GB/s per GPU while "
+                                "every GPU's HBM is saturated by its own gather (profiles/r2_partition_diag_n4.txt)")
 
     replicated = None
     if part is not None:
@@ -617,9 +623,10 @@ def run_ours(args):
         edges, n_in_total = hr["edges"], hr["n_in_total"]
         sample_ms, gather_ms, hits, misses = hr["sample_ms"], hr["gather_ms"], hr["hits"], hr["misses"]
         launches, clk, cache_s, r = hr["launches"], hr["clk"], hr["cache_s"], hr
-        if part_striped is not None:
-            for k in ("raw", "ms_total", "edges"):
-                part_striped.pop(k)
+        for extra_leg in (part_striped, part_cap):
+            if extra_leg is not None:
+                for k in ("raw", "ms_total", "edges"):
+                    extra_leg.pop(k)
 
     # ---- roofline of the dominant kernel: the fused cache-aware feature gather -----------
     peak, peak_kind = peaks()
@@ -670,6 +677,8 @@ def run_ours(args):
         out["extra"]["replicated_cache"] = replicated
         if part_striped is not None:
             out["extra"]["partitioned_cache_striped"] = part_striped
+        if part_cap is not None:
+            out["extra"]["partitioned_cache_replicate25"] = part_cap
         out["notes"]["sharding"] = ("seed mini-batches split across ranks (no data-path collective); topology replicated; "
                                      "feature cache PARTITIONED over the GPUs for `value` (hottest %.0f%% of the vertices on "
                                      "every GPU, the rest striped and read by NVLink peer loads); PreSC ranking: NCCL "

@@ -118,7 +118,7 @@ struct RunConfig {
   bool partition_cache = false;
   // partitioned cache, hybrid layout: every trainer keeps the hottest replicate_percentage * V ranks, only the
   // rest of the cache is striped over the trainers (config key "replicate_percentage", env FGNN_REPLICATE_PCT)
-  double replicate_percentage = 0.25;
+  double replicate_percentage = 0.75;  // measured on 4 x B200: cold peer rows are expensive (profiles/r2_partition_diag_n4.txt)
 
   bool UseGPUCache() const { return cache_percentage > 0 && run_arch != kArch1; }  // run_config.h:81-83
   void LoadFromEnv();
