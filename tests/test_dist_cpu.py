@@ -73,3 +73,39 @@ def test_cache_striping_covers_every_slot_once():
                 assert 0 <= o < T and r < rows[o]
                 seen.add((o, r))
             assert len(seen) == num_cached
+
+
+def test_hybrid_layout_replicated_head_and_striped_tail():
+    """fgnn_cache_layout on the host side: slots below the replicated head belong to every GPU (owner None, row =
+    slot), the slots behind it are striped: every one of them has exactly one owner and a unique local row, and the
+    stripes' sizes are those the trainers allocate (Extractor ctor / partition.CacheShards)."""
+    sys.path.insert(0, os.path.join(ROOT, "fgnn-artifacts_b200"))
+    from fgnn_b200 import partition as P
+    for num_cached in (0, 5, 64, 1001):
+        for T in (1, 2, 3, 8):
+            for R in (0, 1, num_cached // 4, num_cached, num_cached + 7):
+                head = min(R, num_cached)
+                rows = [P.stripe_rows(num_cached - head, T, t) for t in range(T)]
+                assert sum(rows) == num_cached - head
+                seen = set()
+                for s in range(num_cached):
+                    o, r = P.slot_owner(s, T, head)
+                    if s < head:
+                        assert o is None and r == s
+                    else:
+                        assert 0 <= o < T and r < rows[o]
+                        seen.add((o, r))
+                assert len(seen) == num_cached - head
+
+
+def test_factored_split_follows_the_reference_placements():
+    """bench.py's S+T split of the factored legs (multi_gpu/common_config.py:182-185; 2 samplers + 6 trainers on 8)."""
+    sys.path.insert(0, ROOT)
+    import bench
+    assert bench.factored_split(1) == (1, 1, True)
+    assert bench.factored_split(2) == (1, 1, False)
+    assert bench.factored_split(4) == (1, 3, False)
+    assert bench.factored_split(8) == (2, 6, False)
+    for n in (2, 3, 4, 5, 6, 7, 8):
+        s, t, single = bench.factored_split(n)
+        assert s >= 1 and t >= 1 and s + t == n and not single
