@@ -814,13 +814,13 @@ def run_factored(args, wl, world, rank, path):
             sys.stderr.write("---- %s leg stderr (tail) ----\n%s\n" % (tag, err[-6000:]))     # for the run's log
             keep = [l for l in err.splitlines() if "Error" in l or "error" in l or "what():" in l or "File " in l][:16]
             return {"error": "%s leg failed: %s || %s" % (tag, " | ".join(keep)[:1500], err[-400:])}
-        f = one(["--no-train", "--num-epoch", "4"], "e2e_factored")
+        f = one(["--no-train", "--num-epoch", "4", "--timeout", "120"], "e2e_factored")
         e = one(["--num-epoch", "3", "--timeout", "120"], "epoch")
         ddp_error = None
         if "error" in e and T > 1:
             # the measured epoch must not depend on the gradient all-reduce coming up: retry without DDP and say so
             ddp_error = e["error"]
-            e = one(["--num-epoch", "3", "--no-ddp"], "epoch")
+            e = one(["--num-epoch", "3", "--no-ddp", "--timeout", "120"], "epoch")
         res = {}
         if "error" in f:
             res["e2e_factored"] = f

@@ -1371,6 +1371,14 @@ void Engine::PollRecvs(bool drain) {
 TaskPtr Engine::RecvTask(bool block) {
   Timer tr;
   uint64_t idx = 0;
+  // Never wait on the ring while a slot of ours is still unreleased: with several trainers the ticket we are about
+  // to take can map to that very slot (ticket t and t + num_slots), its sampler would wait for our release and we
+  // for its publication (seen as a hang of 2 samplers + 6 trainers on 8 x B200 in round 2).  The copies out of the
+  // previous slot were enqueued before the previous batch's gather, so this wait is a few tens of microseconds.
+  if (extractor_) {
+    CUDA_CALL(cudaSetDevice(extractor_->device()));
+    PollRecvs(true);
+  }
   auto ready_of = [this](uint64_t i) { return ring_->ready_of(i); };
   if (!RingBeginRead(&ring_->ctl, ready_of, &stop_, block, &idx)) return nullptr;
   char *slot = ring_->slot(idx);
