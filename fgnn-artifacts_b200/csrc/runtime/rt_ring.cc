@@ -48,7 +48,7 @@ extern "C" long fgnn_rt_ring_selftest(uint32_t num_slots, uint32_t slot_words, u
         const uint64_t seq = next_item.fetch_add(1);
         if (seq >= items) return;
         uint64_t ticket;
-        if (!RingBeginWrite(&ctl, ready_of, &stop, &ticket, unsafe_no_slot_wait == 0)) return;
+        if (!RingBeginWrite(&ctl, ready_of, &stop, &ticket, unsafe_no_slot_wait != 1)) return;
         Slot &s = slots[ticket % num_slots];
         if ((ticket % 3) == p % 3) delay(ticket * 17 + p + 1000);  // slow writers: records complete out of order
         for (uint32_t w = 0; w < slot_words; ++w) {  // a slow, word-by-word write like a DMA in flight
@@ -58,14 +58,28 @@ extern "C" long fgnn_rt_ring_selftest(uint32_t num_slots, uint32_t slot_words, u
         RingEndWrite(&ctl, &s.ready, ticket);
       }
     });
+  // mode 2 / 3: the engine's trainer since round 2 — the copies out of a slot are asynchronous, so the slot is
+  // released LATER than the record is taken: in mode 3 (what Engine::RecvTask does) before the next ticket is
+  // requested, in mode 2 (the bug it had) only after the next ticket has been obtained.
+  const bool deferred = unsafe_no_slot_wait == 2 || unsafe_no_slot_wait == 3;
+  const bool release_after_take = unsafe_no_slot_wait == 2;
   for (uint32_t c = 0; c < consumers; ++c)
     threads.emplace_back([&, c] {
+      bool have_pending = false;
+      uint64_t pending = 0;
+      auto release_pending = [&] {
+        if (!have_pending) return;
+        RingEndRead(&ctl, &slots[pending % num_slots].ready, pending);
+        have_pending = false;
+      };
       for (;;) {
-        if (consumed.load() >= items) return;
+        if (consumed.load() >= items) { release_pending(); return; }
         uint64_t ticket;
+        if (deferred && !release_after_take) release_pending();
         if (!RingBeginRead(&ctl, ready_of, &stop, /*block=*/false, &ticket)) {
           if (stop) return;
-          RingPause();
+          if (release_after_take) { delay(c + 7); release_pending(); }  // an idle trainer does get round to its poll
+          else RingPause();
           continue;
         }
         Slot &s = slots[ticket % num_slots];
@@ -75,7 +89,13 @@ extern "C" long fgnn_rt_ring_selftest(uint32_t num_slots, uint32_t slot_words, u
         for (uint32_t w = 0; w < slot_words; ++w) ok &= (s.words[w] == seq);
         if (!ok) damaged.fetch_add(1);
         else seen[seq].fetch_add(1);
-        RingEndRead(&ctl, &s.ready, ticket);
+        if (deferred) {
+          release_pending();  // mode 2 reaches this with the previous slot still held
+          pending = ticket;
+          have_pending = true;
+        } else {
+          RingEndRead(&ctl, &s.ready, ticket);
+        }
         consumed.fetch_add(1);
       }
     });

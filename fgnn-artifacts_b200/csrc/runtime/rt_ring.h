@@ -112,7 +112,10 @@ extern "C" int fgnn_rt_sanity_check_batch(uint8_t *epoch_map, size_t num_nodes, 
 // once and intact, a positive count of damaged / duplicated / missing records otherwise, -1 on timeout
 // (`timeout_ms`): the consumers or producers stopped making progress.  `unsafe_no_slot_wait` != 0 is the negative
 // control: producers rely on the fill-level semaphore alone — records get overwritten while a slow consumer still
-// holds them, and the sequence words go out of step (dead-lock).
+// holds them, and the sequence words go out of step (dead-lock).  2 and 3 model a consumer whose slot release is
+// deferred (asynchronous copies out of the slot, Engine::RecvTask): 3 releases the previous slot BEFORE asking for
+// the next ticket (the engine's order), 2 only after it got one — with more consumers than slots the ticket it
+// then waits for can map to the slot it still holds (second negative control: times out).
 extern "C" long fgnn_rt_ring_selftest(uint32_t num_slots, uint32_t slot_words, uint32_t producers,
                                       uint32_t consumers, uint64_t items, uint32_t max_delay_us,
                                       uint32_t timeout_ms, int unsafe_no_slot_wait);

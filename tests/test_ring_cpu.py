@@ -46,6 +46,34 @@ def test_negative_control_fill_level_alone_is_not_enough(selftest):
     assert any(o != 0 for o in outcomes), outcomes
 
 
+DEFERRED = [  # the arch5 shapes of the multi-GPU runs: slots = max_copying_jobs + 1 = 5
+    (5, 512, 2, 6, 3000, 100),     # 2 samplers + 6 trainers on 8 GPUs (hung in round 2 with release-after-take)
+    (5, 512, 1, 3, 2000, 100),     # 1 + 3 on 4 GPUs
+    (3, 512, 2, 6, 2000, 50),
+    (2, 64, 4, 8, 4000, 20),
+]
+
+
+@pytest.mark.parametrize("case", DEFERRED)
+def test_deferred_slot_release_in_the_engines_order(selftest, case):
+    """Engine::RecvTask releases a slot only when the copies out of it have completed, i.e. later than it takes the
+    record; it does so BEFORE requesting the next ticket (mode 3)."""
+    ns, words, P, C, items, delay = case
+    assert selftest(ns, words, P, C, items, delay, 60000, 3) == 0
+
+
+def test_negative_control_release_after_next_ticket_hangs(selftest):
+    """Mode 2 = the order the engine had when 2 samplers + 6 trainers hung on 8 GPUs: a trainer that still holds
+    slot (t mod N) takes ticket t + N and waits for its publication, which waits for that slot."""
+    outcomes = []
+    for attempt in range(8):                  # a race: each attempt hangs with high, not full, probability
+        outcomes.append(selftest(5, 512, 2, 6, 20000, 100, 5000, 2))
+        if outcomes[-1] == -1:
+            break
+    assert outcomes[-1] == -1, outcomes
+    assert selftest(5, 512, 2, 6, 20000, 100, 60000, 3) == 0      # same load, the engine's order
+
+
 def test_sanity_check_batch_flags_what_the_reference_asserts():
     """SAMGRAPH_SANITY_CHECK (cuda_shuffler.cc:144-151, cuda_sanity_check.cu:29-59): empty keys, out-of-range ids and
     a train node handed out twice within one epoch ("duplicate batch input")."""
