@@ -812,8 +812,12 @@ def run_factored(args, wl, world, rank, path):
                     return json.loads(line[len("FACTORED_JSON "):])
             err = r.stderr.strip()
             sys.stderr.write("---- %s leg stderr (tail) ----\n%s\n" % (tag, err[-6000:]))     # for the run's log
-            keep = [l for l in err.splitlines() if "Error" in l or "error" in l or "what():" in l or "File " in l][:16]
-            return {"error": "%s leg failed: %s || %s" % (tag, " | ".join(keep)[:1500], err[-400:])}
+            # one readable line for the JSON: the example's own verdict first ("timeout after ...", "a worker failed"),
+            # then exception / abort lines; the interleaved per-process stack dumps stay in the log above
+            lines = err.splitlines()
+            keep = [l.strip() for l in lines if l.startswith("train_graphsage_multi_gpu:")]
+            keep += [l.strip() for l in lines if ("Error" in l or "what():" in l or "CHECK" in l) and len(l) < 300][:6]
+            return {"error": "%s leg failed: %s" % (tag, " | ".join(dict.fromkeys(keep))[:1200] or err[-400:])}
         f = one(["--no-train", "--num-epoch", "4", "--timeout", "120"], "e2e_factored")
         e = one(["--num-epoch", "3", "--timeout", "120"], "epoch")
         ddp_error = None
