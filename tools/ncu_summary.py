@@ -87,5 +87,44 @@ def traffic(path, pattern="gather_bulk"):
                       "how": "ncu --set full --clock-control none, bench.py timed region (cold cache, serialised replay)"}))
 
 
+def stalls(path):
+    """Warp-state breakdown per kernel (smsp__average_warps_issue_stalled_*_per_issue_active: warps stalled in that
+    state per issued instruction) plus the DRAM sector figures: which latency the kernel sits on."""
+    out = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(out.splitlines()))
+    hdr = rows[0]
+    ki, gi = hdr.index("Kernel Name"), hdr.index("Grid Size")
+    pre, suf = "smsp__average_warps_issue_stalled_", "_per_issue_active.ratio"
+    cols = [(i, h[len(pre):-len(suf)]) for i, h in enumerate(hdr) if h.startswith(pre) and h.endswith(suf)]
+    extra = [("dram__sectors_read.sum", "dram_rd_sectors"), ("dram__sectors_write.sum", "dram_wr_sectors"),
+             ("gpu__time_duration.sum", "time"), ("smsp__issue_active.avg.pct_of_peak_sustained_active", "issue_active_pct"),
+             ("lts__t_sectors_op_atom.sum", "l2_atom_sectors"), ("lts__t_sectors_op_red.sum", "l2_red_sectors")]
+    print("# %s: warps stalled per issued instruction, by state (top 5), ncu --set full" % path)
+    seen = collections.OrderedDict()
+    for r in rows[2:]:
+        name = r[ki].split("(")[0].replace("void ", "").replace("fgnn::<unnamed>::", "")
+        key = (name, r[gi])
+        if key in seen:
+            continue
+        seen[key] = 1
+        vals = []
+        for i, st in cols:
+            try:
+                vals.append((float(r[i]), st))
+            except ValueError:
+                pass
+        vals.sort(reverse=True)
+        tot = sum(v for v, _ in vals) or 1.0
+        parts = ["%-30s grid=%-14s" % (name[:30], r[gi])]
+        parts.append(" ".join("%s=%.2f(%.0f%%)" % (st, v, 100 * v / tot) for v, st in vals[:5]))
+        for k, short in extra:
+            if k in hdr:
+                try:
+                    parts.append("%s=%.4g%s" % (short, float(r[hdr.index(k)]), rows[1][hdr.index(k)]))
+                except ValueError:
+                    pass
+        print("  ".join(parts))
+
+
 if __name__ == "__main__":
-    {"rep": rep, "list": launch_list, "traffic": traffic}[sys.argv[1]](*sys.argv[2:])
+    {"rep": rep, "list": launch_list, "traffic": traffic, "stalls": stalls}[sys.argv[1]](*sys.argv[2:])
