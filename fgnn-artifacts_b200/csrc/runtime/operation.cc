@@ -99,6 +99,14 @@ void samgraph_shutdown() { Engine::Get()->Shutdown(); }
 size_t samgraph_num_epoch() { return Engine::Get()->NumEpoch(); }
 size_t samgraph_steps_per_epoch() { return Engine::Get()->NumStep(); }
 size_t samgraph_num_local_step() { return Engine::Get()->NumLocalStep(); }
+// test hook (not part of the reference ABI): the cache ranking the loader produced — the policy's file, or the host
+// build of degree_hop / fake_optimal when the file is absent; nullptr before data_init or for GPU-built policies
+const uint32_t *fgnn_rt_dataset_ranking(size_t *num_nodes) {
+  const Dataset *ds = Engine::Get()->GetDataset();
+  if (!ds || !ds->ranking_nodes) return nullptr;
+  if (num_nodes) *num_nodes = ds->num_node;
+  return (const uint32_t *)ds->ranking_nodes->data;
+}
 size_t samgraph_num_class() { return Engine::Get()->GetDataset()->num_class; }
 size_t samgraph_feat_dim() { return Engine::Get()->GetDataset()->feat_dim; }
 

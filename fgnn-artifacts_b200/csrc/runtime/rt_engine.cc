@@ -1,5 +1,7 @@
 #include "rt_engine.h"
 
+#include "fgnn_dataset_tools.h"
+
 #include <sched.h>
 #include <sys/mman.h>
 #include <sys/stat.h>
@@ -911,11 +913,32 @@ void Engine::LoadDataset() {  // engine.cc:73-264
       default: FCHECK(false) << "cache policy " << rc.cache_policy << " is outside the hot-path scope";
     }
     // cache_by_degree / cache_by_random / cache_by_heuristic: when the offline tool's file is absent the ranking is computed on the
-    // sampler GPU at init (Engine::DoGpuRanking); the other file-based policies need their file
+    // sampler GPU at init (Engine::DoGpuRanking); degree_hop / fake_optimal are then built here with the host
+    // restatement of the reference's offline tools (fgnn_dataset_tools.h; no CUDA: this runs before the fork)
     const bool on_gpu_ok = rc.cache_policy == kCacheByDegree || rc.cache_policy == kCacheByRandom ||
                            rc.cache_policy == kCacheByHeuristic;
-    if (f && (FileExists(path + f) || !on_gpu_ok))
+    const bool on_host_ok = rc.cache_policy == kCacheByDegreeHop || rc.cache_policy == kCacheByFakeOptimal;
+    if (f && !FileExists(path + f) && on_host_ok) {
+      Timer tb;
+      auto store = std::make_shared<std::vector<uint32_t>>(ds->num_node);
+      auto rank = Tensor::View(store->data(), kI32, {ds->num_node}, Context(kCPU, 0), store, "dataset.ranking_nodes");
+      const auto *indptr = (const uint32_t *)ds->indptr->data, *indices = (const uint32_t *)ds->indices->data;
+      const auto *train = (const uint32_t *)ds->train_set->data;
+      const size_t n_train = ds->train_set->NumItems();
+      int rc_build;
+      if (rc.cache_policy == kCacheByDegreeHop) {
+        rc_build = fgnn_rt_rank_degree_hop(indptr, indices, ds->num_node, train, n_train, 2, (int)rc.omp_thread_num,
+                                           (uint32_t *)rank->data);
+      } else {  // the tool's constants: fanout {25, 10}, 48 threads (cache_by_fake_optimal.cc:170, options.cc:28)
+        rc_build = fgnn_rt_rank_fake_optimal(indptr, indices, ds->num_node, train, n_train, 25, 10, 48,
+                                             (int)rc.omp_thread_num, (uint32_t *)rank->data);
+      }
+      FCHECK_EQ(rc_build, 0) << "building " << f << " failed";
+      FLOG(Info) << f << " absent: ranking built on the host in " << tb.Passed() << " s";
+      ds->ranking_nodes = rank;
+    } else if (f && (FileExists(path + f) || !on_gpu_ok)) {
       ds->ranking_nodes = Tensor::FromMmap(path + f, kI32, {ds->num_node}, "dataset.ranking_nodes");
+    }
   }
   dataset_ = std::move(ds);
 }

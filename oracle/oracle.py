@@ -276,6 +276,75 @@ class Oracle:
                 added[v] = True
         return np.array(rank, np.uint32)
 
+    def rank_by_degree_hop(self, indptr, indices, train_set, hops=2):
+        """toolkit/cache/cache_by_degree_hop.cc:31-180: vertices within `hops` hops of the training set (hopNodes,
+        :31-82) are ranked first, by their out-degree inside the sub-graph that keeps only those vertices' adjacency
+        rows (gen_khop_graph :85-118, merged with bit 30 set :120-131); all others by whole-graph out-degree."""
+        indptr, indices = _u32(indptr), _u32(indices)
+        V = len(indptr) - 1
+        before = np.zeros(V, np.uint8)
+        before[_u32(train_set)] = 2
+        for _ in range(hops):
+            after = np.zeros(V, bool)
+            for v in np.nonzero(before == 2)[0]:
+                after[indices[indptr[v]:indptr[v + 1]]] = True
+            fresh = after & (before == 0)
+            before[before != 0] = 1
+            before[fresh] = 2
+        touched = before != 0
+        whole = np.bincount(indices, minlength=V).astype(np.uint32)
+        keep = np.repeat(touched, np.diff(indptr.astype(np.int64)))
+        sub = np.bincount(indices[keep], minlength=V).astype(np.uint32)
+        return self.presc_rank(np.where(touched, sub | np.uint32(0x40000000), whole).astype(np.uint32))
+
+    @staticmethod
+    def rank_by_fake_optimal(indptr, indices, train_set, fanout=(25, 10), order_threads=1):
+        """toolkit/cache/cache_by_fake_optimal.cc:61-183 with the tool's batch_size = 1 (:173): per training node,
+        hop1_miss[v] = prod over its edges to v of max(0, 1 - fanout[1]/deg(seed)); hop2_miss[w] = prod over the
+        edges h->w of the touched vertices h of (1 - (1 - hop1_miss[h]) * min(1, fanout[0]/deg(h))), the touched
+        vertices visited in TouchedNodeCtx::compact() order (buckets id % threads, :44-60); the seed itself is a
+        certain hit; expectation[v] += 1 - hop1_miss[v]*hop2_miss[v]; ranking = {expectation, id} descending.
+        Plain IEEE doubles in the tool's operation order, so the ranking is bit-exact against the tool."""
+        indptr, indices = _u32(indptr), _u32(indices)
+        V, T = len(indptr) - 1, int(order_threads)
+        exp = [0.0] * V
+        for t in (int(x) for x in _u32(train_set)):
+            buckets = [[] for _ in range(T)]
+            seen = set()
+
+            def touch(v):
+                if v not in seen:
+                    seen.add(v)
+                    buckets[v % T].append(v)
+            touch(t)
+            h1, h2 = {}, {}
+            row = [int(x) for x in indices[indptr[t]:indptr[t + 1]]]
+            if row:
+                miss = max(0.0, 1 - fanout[1] / float(len(row)))
+                for d in row:
+                    h1[d] = h1.get(d, 1.0) * miss
+                    touch(d)
+            h1[t] = 0.0
+            for h in [v for b in buckets for v in b]:
+                nb = [int(x) for x in indices[indptr[h]:indptr[h + 1]]]
+                if not nb:
+                    continue
+                b1_hit = 1 - h1.get(h, 1.0)
+                b2_hit = min(1.0, fanout[0] / float(len(nb)))
+                path_miss = 1 - b1_hit * b2_hit
+                for w in nb:
+                    h2[w] = h2.get(w, 1.0) * path_miss
+                    touch(w)
+            h2[t] = 0.0
+            for v in seen:
+                a, b = h1.get(v, 1.0), h2.get(v, 1.0)
+                if a == 1 and b == 1:
+                    continue
+                exp[v] += 1 - a * b
+        e = np.array(exp, np.float64)
+        order = np.lexsort((np.arange(V), e))[::-1]          # {expectation, id} descending (std::greater on pairs)
+        return order.astype(np.uint32), e
+
     # ---- block hand-off ----
     @staticmethod
     def coo_to_csc(row, col, num_dst):

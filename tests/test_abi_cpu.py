@@ -62,6 +62,16 @@ def test_runtime_library_exports_reference_abi(built):
     assert hasattr(lib, "PyInit_c_lib")
 
 
+def test_runtime_library_exports_the_dataset_tools(built):
+    src = open(os.path.join(ROOT, "include", "fgnn_dataset_tools.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    names = sorted(set(re.findall(r"\b(fgnn_rt_[a-z0-9_]+)\s*\(", src)))
+    assert names == ["fgnn_rt_rank_degree_hop", "fgnn_rt_rank_fake_optimal"]
+    lib = ctypes.CDLL(built[1])
+    for n in names:
+        assert hasattr(lib, n), "c_lib.so does not export %s" % n
+
+
 def test_python_binding_table_covers_the_header(built):
     from fgnn_b200 import kernels
     assert sorted(kernels.exported_symbols()) == declared("fgnn_kernels.h")

@@ -82,6 +82,42 @@ def test_data_init_loads_the_reference_dataset_format(tmp_path, dataset):
     assert out["label_sum"] == int(dataset["label"].sum())
 
 
+@pytest.mark.parametrize("policy", ["degree_hop", "fake_optimal"])
+def test_data_init_builds_the_offline_tool_rankings_when_their_file_is_absent(tmp_path, dataset, oracle, policy):
+    """engine.cc:233-244 only loads cache_by_degree_hop.bin / cache_by_fake_optimal.bin; without the file the loader
+    builds the ranking with the host restatement of the reference's offline tool (include/fgnn_dataset_tools.h),
+    and with the file it uses the file."""
+    body = """
+        import ctypes
+        sam.config(cfg)
+        sam.data_init()
+        lib = ctypes.CDLL(sam.c_lib.__file__)
+        lib.fgnn_rt_dataset_ranking.restype = ctypes.POINTER(ctypes.c_uint32)
+        n = ctypes.c_size_t(0)
+        p = lib.fgnn_rt_dataset_ranking(ctypes.byref(n))
+        out["rank"] = np.ctypeslib.as_array(p, shape=(n.value,)).tolist() if p else None
+        sam.shutdown()
+    """
+    import samgraph.common as sc
+    fname = os.path.join(dataset["path"], "cache_by_%s.bin" % policy)
+    assert not os.path.exists(fname)
+    cfg = config(dataset["path"], cache_policy=policy, _cache_policy=sc.cache_policies[policy])
+    r, out = run(tmp_path, cfg, body)
+    assert r.returncode == 0, r.stderr[-2000:]
+    if policy == "degree_hop":
+        want = oracle.rank_by_degree_hop(dataset["indptr"], dataset["indices"], dataset["train_set"])
+    else:
+        want, _ = oracle.rank_by_fake_optimal(dataset["indptr"], dataset["indices"], dataset["train_set"], order_threads=48)
+    assert out["rank"] == want.tolist()
+    try:                                            # a file, when present, wins
+        np.arange(len(want), dtype=np.uint32)[::-1].tofile(fname)
+        r, out = run(tmp_path, cfg, body)
+        assert r.returncode == 0, r.stderr[-2000:]
+        assert out["rank"] == list(range(len(want) - 1, -1, -1))
+    finally:
+        os.remove(fname)
+
+
 def test_profiler_log_api_round_trips(tmp_path, dataset):
     r, out = run(tmp_path, config(dataset["path"]), """
         sam.config(cfg)
