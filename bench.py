@@ -696,8 +696,8 @@ def run_ours(args):
 
     # ---- e2e through the host runtime (samgraph_* C-ABI) with host buffers ------------------
     if not is_headline(args):
-        args.no_cpu_baseline = True      # the reference has CPU code for the uniform samplers only
-        out["notes"]["legs"] = "non-headline sampler / fanout / workload: no CPU-baseline leg"
+        out["notes"]["legs"] = ("non-headline sampler / fanout / workload: the CPU baseline is the reference's own code for "
+                                "the uniform samplers and the oracle port for the others (see cpu_baseline.kind)")
     if not args.no_e2e:
         # release the device-resident leg's buffers first: the engine children build their own caches
         hp.cache = hp.feat_out = hp.cache_table = None
@@ -918,15 +918,16 @@ def run_e2e(args, wl, world, rank, dev, path):
 
 # ---------------------------------------------------------------------------
 def cpu_baseline(args, wl, steps, budget_s):
-    """Reference CPU path (oracle/_ref: CPUSampleKHop2 + CPUHashTable2 + CPUExtract, unmodified reference
-    translation units) on this host's cores, on a bounded sample of the same workload."""
+    """The CPU path on this host's cores, on a bounded sample of the same workload.
+    Uniform samplers (khop2 / khop0): the reference's OWN code (oracle/_ref: CPUSampleKHop2|0 + CPUHashTable2 +
+    CPUExtract, unmodified translation units), kind "reference".  The reference has no CPU code for the other
+    samplers (cpu_sampling_{khop1,weighted_khop,random_walk}.cc are empty stubs): those are timed on the
+    oracle's restatement of the CUDA algorithms (oracle/fgnn_oracle.c: OpenMP samplers, serial ordered unique),
+    kind "port"."""
     import numpy as np
-    from oracle.oracle import RefCPU, have_ref
-    if not have_ref():
-        return {"value": None, "unit": UNIT, "cores": 0, "kind": "reference", "sample": "oracle/_ref missing"}
+    fan = fanouts_of(args)
+    st = getattr(args, "sample_type", "khop2")
     cores = os.cpu_count() or 1
-    ref = RefCPU()
-    ref.set_threads(cores)
     t0 = time.time()
     indptr = wl["indptr"].cpu().numpy().view(np.uint32)
     indices = wl["indices"].cpu().numpy().view(np.uint32)          # CPUSampleKHop2 permutes rows in place
@@ -934,7 +935,54 @@ def cpu_baseline(args, wl, steps, budget_s):
     train = wl["train"].cpu().numpy().view(np.uint32)
     feat = wl["host_feat"].numpy()
     mask = np.uint32(feat.shape[0] - 1)
-    ht = ref.hashtable(2, wl["V"])
+    if st in ("khop2", "khop0"):
+        from oracle.oracle import RefCPU, have_ref
+        if not have_ref():
+            return {"value": None, "unit": UNIT, "cores": 0, "kind": "reference", "sample": "oracle/_ref missing"}
+        ref = RefCPU()
+        ref.set_threads(cores)
+        ht = ref.hashtable(2, wl["V"])
+        sample = ref.sample_khop2 if st == "khop2" else ref.sample_khop0
+        kind = "reference"
+        what = "CPUSample%s + CPUHashTable2 Populate/MapNodes/MapEdges + CPUExtract" % ("KHop2" if st == "khop2" else "KHop0")
+
+        def one_batch(seeds, key):
+            ht.reset()
+            ht.populate(seeds)
+            cur, e_step = seeds, 0
+            for i in range(len(fan) - 1, -1, -1):                  # cpu_loops.cc:55-191
+                s, d = sample(indptr, indices, cur, fan[i])
+                ht.populate(d)
+                cur = ht.map_nodes()
+                ht.map_edges(s, d)
+                e_step += len(s)
+            return cur, e_step
+        extract = ref.extract
+    else:
+        from oracle.oracle import Oracle, sample_batch_oracle
+        o = Oracle()
+        o.lib.fgo_set_threads(cores)
+        graph = dict(indptr=indptr, indices=indices)
+        if st.startswith("weighted"):
+            if "prob_table" in wl or "prefix_table" in wl:         # our arm: the tables the GPU builders made
+                for k_src, k_dst in (("prob_table", "prob_table"), ("alias_table", "alias_table"),
+                                     ("prefix_table", "prob_prefix_table")):
+                    if k_src in wl:
+                        a = wl[k_src].cpu().numpy()
+                        graph[k_dst] = a.view(np.uint32) if k_src == "alias_table" else a
+            else:                                                  # reference arm on a box without our kernels
+                w = np.random.default_rng(SEED_WEIGHTS).integers(1, 11, size=len(indices)).astype(np.float32)
+                if st == "weighted_khop_prefix":
+                    graph["prob_prefix_table"] = o.build_prefix_table(indptr, w)
+                else:
+                    graph["prob_table"], graph["alias_table"] = o.build_alias_table(indptr, indices, w)
+        kind = "port"
+        what = "oracle restatement of the CUDA %s sampler (OpenMP) + ordered unique / remap (serial) + row gather" % st
+
+        def one_batch(seeds, key):
+            b = sample_batch_oracle(o, graph, seeds, fan, st, 0x5EED, key, rw=RW if st == "random_walk" else None)
+            return b["input_nodes"], sum(l["num_edge"] for l in b["layers"])
+        extract = o.extract
     prep = time.time() - t0
     rng = np.random.default_rng(0)
     order = rng.permutation(len(train))
@@ -947,18 +995,9 @@ def cpu_baseline(args, wl, steps, budget_s):
         seeds = train[order[kk * BATCH:(kk + 1) * BATCH]]
         k += 1
         t1 = time.time()
-        ht.reset()
-        ht.populate(seeds)
-        cur = seeds
-        e_step = 0
-        for i in range(len(FANOUTS) - 1, -1, -1):                  # cpu_loops.cc:55-191
-            s, d = ref.sample_khop2(indptr, indices, cur, FANOUTS[i])
-            ht.populate(d)
-            cur = ht.map_nodes()
-            ht.map_edges(s, d)
-            e_step += len(s)
-        f = ref.extract(feat, cur & mask)                          # DoFeatureExtract (mock-masked ids)
-        lb = ref.extract(label, seeds)
+        cur, e_step = one_batch(seeds, k)
+        f = extract(feat, cur & mask)                              # DoFeatureExtract (mock-masked ids)
+        lb = extract(label, seeds)
         dt = time.time() - t1
         if k == 1:
             continue                                               # warm-up step
@@ -968,10 +1007,9 @@ def cpu_baseline(args, wl, steps, budget_s):
         spent += dt
         if steps is None and spent > budget_s:
             break
-    return {"value": edges / spent if spent else None, "unit": UNIT, "cores": cores, "kind": "reference",
-            "sample": "%d mini-batches (batch %d, fanout %s) of the same graph: CPUSampleKHop2 + CPUHashTable2 "
-                      "Populate/MapNodes/MapEdges + CPUExtract (feature rows masked to the 2^k-row host table), "
-                      "%d OpenMP threads; %.1f s" % (done, BATCH, FANOUTS, cores, spent),
+    return {"value": edges / spent if spent else None, "unit": UNIT, "cores": cores, "kind": kind,
+            "sample": "%d mini-batches (batch %d, %s fanout %s) of the same graph: %s (feature rows masked to the "
+                      "2^k-row host table), %d OpenMP threads; %.1f s" % (done, BATCH, st, fan, what, cores, spent),
             "steps": done, "ms_per_step": spent / max(1, done) * 1e3,
             "extract_rows_per_step": n_in / max(1, done), "prep_s": prep}
 
@@ -992,8 +1030,8 @@ def run_reference(args):
            "ms_per_step": cb["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
            "dtype": DTYPE, "data": "synthetic",
            "config": shared_config(args, wl["V"], wl["E"], wl["D"], int(wl["host_feat"].shape[0])),
-           "notes": {"reference_path": "CPUSampleKHop2 + CPUHashTable2 + CPUExtract on the host cores: every feature row "
-                                       "is read from host memory (no GPU, no cache)"},
+           "notes": {"reference_path": "the CPU path on the host cores (cpu_baseline.kind / .sample say which code): every "
+                                       "feature row is read from host memory (no GPU, no cache)"},
            "cpu_baseline": cb,
            "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(out))

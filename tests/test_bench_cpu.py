@@ -33,6 +33,27 @@ def test_reference_arm_prints_the_contract_line(ref):
     assert out["config"]["workload"] == bench.workload_name(A)      # same workload name as our arm's line
 
 
+@pytest.mark.parametrize("sample_type,fanout", [("random_walk", None), ("weighted_khop", "10,5"), ("khop0", "5,10,15")])
+def test_reference_arm_other_samplers(ref, sample_type, fanout):
+    """Configs #3 / #5 (PinSAGE random walk, weighted k-hop): the reference has no CPU code for them (empty stubs,
+    SURVEY §8c), so the arm times the oracle port and says so (kind "port"); khop0 with another fanout list is the
+    reference's own code again."""
+    if ref is None:
+        pytest.skip("oracle/_ref not built (needs /root/reference)")
+    cmd = [sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--workload", "ci-64k", "--steps", "2",
+           "--warmup", "1", "--empty-feat", "14", "--sample-type", sample_type]
+    if fanout:
+        cmd += ["--fanout", fanout]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600,
+                       env=dict(os.environ, CUDA_VISIBLE_DEVICES="", OMP_NUM_THREADS="4"))
+    assert r.returncode == 0, r.stderr[-2000:]
+    out = json.loads([x for x in r.stdout.splitlines() if x.startswith("{")][-1])
+    cb = out["cpu_baseline"]
+    assert out["impl"] == "reference" and out["value"] > 0 and cb["value"] == out["value"] and cb["steps"] == 2
+    assert cb["kind"] == ("reference" if sample_type == "khop0" else "port")
+    assert sample_type in cb["sample"] and out["config"]["sample_type"] == sample_type
+
+
 def test_rank_nonzero_of_reference_arm_is_silent():
     env = dict(os.environ, CUDA_VISIBLE_DEVICES="", RANK="1", WORLD_SIZE="2", LOCAL_RANK="1")
     r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2"],
