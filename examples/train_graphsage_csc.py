@@ -9,8 +9,9 @@ for boxes where it is not.
       --cache-percentage 0.25 --num-epoch 3 [--pipeline]
   PYTHONPATH=fgnn-artifacts_b200 python examples/train_graphsage_csc.py --synthetic ci-1m      # generated dataset
 
-STATUS: the model below is unit-tested on CPU (tests/test_example_model_cpu.py); the full script had no GPU run yet
-(written after round 1's GPU budget was spent).
+STATUS: the model below is unit-tested on CPU (tests/test_example_model_cpu.py) and trains on B200s as the consumer of
+examples/train_graphsage_multi_gpu.py (bench.py's measured-epoch leg, tests/test_runtime_gpu.py); the single-process
+main() of THIS file has not been run on a GPU.
 """
 import argparse
 import os
