@@ -818,13 +818,17 @@ def run_factored(args, wl, world, rank, path):
             keep = [l.strip() for l in lines if l.startswith("train_graphsage_multi_gpu:")]
             keep += [l.strip() for l in lines if ("Error" in l or "what():" in l or "CHECK" in l) and len(l) < 300][:6]
             return {"error": "%s leg failed: %s" % (tag, " | ".join(dict.fromkeys(keep))[:1200] or err[-400:])}
+        # the consumer of the epoch leg is the reference's model for the configuration: GraphSAGE (headline, weighted),
+        # GCN for the three-layer k-hop config (#4), PinSAGE on the random-walk blocks (#3)
+        model = "pinsage" if args.sample_type == "random_walk" else ("gcn" if len(fanouts_of(args)) == 3 else "graphsage")
+        margs = [] if model == "graphsage" else ["--model", model]
         f = one(["--no-train", "--num-epoch", "4", "--timeout", "120"], "e2e_factored")
-        e = one(["--num-epoch", "3", "--timeout", "120"], "epoch")
+        e = one(["--num-epoch", "3", "--timeout", "120"] + margs, "epoch")
         ddp_error = None
         if "error" in e and T > 1:
             # the measured epoch must not depend on the gradient all-reduce coming up: retry without DDP and say so
             ddp_error = e["error"]
-            e = one(["--num-epoch", "3", "--no-ddp", "--timeout", "120"], "epoch")
+            e = one(["--num-epoch", "3", "--no-ddp", "--timeout", "120"] + margs, "epoch")
         res = {}
         if "error" in f:
             res["e2e_factored"] = f
@@ -857,8 +861,10 @@ def run_factored(args, wl, world, rank, path):
                 "kLogEpochTrainTime_s": sum(x["train_s"] for x in timed) / k,
                 "epoch_wall_s": [round(x["wall_s"], 5) for x in e["epochs"]], "loss": e["loss"],
                 "ddp": ddp_error is None and T > 1, "ddp_error": ddp_error,
-                "model": "GraphSAGE %d layers, hidden 256, mean aggregation as CSR SpMM on the CSC hand-off, Adam, "
-                         "DDP (NCCL) between the trainers; examples/train_graphsage_multi_gpu.py --pipeline" % len(fanouts_of(args)),
+                "model": "%s %d layers, hidden 256, aggregation as CSR SpMM on the CSC hand-off, Adam, "
+                         "DDP (NCCL) between the trainers; examples/train_graphsage_multi_gpu.py --pipeline"
+                         % ({"graphsage": "GraphSAGE (mean)", "gcn": "GCN (GraphConv norm=both)",
+                             "pinsage": "PinSAGE (WeightedSAGEConv)"}[model], len(fanouts_of(args))),
                 "note": "measured, not extrapolated: whole epochs of the papers100M-shaped train set through samgraph.torch "
                         "with the model as consumer; max over trainers; first epoch dropped like the scripts do"}
     if world > 1:

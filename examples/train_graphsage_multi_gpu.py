@@ -10,6 +10,7 @@ should start from 0"), samplers on cuda:T..T+S-1 (--single-gpu: everything on cu
   PYTHONPATH=fgnn-artifacts_b200 python examples/train_graphsage_multi_gpu.py --dataset-path /data/papers100M \\
       --num-sample-worker 2 --num-train-worker 6 --cache-percentage 0.25 --num-epoch 4 --pipeline
 
+--model gcn | pinsage selects the reference's other two model families (examples/gnn_models_csc.py).
 --no-train skips the model (the trainers only take the batches and read the labels back): the path the bench's
 `e2e_factored` leg times.  --json prints one machine-readable line with per-epoch times (bench.py extra.epoch).
 """
@@ -40,6 +41,9 @@ def parse(argv=None):
     ap.add_argument("--batch-size", type=int, default=8000)
     ap.add_argument("--num-epoch", type=int, default=4)
     ap.add_argument("--num-hidden", type=int, default=256)
+    ap.add_argument("--model", default="graphsage", choices=["graphsage", "gcn", "pinsage"],
+                    help="trainer-side consumer: the reference's multi_gpu/train_graphsage.py, train_gcn.py or "
+                         "train_pinsage.py model (examples/gnn_models_csc.py); pinsage needs --sample-type random_walk")
     ap.add_argument("--lr", type=float, default=0.003)
     ap.add_argument("--dropout", type=float, default=0.5)
     ap.add_argument("--cache-policy", default="pre_sample")
@@ -126,7 +130,14 @@ def run_train(worker_id, a, ctx, barrier, outdir):
                 os.environ.pop(k)          # not a torchrun worker even when launched from one (agent store!)
             torch.distributed.init_process_group(backend="nccl", init_method="tcp://127.0.0.1:%d" % a.master_port,
                                                  world_size=T, rank=worker_id, device_id=dev)
-        model = SAGE(sam.feat_dim(), a.num_hidden, sam.num_class(), L, a.dropout).to(dev)
+        if a.model == "graphsage":
+            model = SAGE(sam.feat_dim(), a.num_hidden, sam.num_class(), L, a.dropout).to(dev)
+        else:
+            from gnn_models_csc import build_model, csc_blocks_weighted
+            assert a.model != "pinsage" or a.sample_type == "random_walk", "pinsage consumes the random-walk edge weights"
+            model = build_model(a.model, sam.feat_dim(), a.num_hidden, sam.num_class(), L, a.dropout).to(dev)
+            if a.model == "pinsage":
+                csc_blocks = csc_blocks_weighted
         if T > 1 and not a.no_ddp:
             model = torch.nn.parallel.DistributedDataParallel(model, device_ids=[dev], output_device=dev)
         loss_fn = nn.CrossEntropyLoss().to(dev)
