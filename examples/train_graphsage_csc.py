@@ -75,6 +75,8 @@ def parse():
     ap.add_argument("--batch-size", type=int, default=8000)
     ap.add_argument("--num-epoch", type=int, default=3)
     ap.add_argument("--num-hidden", type=int, default=256)
+    ap.add_argument("--model", default="graphsage", choices=["graphsage", "gcn", "pinsage"],
+                    help="gcn / pinsage: the reference's train_gcn.py / train_pinsage.py models (examples/gnn_models_csc.py)")
     ap.add_argument("--lr", type=float, default=0.003)
     ap.add_argument("--dropout", type=float, default=0.5)
     ap.add_argument("--cache-policy", default="pre_sample")
@@ -103,12 +105,25 @@ def main():
            "max_sampling_jobs": 10, "max_copying_jobs": 2, "omp_thread_num": os.cpu_count() or 1,
            "sampler_ctx": a.device, "trainer_ctx": a.device, "fanout": a.fanout, "num_fanout": len(a.fanout),
            "num_layer": len(a.fanout), "presample_epoch": 1}
+    if a.sample_type == "random_walk":         # train_pinsage.py:122-126
+        for k in ("fanout", "num_fanout"):
+            cfg.pop(k)
+        cfg.update(random_walk_length=3, random_walk_restart_prob=0.5, num_random_walk=4, num_neighbor=5, num_layer=3)
     sam.config(cfg)
     sam.init()
     dev = torch.device(a.device)
     torch.cuda.set_device(dev)
-    L = len(a.fanout)
-    model = SAGE(sam.feat_dim(), a.num_hidden, sam.num_class(), L, a.dropout).to(dev)
+    L = 3 if a.sample_type == "random_walk" else len(a.fanout)
+    get_blocks = csc_blocks
+    if a.model == "graphsage":
+        model = SAGE(sam.feat_dim(), a.num_hidden, sam.num_class(), L, a.dropout).to(dev)
+    else:
+        sys.path.insert(0, here)
+        from gnn_models_csc import build_model, csc_blocks_weighted
+        assert a.model != "pinsage" or a.sample_type == "random_walk", "pinsage consumes the random-walk edge weights"
+        model = build_model(a.model, sam.feat_dim(), a.num_hidden, sam.num_class(), L, a.dropout).to(dev)
+        if a.model == "pinsage":
+            get_blocks = csc_blocks_weighted
     loss_fn = nn.CrossEntropyLoss()
     opt = torch.optim.Adam(model.parameters(), lr=a.lr)
     num_epoch, num_step = sam.num_epoch(), sam.steps_per_epoch()
@@ -124,7 +139,7 @@ def main():
                 sam.sample_once()
             batch_key = sam.get_next_batch()
             t1 = time.time()
-            blocks, feat, label = csc_blocks(sam, batch_key, L)
+            blocks, feat, label = get_blocks(sam, batch_key, L)
             t2 = time.time()
             loss = loss_fn(model(blocks, feat), label)
             opt.zero_grad()
